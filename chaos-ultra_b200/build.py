@@ -1,0 +1,103 @@
+"""Build recipes: the C-ABI host library and one sm_100a cubin per fractal module.
+
+Role in the reference: src/main/cuda/compile.sh:10-15 / compile_all.sh (one PTX per fractal,
+``-arch=sm_30``) plus Maven for the host.  Here: ``nvcc -cubin`` for sm_100a only, ``g++`` for
+the driver-API host library.  Everything is built in-tree so the artefacts travel with the
+repository snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+KERNELS_DIR = PKG_DIR / "cudaKernels"
+LIB_DIR = PKG_DIR / "lib"
+LIB_PATH = LIB_DIR / "libchaos_ultra.so"
+
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; the fractal modules cannot be built")
+    return exe
+
+
+def _cuda_include() -> str:
+    return str(Path(_nvcc()).resolve().parent.parent / "include")
+
+
+def _newer(target: Path, sources) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(Path(s).stat().st_mtime <= t for s in sources)
+
+
+def _run(cmd, log=None):
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if log is not None:
+        Path(log).write_text(res.stdout + res.stderr)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("build step failed: " + " ".join(map(str, cmd)))
+    return res.stdout + res.stderr
+
+
+def module_sources():
+    return sorted((CSRC / "fractals").glob("*.cu"))
+
+
+def build_module(src: Path, force: bool = False) -> Path:
+    """fractals/<name>.cu (+ render_generic.cuh) -> cudaKernels/<name>.cubin"""
+    KERNELS_DIR.mkdir(exist_ok=True)
+    out = KERNELS_DIR / (src.stem + ".cubin")
+    deps = [src] + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [Path(__file__)]
+    if not force and _newer(out, deps):
+        return out
+    cmd = [_nvcc(), "-cubin", *ARCH_FLAGS, *NVCC_FLAGS, "-I", str(CSRC), str(src), "-o", str(out)]
+    _run(cmd, log=KERNELS_DIR / (src.stem + ".ptxas.log"))
+    return out
+
+
+def build_library(force: bool = False) -> Path:
+    LIB_DIR.mkdir(exist_ok=True)
+    srcs = [CSRC / "chaos_abi.cpp"]
+    deps = srcs + sorted(CSRC.glob("*.h")) + [PKG_DIR.parent / "include" / "chaos_ultra.h", Path(__file__)]
+    if not force and _newer(LIB_PATH, deps):
+        return LIB_PATH
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-fvisibility=hidden",
+           "-I", _cuda_include(), *map(str, srcs), "-o", str(LIB_PATH), "-ldl", "-lm"]
+    _run(cmd)
+    return LIB_PATH
+
+
+def build_bench_kernels(force: bool = False) -> Path:
+    """bench_kernels/peak.cu -> bench_kernels/peak.cubin (measurement only: FP64/FP32 FMA peak)"""
+    src = PKG_DIR.parent / "bench_kernels" / "peak.cu"
+    out = src.with_suffix(".cubin")
+    if not force and _newer(out, [src]):
+        return out
+    _run([_nvcc(), "-cubin", *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", str(src), "-o", str(out)])
+    return out
+
+
+def build_all(force: bool = False):
+    lib = build_library(force)
+    mods = [build_module(s, force) for s in module_sources()]
+    build_bench_kernels(force)
+    return lib, mods
+
+
+if __name__ == "__main__":
+    lib, mods = build_all(force="--force" in sys.argv)
+    print(lib)
+    for m in mods:
+        print(m)

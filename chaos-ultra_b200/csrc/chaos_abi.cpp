@@ -1,0 +1,839 @@
+/*
+ * chaos_abi.cpp -- host half of the render backend behind include/chaos_ultra.h.
+ *
+ * Re-implements, on the CUDA driver API and without any Java/JCuda/GL dependency, the host
+ * logic of the reference backend (paths under
+ * /root/reference/src/main/java/cz/cuni/mff/cgg/teichmaa/chaosultra/cudarenderer/):
+ *   CudaFractalRendererProvider.java:14-91   registry of modules, one active renderer
+ *   FractalRenderingModule.java:31-280       module = one file found by name; constants by name
+ *   modules/Module*.java                     per-fractal defaults and custom-parameter parsing
+ *   CudaFractalRenderer.java:32-430          state machine, quality/fast frame logic, precision rule
+ *   DeviceMemoryDoubleBuffer2D.java:17-152   two pitched record buffers, swap, dirty flag
+ *   RenderingKernel.java:68-72,124-146       argument validation, float/double limit tests
+ * What is new: modules are sm_100a cubins launched as persistent grids sized from the SM count,
+ * the composed frame goes to pinned host memory (or stays on the device) instead of a GL
+ * texture, every frame is timed with CUDA events, and a renderer can own a row-band partition
+ * of the frame for multi-GPU rendering.
+ *
+ * There is deliberately no CPU fallback: without a driver, a device or the module file every
+ * entry point fails with a message.
+ */
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/chaos_ultra.h"
+#include "chaos_device.h"
+#include "cuda_driver.h"
+
+/* ------------------------------------------------------------------------------------------
+ * errors
+ * ---------------------------------------------------------------------------------------- */
+static thread_local char g_last_error[1024] = "";
+
+static chaos_status fail(chaos_status st, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof g_last_error, fmt, ap);
+    va_end(ap);
+    return st;
+}
+
+extern "C" const char *chaos_last_error(void) { return g_last_error; }
+extern "C" uint32_t chaos_abi_version(void) { return CHAOS_ABI_VERSION; }
+
+/* ------------------------------------------------------------------------------------------
+ * driver binding
+ * ---------------------------------------------------------------------------------------- */
+#define CHAOS_STR2(x) #x
+#define CHAOS_STR(x) CHAOS_STR2(x)
+
+const chaos_cuda_driver *chaos_cuda_driver_get(const char **err)
+{
+    static chaos_cuda_driver drv;
+    static bool tried = false, ok = false;
+    static std::string error;
+    if (!tried) {
+        tried = true;
+        drv.handle = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!drv.handle) drv.handle = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!drv.handle) {
+            error = std::string("Error while loading the Cuda native library. Do you have CUDA installed? (") + dlerror() + ")";
+        } else {
+            ok = true;
+            /* cuda.h maps e.g. cuMemAlloc -> cuMemAlloc_v2; stringify after expansion */
+#define X(name)                                                                    \
+    drv.p_##name = (decltype(&name))dlsym(drv.handle, CHAOS_STR(name));            \
+    if (!drv.p_##name) { ok = false; error = std::string("libcuda lacks ") + CHAOS_STR(name); }
+            CHAOS_CU_FUNCS(X)
+#undef X
+        }
+    }
+    if (!ok) {
+        if (err) *err = error.c_str();
+        return nullptr;
+    }
+    return &drv;
+}
+
+static const chaos_cuda_driver *D = nullptr;
+
+static const char *cu_err_name(CUresult r)
+{
+    const char *s = nullptr;
+    if (D && D->p_cuGetErrorName(r, &s) == CUDA_SUCCESS && s) return s;
+    return "CUDA_ERROR_UNKNOWN";
+}
+
+#define CU_TRY(call, st)                                                                     \
+    do {                                                                                     \
+        CUresult _r = D->p_##call;                                                           \
+        if (_r != CUDA_SUCCESS) return fail(st, "%s failed: %s", #call, cu_err_name(_r));    \
+    } while (0)
+
+/* ------------------------------------------------------------------------------------------
+ * module registry (CudaFractalRendererProvider.java:19-31 + modules/*.java)
+ * ---------------------------------------------------------------------------------------- */
+struct chaos_renderer;
+
+struct module_desc {
+    const char *fractal_name;                      /* display name, the key of getRenderer() */
+    const char *file_stem;                         /* <kernels_dir>/<file_stem>.cubin */
+    chaos_status (*on_initialize)(chaos_renderer *);                  /* Module*.initialize() extras */
+    chaos_status (*set_custom_params)(chaos_renderer *, const char *);
+    void (*supply_defaults)(chaos_defaults *);
+};
+
+static chaos_status write_constant(chaos_renderer *r, const char *symbol, const void *data, size_t bytes, const char *what);
+
+/* FractalRenderingModule.parseParamsAsDoubles :233-245: split on [,;], Double.parseDouble (trims) */
+static bool parse_doubles(const char *text, std::vector<double> &out)
+{
+    std::string s(text ? text : "");
+    size_t pos = 0;
+    while (pos <= s.size()) {
+        size_t e = s.find_first_of(",;", pos);
+        if (e == std::string::npos) e = s.size();
+        std::string tok = s.substr(pos, e - pos);
+        size_t a = tok.find_first_not_of(" \t\r\n"), b = tok.find_last_not_of(" \t\r\n");
+        if (a == std::string::npos) return false;      /* NumberFormatException: empty String */
+        tok = tok.substr(a, b - a + 1);
+        char *end = nullptr;
+        double v = strtod(tok.c_str(), &end);
+        if (end == tok.c_str() || *end != '\0') return false;
+        out.push_back(v);
+        pos = e + 1;
+        if (e == s.size()) break;
+    }
+    return !out.empty();
+}
+
+static void defaults_base(chaos_defaults *d) { d->custom_params[0] = '\0'; }
+
+/* modules/ModuleMandelbrot.java:9-25 */
+static void defaults_mandelbrot(chaos_defaults *d)
+{
+    defaults_base(d);
+    d->has_segment = 1; d->center_x = -0.5; d->center_y = 0; d->zoom = 2;
+    d->has_max_iterations = 1; d->max_iterations = 1600;
+    d->has_max_super_sampling = 1; d->max_super_sampling = 5;
+}
+static chaos_status custom_none(chaos_renderer *, const char *) { return CHAOS_OK; }
+
+/* modules/ModuleJulia.java:9-49 */
+static chaos_status julia_set_c(chaos_renderer *r, double x, double y)
+{
+    double c[2] = {x, y};
+    return write_constant(r, "julia_c", c, sizeof c, "PointDouble");
+}
+static chaos_status julia_on_initialize(chaos_renderer *r) { return julia_set_c(r, 0, 0); }
+static chaos_status julia_custom(chaos_renderer *r, const char *text)
+{
+    std::vector<double> v;
+    if (!parse_doubles(text, v)) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "NumberFormatException: For input string: \"%s\"", text ? text : "");
+    if (v.size() < 2) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "ArrayIndexOutOfBoundsException: julia expects \"x;y\" but got \"%s\"", text);
+    return julia_set_c(r, v[0], v[1]);
+}
+static void defaults_julia(chaos_defaults *d)
+{
+    defaults_base(d);
+    d->has_max_iterations = 1; d->max_iterations = 900;
+    snprintf(d->custom_params, sizeof d->custom_params, "-0.4;0.6");
+}
+
+/* modules/ModuleTest.java:9-23 */
+static chaos_status test_custom(chaos_renderer *r, const char *text)
+{
+    char *end = nullptr;
+    long v = strtol(text ? text : "", &end, 10);
+    if (!text || end == text || *end != '\0') return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "NumberFormatException: For input string: \"%s\"", text ? text : "");
+    int iv = (int)v;
+    return write_constant(r, "amplifier", &iv, sizeof iv, "double");
+}
+static void defaults_test(chaos_defaults *d)
+{
+    defaults_base(d);
+    snprintf(d->custom_params, sizeof d->custom_params, "10");
+}
+static void defaults_plain(chaos_defaults *d) { defaults_base(d); }
+
+/* the 7 names the reference registers (CudaFractalRendererProvider.java:21-27); a module whose
+ * file is missing fails at chaos_open() with the path, like cuModuleLoad does there */
+static const module_desc g_modules[] = {
+    {"julia", "julia", julia_on_initialize, julia_custom, defaults_julia},
+    {"mandelbrot", "mandelbrot", nullptr, custom_none, defaults_mandelbrot},
+    {"newton wired", "newton_wired", nullptr, custom_none, defaults_plain},
+    {"newton generic", "newton_generic", nullptr, custom_none, defaults_plain},
+    {"newton colored by iterations", "newton_iterations", nullptr, custom_none, defaults_plain},
+    {"test", "test", nullptr, test_custom, defaults_test},
+    {"goc", "goc", nullptr, custom_none, defaults_plain},
+};
+static const uint32_t g_n_modules = sizeof g_modules / sizeof g_modules[0];
+
+/* ------------------------------------------------------------------------------------------
+ * objects
+ * ---------------------------------------------------------------------------------------- */
+struct chaos_provider {
+    std::string kernels_dir;
+    int device = 0;
+    CUdevice cu_device = 0;
+    CUcontext ctx = nullptr;
+    int sm_count = 0;
+    chaos_renderer *active = nullptr;
+};
+
+struct ctx_guard {
+    bool pushed = false;
+    explicit ctx_guard(chaos_provider *p) { if (p && p->ctx && D->p_cuCtxPushCurrent(p->ctx) == CUDA_SUCCESS) pushed = true; }
+    ~ctx_guard() { if (pushed) { CUcontext c; D->p_cuCtxPopCurrent(&c); } }
+};
+
+struct record_buffer {
+    CUdeviceptr ptr = 0;
+    size_t pitch = 0;
+};
+
+struct chaos_renderer {
+    chaos_provider *provider = nullptr;
+    const module_desc *desc = nullptr;
+    /* module (FractalRenderingModule) */
+    CUmodule module = nullptr;
+    CUfunction k_main_f = nullptr, k_main_d = nullptr, k_adv_f = nullptr, k_adv_d = nullptr;
+    CUfunction k_compose = nullptr, k_undersampled = nullptr, k_debug = nullptr;
+    int blocks_main_f = 0, blocks_main_d = 0, blocks_adv_f = 0, blocks_adv_d = 0;
+    /* renderer state (CudaFractalRenderer) */
+    chaos_state state = CHAOS_STATE_NOT_INITIALIZED;
+    uint32_t width = 0, height = 0;
+    chaos_output_mode mode = CHAOS_OUTPUT_HOST;
+    record_buffer buf[2];          /* DeviceMemoryDoubleBuffer2D: [0] primary, [1] secondary */
+    bool buffers_switched = false;
+    bool primary_dirty = true;
+    bool have_last = false;        /* lastRendering != null */
+    chaos_params last;             /* lastRendering = model.copy() */
+    CUdeviceptr palette = 0;
+    uint32_t palette_len = 0;
+    CUdeviceptr rgba_dev = 0;      /* DEVICE mode frame, or device alias of rgba_host */
+    uint32_t *rgba_host = nullptr; /* HOST mode: pinned + mapped */
+    CUdeviceptr counters = 0;
+    chaos_counters *counters_host = nullptr; /* pinned staging for the read-back */
+    CUstream stream = nullptr;
+    CUevent ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t part_index = 0, part_count = 1, band_rows = 64;
+    chaos_stats stats;
+    uint32_t engine = 0;
+};
+
+static chaos_status check_renderer(const chaos_renderer *r)
+{
+    if (!r) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "renderer handle is NULL");
+    if (!r->module) return fail(CHAOS_ERR_ILLEGAL_STATE, "Module has not been initialized or has been closed.");
+    return CHAOS_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * provider
+ * ---------------------------------------------------------------------------------------- */
+extern "C" chaos_status chaos_provider_create(const char *kernels_dir, int device, chaos_provider **out)
+{
+    if (!out) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!kernels_dir) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "kernels_dir is NULL (the reference falls back to 'cudaKernels', FractalRenderingModule.java:51-55; pass it explicitly)");
+    const char *err = nullptr;
+    D = chaos_cuda_driver_get(&err);
+    if (!D) return fail(CHAOS_ERR_CUDA_INIT, "%s", err ? err : "cannot load libcuda");
+    CU_TRY(cuInit(0), CHAOS_ERR_CUDA_INIT);
+    int n = 0;
+    CU_TRY(cuDeviceGetCount(&n), CHAOS_ERR_CUDA_INIT);
+    if (n <= 0) return fail(CHAOS_ERR_CUDA_INIT, "CUDA_ERROR_NO_DEVICE: no CUDA device is visible; this backend has no CPU fallback");
+    if (device < 0 || device >= n) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "device %d out of range (0..%d)", device, n - 1);
+    chaos_provider *p = new chaos_provider();
+    p->kernels_dir = kernels_dir;
+    p->device = device;
+    CUresult r = D->p_cuDeviceGet(&p->cu_device, device);
+    if (r == CUDA_SUCCESS) r = D->p_cuDevicePrimaryCtxRetain(&p->ctx, p->cu_device);
+    if (r != CUDA_SUCCESS) {
+        delete p;
+        return fail(CHAOS_ERR_CUDA_INIT, "cannot create a context on device %d: %s", device, cu_err_name(r));
+    }
+    D->p_cuDeviceGetAttribute(&p->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, p->cu_device);
+    int major = 0, minor = 0;
+    D->p_cuDeviceGetAttribute(&major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, p->cu_device);
+    D->p_cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, p->cu_device);
+    if (major != 10) {
+        D->p_cuDevicePrimaryCtxRelease(p->cu_device);
+        delete p;
+        return fail(CHAOS_ERR_CUDA_INIT, "device %d is sm_%d%d; the modules are built for sm_100a (B200) only", device, major, minor);
+    }
+    *out = p;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_close(chaos_renderer *r);
+
+extern "C" chaos_status chaos_provider_destroy(chaos_provider *p)
+{
+    if (!p) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "provider handle is NULL");
+    if (p->active) { chaos_close(p->active); }
+    if (p->ctx) D->p_cuDevicePrimaryCtxRelease(p->cu_device);
+    delete p;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_list_fractals(chaos_provider *p, const char **names, uint32_t capacity, uint32_t *count)
+{
+    if (!p) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "provider handle is NULL");
+    if (count) *count = g_n_modules;
+    if (names) for (uint32_t i = 0; i < g_n_modules && i < capacity; ++i) names[i] = g_modules[i].fractal_name;
+    return CHAOS_OK;
+}
+
+static chaos_status get_function(chaos_renderer *r, const char *name, CUfunction *fn)
+{
+    CUresult e = D->p_cuModuleGetFunction(fn, r->module, name);
+    if (e == CUDA_ERROR_NOT_FOUND)
+        return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Function %s not found in module %s (CudaKernel.java:36-38)", name, r->desc->file_stem);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA_INIT, "cuModuleGetFunction(%s) failed: %s", name, cu_err_name(e));
+    return CHAOS_OK;
+}
+
+static void unload_module(chaos_renderer *r)
+{
+    if (r->module) { D->p_cuModuleUnload(r->module); r->module = nullptr; }
+}
+
+static int persistent_blocks(chaos_renderer *r, CUfunction fn, int threads)
+{
+    int per_sm = 0;
+    if (D->p_cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != CUDA_SUCCESS || per_sm < 1) per_sm = 1;
+    return per_sm * r->provider->sm_count;   /* a whole number of CTAs per SM: 148 x resident CTAs */
+}
+
+/* FractalRenderingModule.initialize :73-100 */
+static chaos_status load_module(chaos_renderer *r)
+{
+    std::string path = r->provider->kernels_dir + "/" + r->desc->file_stem + ".cubin";
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f)
+        return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Invalid module file name: %s\nHave you set the kernels directory (cudaKernelsDir) properly?", path.c_str());
+    std::vector<char> image;
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    image.resize(sz > 0 ? (size_t)sz : 0);
+    size_t got = image.empty() ? 0 : fread(image.data(), 1, image.size(), f);
+    fclose(f);
+    if (got != image.size() || image.empty()) return fail(CHAOS_ERR_CUDA_INIT, "cannot read module file %s", path.c_str());
+    CUresult e = D->p_cuModuleLoadData(&r->module, image.data());
+    if (e != CUDA_SUCCESS) { r->module = nullptr; return fail(CHAOS_ERR_CUDA_INIT, "cuModuleLoadData(%s) failed: %s", path.c_str(), cu_err_name(e)); }
+
+    /* all kernels are resolved eagerly; a missing one is an error (FractalRenderingModule.java:91-97) */
+    struct { const char *name; CUfunction *fn; } fns[] = {
+        {"fractalRenderMainFloat", &r->k_main_f}, {"fractalRenderMainDouble", &r->k_main_d},
+        {"fractalRenderAdvancedFloat", &r->k_adv_f}, {"fractalRenderAdvancedDouble", &r->k_adv_d},
+        {"fractalRenderUnderSampled", &r->k_undersampled}, {"compose", &r->k_compose}, {"debug", &r->k_debug},
+    };
+    for (auto &k : fns) {
+        chaos_status st = get_function(r, k.name, k.fn);
+        if (st != CHAOS_OK) { unload_module(r); return st; }
+    }
+    CUdeviceptr abi_ptr = 0;
+    size_t abi_size = 0;
+    uint32_t abi = 0;
+    if (D->p_cuModuleGetGlobal(&abi_ptr, &abi_size, r->module, "CHAOS_MODULE_ABI_VERSION") != CUDA_SUCCESS || abi_size != 4 ||
+        D->p_cuMemcpyDtoH(&abi, abi_ptr, 4) != CUDA_SUCCESS || abi != CHAOS_MODULE_ABI) {
+        unload_module(r);
+        return fail(CHAOS_ERR_CUDA_INIT, "module %s was built for launch contract %u, this library speaks %u; rebuild the module", path.c_str(), abi, CHAOS_MODULE_ABI);
+    }
+    r->blocks_main_f = persistent_blocks(r, r->k_main_f, 256);
+    r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256);
+    r->blocks_adv_f = persistent_blocks(r, r->k_adv_f, 256);
+    r->blocks_adv_d = persistent_blocks(r, r->k_adv_d, 256);
+    if (r->desc->on_initialize) {
+        chaos_status st = r->desc->on_initialize(r);
+        if (st != CHAOS_OK) { unload_module(r); return st; }
+    }
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, int force_reload, chaos_renderer **out)
+{
+    if (!p) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "provider handle is NULL");
+    if (!out) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "out is NULL");
+    if (!fractal_name) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Unknown fractal: null");
+    ctx_guard g(p);
+    if (p->active) {
+        if (!strcmp(p->active->desc->fractal_name, fractal_name) && !force_reload) { *out = p->active; return CHAOS_OK; }
+        chaos_close(p->active);                                    /* closing the previous renderer :52 */
+    }
+    *out = nullptr;
+    const module_desc *desc = nullptr;
+    for (uint32_t i = 0; i < g_n_modules; ++i)
+        if (!strcmp(g_modules[i].fractal_name, fractal_name)) desc = &g_modules[i];
+    if (!desc) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Unknown fractal: %s", fractal_name);
+    chaos_renderer *r = new chaos_renderer();
+    r->provider = p;
+    r->desc = desc;
+    memset(&r->stats, 0, sizeof r->stats);
+    r->stats.struct_size = sizeof(chaos_stats);
+    const char *eng = getenv("CHAOS_ENGINE");
+    r->engine = eng ? (uint32_t)atoi(eng) : 0u;
+    chaos_status st = load_module(r);
+    if (st != CHAOS_OK) { delete r; return st; }
+    CUresult e = D->p_cuStreamCreate(&r->stream, CU_STREAM_NON_BLOCKING);
+    for (int i = 0; i < 4 && e == CUDA_SUCCESS; ++i) e = D->p_cuEventCreate(&r->ev[i], CU_EVENT_DEFAULT);
+    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->counters, sizeof(chaos_counters));
+    if (e == CUDA_SUCCESS) e = D->p_cuMemHostAlloc((void **)&r->counters_host, sizeof(chaos_counters), 0);
+    if (e != CUDA_SUCCESS) {
+        st = fail(CHAOS_ERR_CUDA_INIT, "cannot create stream/events/counters: %s", cu_err_name(e));
+        p->active = r;
+        chaos_close(r);
+        return st;
+    }
+    p->active = r;
+    *out = r;
+    return CHAOS_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * lifecycle
+ * ---------------------------------------------------------------------------------------- */
+static void free_frame_memory(chaos_renderer *r)
+{
+    for (int i = 0; i < 2; ++i) if (r->buf[i].ptr) { D->p_cuMemFree(r->buf[i].ptr); r->buf[i].ptr = 0; r->buf[i].pitch = 0; }
+    if (r->palette) { D->p_cuMemFree(r->palette); r->palette = 0; }
+    if (r->rgba_host) { D->p_cuMemFreeHost(r->rgba_host); r->rgba_host = nullptr; r->rgba_dev = 0; }
+    if (r->rgba_dev) { D->p_cuMemFree(r->rgba_dev); r->rgba_dev = 0; }
+}
+
+extern "C" chaos_status chaos_initialize(chaos_renderer *r, uint32_t width, uint32_t height,
+                                         const uint32_t *palette_rgba, uint32_t palette_len, chaos_output_mode mode)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (r->state == CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Already initialized.");
+    if (width == 0 || height == 0) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "output size must be positive but is %ux%u", width, height);
+    if (!palette_rgba || palette_len == 0) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "palette must hold at least one colour");
+    if (palette_len > 12000) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "palette of %u entries does not fit the compose kernel's shared-memory stage (max 12000)", palette_len);
+    /* the reference refuses grids above 65535 blocks of 32 px (CudaFractalRenderer.java:248-253) */
+    if (width > 65535u * 32u) return fail(CHAOS_ERR_RENDERER, "Unsupported input parameter: width must be smaller than %u", 65535u * 32u);
+    if (height > 65535u * 32u) return fail(CHAOS_ERR_RENDERER, "Unsupported input parameter: height must be smaller than %u", 65535u * 32u);
+    if (mode != CHAOS_OUTPUT_HOST && mode != CHAOS_OUTPUT_DEVICE) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "unknown output mode %d", (int)mode);
+    ctx_guard g(r->provider);
+    free_frame_memory(r);
+    /* two pitched buffers of 16-byte records (DeviceMemoryDoubleBuffer2D.java:116-146) */
+    for (int i = 0; i < 2; ++i) {
+        CUresult e = D->p_cuMemAllocPitch(&r->buf[i].ptr, &r->buf[i].pitch, (size_t)width * 16u, height, 16);
+        if (e != CUDA_SUCCESS) { free_frame_memory(r); return fail(CHAOS_ERR_CUDA, "cuMemAllocPitch(%ux%u) failed: %s", width, height, cu_err_name(e)); }
+    }
+    CUresult e = D->p_cuMemAlloc(&r->palette, (size_t)palette_len * 4u);
+    if (e == CUDA_SUCCESS) e = D->p_cuMemcpyHtoD(r->palette, palette_rgba, (size_t)palette_len * 4u);
+    size_t frame_bytes = (size_t)width * height * 4u;
+    if (e == CUDA_SUCCESS) {
+        if (mode == CHAOS_OUTPUT_HOST) {
+            e = D->p_cuMemHostAlloc((void **)&r->rgba_host, frame_bytes, CU_MEMHOSTALLOC_DEVICEMAP);
+            if (e == CUDA_SUCCESS) e = D->p_cuMemHostGetDevicePointer(&r->rgba_dev, r->rgba_host, 0);
+            if (e == CUDA_SUCCESS) memset(r->rgba_host, 0, frame_bytes);
+        } else {
+            e = D->p_cuMemAlloc(&r->rgba_dev, frame_bytes);
+            if (e == CUDA_SUCCESS) e = D->p_cuMemsetD8Async(r->rgba_dev, 0, frame_bytes, r->stream);
+            if (e == CUDA_SUCCESS) e = D->p_cuStreamSynchronize(r->stream);
+        }
+    }
+    if (e != CUDA_SUCCESS) { free_frame_memory(r); return fail(CHAOS_ERR_CUDA, "cannot allocate palette/output: %s", cu_err_name(e)); }
+    r->width = width; r->height = height; r->mode = mode; r->palette_len = palette_len;
+    r->buffers_switched = false;
+    r->primary_dirty = true;                                       /* reallocatePrimary2DBuffer :45-49 */
+    r->state = CHAOS_STATE_READY_TO_RENDER;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_free_resources(chaos_renderer *r)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (r->state == CHAOS_STATE_NOT_INITIALIZED) return fail(CHAOS_ERR_ILLEGAL_STATE, "Already free.");
+    ctx_guard g(r->provider);
+    D->p_cuStreamSynchronize(r->stream);
+    free_frame_memory(r);
+    r->state = CHAOS_STATE_NOT_INITIALIZED;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_close(chaos_renderer *r)
+{
+    if (!r) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "renderer handle is NULL");
+    ctx_guard g(r->provider);
+    if (r->stream) D->p_cuStreamSynchronize(r->stream);
+    free_frame_memory(r);
+    if (r->counters) D->p_cuMemFree(r->counters);
+    if (r->counters_host) D->p_cuMemFreeHost(r->counters_host);
+    for (int i = 0; i < 4; ++i) if (r->ev[i]) D->p_cuEventDestroy(r->ev[i]);
+    if (r->stream) D->p_cuStreamDestroy(r->stream);
+    unload_module(r);
+    if (r->provider && r->provider->active == r) r->provider->active = nullptr;
+    delete r;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_state chaos_get_state(const chaos_renderer *r) { return r ? r->state : CHAOS_STATE_NOT_INITIALIZED; }
+extern "C" uint32_t chaos_get_width(const chaos_renderer *r) { return r ? r->width : 0; }
+extern "C" uint32_t chaos_get_height(const chaos_renderer *r) { return r ? r->height : 0; }
+extern "C" const char *chaos_fractal_name(const chaos_renderer *r) { return r ? r->desc->fractal_name : ""; }
+extern "C" const uint32_t *chaos_output_rgba(const chaos_renderer *r) { return r ? r->rgba_host : nullptr; }
+extern "C" uint64_t chaos_output_rgba_device(const chaos_renderer *r) { return (r && r->mode == CHAOS_OUTPUT_DEVICE) ? (uint64_t)r->rgba_dev : 0; }
+
+/* ------------------------------------------------------------------------------------------
+ * constants by name (FractalRenderingModule.java:163-227)
+ * ---------------------------------------------------------------------------------------- */
+static chaos_status write_constant(chaos_renderer *r, const char *symbol, const void *data, size_t bytes, const char *what)
+{
+    CUdeviceptr ptr = 0;
+    size_t size = 0;
+    CUresult e = D->p_cuModuleGetGlobal(&ptr, &size, r->module, symbol);
+    if (e == CUDA_ERROR_NOT_FOUND) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "module %s has no constant named %s", r->desc->file_stem, symbol);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuModuleGetGlobal(%s) failed: %s", symbol, cu_err_name(e));
+    if (size < bytes) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Attempt to write %s to device memory allocated to size %zu", what, size);
+    e = D->p_cuMemcpyHtoD(ptr, data, bytes);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "write to constant %s failed: %s", symbol, cu_err_name(e));
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_write_constant(chaos_renderer *r, const char *symbol, const void *data, size_t bytes)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (!symbol || !data) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "symbol/data is NULL");
+    ctx_guard g(r->provider);
+    D->p_cuStreamSynchronize(r->stream);
+    char what[32];
+    snprintf(what, sizeof what, "%zu bytes", bytes);
+    return write_constant(r, symbol, data, bytes, what);
+}
+
+extern "C" chaos_status chaos_set_custom_params(chaos_renderer *r, const char *text)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    ctx_guard g(r->provider);
+    D->p_cuStreamSynchronize(r->stream);
+    return r->desc->set_custom_params(r, text);
+}
+
+extern "C" chaos_status chaos_supply_defaults(chaos_renderer *r, chaos_defaults *out)
+{
+    if (!r) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "renderer handle is NULL");
+    if (!out || out->struct_size != sizeof(chaos_defaults)) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "chaos_defaults.struct_size mismatch");
+    memset(out, 0, sizeof *out);
+    out->struct_size = sizeof(chaos_defaults);
+    r->desc->supply_defaults(out);
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_set_partition(chaos_renderer *r, uint32_t part_index, uint32_t part_count, uint32_t band_rows)
+{
+    if (!r) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "renderer handle is NULL");
+    if (part_count == 0 || part_index >= part_count) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "partition %u of %u is not valid", part_index, part_count);
+    if (band_rows == 0 || (band_rows & 3u)) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "band_rows must be a positive multiple of 4 (vote tiles are 4 rows high) but is %u", band_rows);
+    r->part_index = part_index; r->part_count = part_count; r->band_rows = band_rows;
+    r->primary_dirty = true;
+    return CHAOS_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * precision rule (CudaFractalRenderer.java:409-419, RenderingKernel.java:124-138)
+ * ---------------------------------------------------------------------------------------- */
+static double ulp_of_float(float v)          /* Math.ulp(float) */
+{
+    v = fabsf(v);
+    if (v != v || isinf(v)) return (double)v;
+    float n = nextafterf(v, INFINITY);
+    if (isinf(n)) return (double)(v - nextafterf(v, 0.f));
+    return (double)(n - v);
+}
+static double ulp_of_double(double v)        /* Math.ulp(double) */
+{
+    v = fabs(v);
+    if (v != v || isinf(v)) return v;
+    double n = nextafter(v, INFINITY);
+    if (isinf(n)) return v - nextafter(v, 0.0);
+    return n - v;
+}
+static chaos_precision choose_precision(const double s[4], uint32_t W, uint32_t H)
+{
+    double pw = fabs(s[2] - s[0]) / (double)W, ph = fabs(s[3] - s[1]) / (double)H;
+    chaos_precision p = CHAOS_PRECISION_SINGLE;
+    if (pw < ulp_of_float((float)s[0]) || ph < ulp_of_float((float)s[1])) p = CHAOS_PRECISION_DOUBLE;
+    if (pw < ulp_of_double(s[0]) || ph < ulp_of_double(s[1])) p = CHAOS_PRECISION_TOO_BIG;
+    return p;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * frames
+ * ---------------------------------------------------------------------------------------- */
+static chaos_status validate_model(const chaos_renderer *r, const chaos_params *m)
+{
+    if (r->state != CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Renderer has to be initialized first");
+    if (!m || m->struct_size != sizeof(chaos_params)) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "chaos_params.struct_size mismatch");
+    if (m->max_iterations < 1) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "maxIterations must be a positive number, but is : %d", m->max_iterations);
+    static const char *names[4] = {"left_bottom_x", "left_bottom_y", "right_top_x", "right_top_y"};
+    for (int i = 0; i < 4; ++i)
+        if (!isfinite(m->segment[i])) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Argument segment %s must be a finite float but is %g.", names[i], m->segment[i]);
+    return CHAOS_OK;
+}
+
+static void fill_render_args(const chaos_renderer *r, const chaos_params *m, chaos_render_args *a)
+{
+    memset(a, 0, sizeof *a);
+    a->counters = (chaos_counters *)r->counters;
+    for (int i = 0; i < 4; ++i) { a->image[i] = m->segment[i]; a->imagef[i] = (float)m->segment[i]; }
+    a->width = r->width; a->height = r->height;
+    a->max_iter = (uint32_t)m->max_iterations;
+    a->max_ss = m->max_super_sampling;
+    /* flag word: KernelMain.java:12-13, KernelAdvanced.java:17-20 */
+    a->flags = (m->use_adaptive_super_sampling ? CHAOS_FLAG_ADAPTIVE_SS : 0u) | (m->visualise_sample_count ? 2u : 0u) |
+               (m->use_foveated_rendering ? CHAOS_FLAG_FOVEATION : 0u) | (m->use_sample_reuse ? CHAOS_FLAG_SAMPLE_REUSE : 0u) |
+               (m->is_zooming ? CHAOS_FLAG_IS_ZOOMING : 0u) | (m->is_zooming_in ? CHAOS_FLAG_ZOOMING_IN : 0u);
+    a->focus_x = (uint32_t)m->mouse_focus[0]; a->focus_y = (uint32_t)m->mouse_focus[1];
+    a->tiles_x = (r->width + 7u) / 8u;
+    a->tile_rows = (r->height + 3u) / 4u;
+    a->part_index = r->part_index; a->part_count = r->part_count; a->band_tile_rows = r->band_rows / 4u;
+    uint32_t owned_rows = a->tile_rows;
+    if (r->part_count > 1u) {
+        owned_rows = 0;
+        uint32_t bands = (a->tile_rows + a->band_tile_rows - 1u) / a->band_tile_rows;
+        for (uint32_t b = r->part_index; b < bands; b += r->part_count)
+            owned_rows += std::min(a->band_tile_rows, a->tile_rows - b * a->band_tile_rows);
+    }
+    a->n_tiles = owned_rows * a->tiles_x;
+    a->engine = r->engine;
+}
+
+static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg)
+{
+    void *params[1] = {arg};
+    CUresult e = D->p_cuLaunchKernel(fn, (unsigned)blocks, 1, 1, (unsigned)threads, 1, 1, smem, r->stream, params, nullptr);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "Error just after launching a kernel:%s", cu_err_name(e));
+    r->stats.kernel_launches += 1;
+    r->stats.launches_total += 1;
+    return CHAOS_OK;
+}
+
+/* launchDrawingKernel :275-364 without the GL map/unmap and surface objects */
+static chaos_status launch_compose(chaos_renderer *r, const chaos_params *m)
+{
+    chaos_compose_args c;
+    memset(&c, 0, sizeof c);
+    c.in = (const chaos_pixel_info *)r->buf[0].ptr;
+    c.in_pitch = r->buf[0].pitch;
+    c.out_rgba = (uint32_t *)r->rgba_dev;
+    c.palette = (const uint32_t *)r->palette;
+    c.palette_len = r->palette_len;
+    c.width = r->width; c.height = r->height;
+    c.max_ss = m->max_super_sampling;
+    c.part_index = r->part_index; c.part_count = r->part_count; c.band_rows = r->band_rows;
+    uint64_t quads = (uint64_t)((r->width + 3u) / 4u) * r->height;
+    int max_blocks = r->provider->sm_count * 8;
+    int blocks = (int)std::min<uint64_t>((quads + 255u) / 256u, (uint64_t)max_blocks);
+    if (blocks < 1) blocks = 1;
+    return launch(r, r->k_compose, blocks, 256, r->palette_len * 4u, &c);
+}
+
+static chaos_status finish_frame(chaos_renderer *r)
+{
+    CUresult e = D->p_cuMemcpyDtoHAsync(r->counters_host, r->counters, sizeof(chaos_counters), r->stream);
+    if (e == CUDA_SUCCESS) e = D->p_cuStreamSynchronize(r->stream);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "Error just after launching a kernel:%s", cu_err_name(e));
+    D->p_cuEventElapsedTime(&r->stats.render_ms, r->ev[0], r->ev[1]);
+    D->p_cuEventElapsedTime(&r->stats.compose_ms, r->ev[2], r->ev[3]);
+    r->stats.pixel_iterations = r->counters_host->pixel_iterations;
+    r->stats.samples = r->counters_host->samples;
+    return CHAOS_OK;
+}
+
+static chaos_status set_module_constants(chaos_renderer *r, const chaos_params *m)
+{
+    /* setModuleConstants :227-233: rewritten only when the flag changes */
+    if (!r->have_last || (m->visualise_sample_count != 0) != (r->last.visualise_sample_count != 0)) {
+        int v = m->visualise_sample_count ? 1 : 0;   /* host copies symbol-size bytes of a little-endian int */
+        D->p_cuStreamSynchronize(r->stream);
+        return write_constant(r, "VISUALIZE_SAMPLE_COUNT", &v, 1, "boolean");
+    }
+    return CHAOS_OK;
+}
+
+static chaos_precision frame_precision(const chaos_renderer *r, chaos_params *m)
+{
+    chaos_precision p = choose_precision(m->segment, r->width, r->height);
+    m->float_precision = (int32_t)p;                               /* model.setFloatingPointPrecision :418 */
+    if (m->force_precision == 1) return CHAOS_PRECISION_SINGLE;
+    if (m->force_precision == 2) return CHAOS_PRECISION_DOUBLE;
+    return p;
+}
+
+static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
+{
+    chaos_status st = set_module_constants(r, m);
+    if (st != CHAOS_OK) return st;
+    /* the main kernel asserts maxSuperSampling >= 1 on the device (fractalRendererGeneric.cu:174) */
+    if (!(m->max_super_sampling >= 1.0f))
+        return fail(CHAOS_ERR_RENDERER, "maxSuperSampling must be >= 1 for a quality render but is %g (device assert, fractalRendererGeneric.cu:174)", m->max_super_sampling);
+    chaos_precision prec = frame_precision(r, m);
+    const bool dbl = prec != CHAOS_PRECISION_SINGLE;               /* tooBig still runs the double kernel :213-217 */
+    if (r->buffers_switched) { std::swap(r->buf[0], r->buf[1]); r->buffers_switched = false; }  /* resetBufferOrder */
+    chaos_render_args a;
+    fill_render_args(r, m, &a);
+    a.out = (chaos_pixel_info *)r->buf[0].ptr; a.out_pitch = r->buf[0].pitch;
+    r->stats.kernel_launches = 0;
+    CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters), r->stream);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
+    D->p_cuEventRecord(r->ev[0], r->stream);
+    if (a.n_tiles) {
+        st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, 0, &a);
+        if (st != CHAOS_OK) return st;
+    }
+    D->p_cuEventRecord(r->ev[1], r->stream);
+    D->p_cuEventRecord(r->ev[2], r->stream);
+    st = launch_compose(r, m);
+    if (st != CHAOS_OK) return st;
+    D->p_cuEventRecord(r->ev[3], r->stream);
+    st = finish_frame(r);
+    if (st != CHAOS_OK) return st;
+    r->last = *m; r->have_last = true;                             /* lastRendering = model.copy() */
+    r->primary_dirty = false;
+    m->sample_reuse_cache_dirty = 0;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_render_quality(chaos_renderer *r, chaos_params *m)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    st = validate_model(r, m);
+    if (st != CHAOS_OK) return st;
+    ctx_guard g(r->provider);
+    return render_quality_locked(r, m);
+}
+
+extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    st = validate_model(r, m);
+    if (st != CHAOS_OK) return st;
+    ctx_guard g(r->provider);
+    st = set_module_constants(r, m);
+    if (st != CHAOS_OK) return st;
+    /* nothing to reuse -> create it (:164-168) */
+    if (m->sample_reuse_cache_dirty || r->primary_dirty || !r->have_last) return render_quality_locked(r, m);
+
+    chaos_precision prec = frame_precision(r, m);
+    const bool dbl = prec != CHAOS_PRECISION_SINGLE;
+    chaos_render_args a;
+    fill_render_args(r, m, &a);
+    for (int i = 0; i < 4; ++i) { a.image_reused[i] = r->last.segment[i]; a.image_reusedf[i] = (float)r->last.segment[i]; }
+    a.in = (const chaos_pixel_info *)r->buf[0].ptr; a.in_pitch = r->buf[0].pitch;   /* input = primary */
+    a.out = (chaos_pixel_info *)r->buf[1].ptr; a.out_pitch = r->buf[1].pitch;       /* output = secondary */
+    r->stats.kernel_launches = 0;
+    CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters), r->stream);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
+    D->p_cuEventRecord(r->ev[0], r->stream);
+    if (a.n_tiles) {
+        st = launch(r, dbl ? r->k_adv_d : r->k_adv_f, dbl ? r->blocks_adv_d : r->blocks_adv_f, 256, 0, &a);
+        if (st != CHAOS_OK) return st;
+    }
+    D->p_cuEventRecord(r->ev[1], r->stream);
+    std::swap(r->buf[0], r->buf[1]);                               /* switch2DBuffers :180 */
+    r->buffers_switched = !r->buffers_switched;
+    D->p_cuEventRecord(r->ev[2], r->stream);
+    st = launch_compose(r, m);
+    if (st != CHAOS_OK) return st;
+    D->p_cuEventRecord(r->ev[3], r->stream);
+    st = finish_frame(r);
+    if (st != CHAOS_OK) return st;
+    r->last = *m; r->have_last = true;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_debug(chaos_renderer *r)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    ctx_guard g(r->provider);
+    CUresult e = D->p_cuLaunchKernel(r->k_debug, 1, 1, 1, 32, 32, 1, 0, r->stream, nullptr, nullptr);  /* grid 1x1, block 32x32 :147-154 */
+    if (e == CUDA_SUCCESS) e = D->p_cuStreamSynchronize(r->stream);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "Error just after launching a kernel:%s", cu_err_name(e));
+    r->stats.launches_total += 1;
+    fflush(stdout);
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_download_rgba(chaos_renderer *r, uint32_t *dst, size_t dst_bytes)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (r->state != CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Renderer has to be initialized first");
+    size_t need = (size_t)r->width * r->height * 4u;
+    if (!dst || dst_bytes < need) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Output buffer must be at least width * height * 4 bytes long. Buffer capacity: %zu", dst_bytes);
+    ctx_guard g(r->provider);
+    if (r->mode == CHAOS_OUTPUT_HOST) { memcpy(dst, r->rgba_host, need); return CHAOS_OK; }
+    CUresult e = D->p_cuMemcpyDtoHAsync(dst, r->rgba_dev, need, r->stream);
+    if (e == CUDA_SUCCESS) e = D->p_cuStreamSynchronize(r->stream);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemcpyDtoH failed: %s", cu_err_name(e));
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_download_records(chaos_renderer *r, void *dst, size_t dst_bytes)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (r->state != CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Renderer has to be initialized first");
+    size_t row = (size_t)r->width * 16u, need = row * r->height;
+    if (!dst || dst_bytes < need) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Output buffer must be at least width * height * 16 bytes long. Buffer capacity: %zu", dst_bytes);
+    ctx_guard g(r->provider);
+    D->p_cuStreamSynchronize(r->stream);
+    CUDA_MEMCPY2D c;
+    memset(&c, 0, sizeof c);
+    c.srcMemoryType = CU_MEMORYTYPE_DEVICE; c.srcDevice = r->buf[0].ptr; c.srcPitch = r->buf[0].pitch;
+    c.dstMemoryType = CU_MEMORYTYPE_HOST; c.dstHost = dst; c.dstPitch = row;
+    c.WidthInBytes = row; c.Height = r->height;
+    CUresult e = D->p_cuMemcpy2D(&c);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemcpy2D failed: %s", cu_err_name(e));
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_get_stats(const chaos_renderer *r, chaos_stats *out)
+{
+    if (!r) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "renderer handle is NULL");
+    if (!out || out->struct_size != sizeof(chaos_stats)) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "chaos_stats.struct_size mismatch");
+    *out = r->stats;
+    out->struct_size = sizeof(chaos_stats);
+    return CHAOS_OK;
+}

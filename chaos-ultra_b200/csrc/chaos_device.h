@@ -1,0 +1,75 @@
+/*
+ * chaos_device.h -- the launch contract between the host library (chaos_abi.cpp) and a fractal
+ * module (one cubin per fractal, built from fractals/<name>.cu + render_generic.cuh).
+ *
+ * It replaces the positional kernel parameter lists the reference marshals from Java
+ * (cudarenderer/RenderingKernel.java:21-25, KernelMain.java:19-20, KernelAdvanced.java:26-29,
+ * KernelCompose.java:24-33): every kernel takes ONE by-value struct.  Entry names stay the
+ * reference's (FractalRenderingModule.java:91-97) so a module is still found by name.
+ */
+#ifndef CHAOS_DEVICE_H
+#define CHAOS_DEVICE_H
+
+#include <stdint.h>
+
+#define CHAOS_MODULE_ABI 3u
+
+/* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
+struct chaos_pixel_info {
+    float value;
+    float weight;
+    uint32_t is_reused; /* byte 0 = isReused, bytes 1..3 = padding (written as 0 here) */
+    float weight_of_new_samples;
+};
+
+/* fractalRendererGeneric.cu:157-161 */
+#define CHAOS_FLAG_ADAPTIVE_SS (1u << 0)
+#define CHAOS_FLAG_FOVEATION (1u << 2)
+#define CHAOS_FLAG_SAMPLE_REUSE (1u << 3)
+#define CHAOS_FLAG_IS_ZOOMING (1u << 4)
+#define CHAOS_FLAG_ZOOMING_IN (1u << 5)
+
+/* device counters, one block per renderer (zeroed by the host before each render call) */
+struct chaos_counters {
+    unsigned int next_tile;             /* work-stealing cursor over vote tiles */
+    unsigned int next_tile_b;           /* second cursor (advanced kernel, sampling pass) */
+    unsigned long long pixel_iterations;
+    unsigned long long samples;
+    unsigned int pad[2];
+};
+
+struct chaos_render_args {
+    chaos_pixel_info *out;  /* output records, pitch-linear */
+    uint64_t out_pitch;     /* bytes */
+    const chaos_pixel_info *in; /* previous frame (advanced kernels) */
+    uint64_t in_pitch;
+    chaos_counters *counters;
+    double image[4];        /* lb.x lb.y rt.x rt.y; float kernels read imagef (host-cast, KernelMainFloat.java:19-21) */
+    double image_reused[4];
+    float imagef[4];
+    float image_reusedf[4];
+    uint32_t width, height;
+    uint32_t max_iter;
+    float max_ss;
+    uint32_t flags;
+    uint32_t focus_x, focus_y;
+    uint32_t tiles_x;       /* ceil(width / 8) */
+    uint32_t tile_rows;     /* ceil(height / 4) */
+    /* multi-GPU row-band partition: this launch covers bands b with b % part_count == part_index */
+    uint32_t part_index, part_count, band_tile_rows;
+    uint32_t n_tiles;       /* vote tiles owned by this launch */
+    uint32_t engine;        /* 0 = tile-synchronous, 1 = lane-refill scheduler */
+};
+
+struct chaos_compose_args {
+    const chaos_pixel_info *in;
+    uint64_t in_pitch;
+    uint32_t *out_rgba;     /* device or mapped-host pointer, width*height, row 0 = top */
+    const uint32_t *palette;
+    uint32_t palette_len;
+    uint32_t width, height;
+    float max_ss;
+    uint32_t part_index, part_count, band_rows;
+};
+
+#endif

@@ -1,0 +1,164 @@
+/*
+ * chaos_ultra.h -- C ABI of the B200-native render backend for chaos-ultra.
+ *
+ * This is the drop-in boundary: the functions below are exactly what a JNI / Panama binding
+ * of the reference's renderer plugin interface would bind (INTEGRATION.md shows the Java
+ * side).  Plain pointers and sizes only; no CUDA, torch or C++ types.
+ *
+ * Reference interfaces replaced (paths relative to
+ * /root/reference/src/main/java/cz/cuni/mff/cgg/teichmaa/chaosultra/):
+ *   rendering/FractalRendererProvider.java:11-27      -> chaos_provider_*, chaos_open
+ *   rendering/FractalRenderer.java:14-77              -> chaos_initialize ... chaos_close
+ *   cudarenderer/CudaFractalRendererProvider.java:14-91  (registry, one active renderer)
+ *   cudarenderer/CudaFractalRenderer.java:32-430      (frame logic, state machine)
+ *   cudarenderer/FractalRenderingModule.java:31-280   (module file by name, constants by name)
+ *   rendering/model/RenderingModel.java:6-20          -> chaos_params
+ *
+ * Threading: like the reference (one AWT/GL/CUDA thread, CudaHelpers.java:47-49) all calls
+ * on one provider must come from one thread at a time.  No GL context is required.
+ * Errors: every function returns a chaos_status; chaos_last_error() returns the message of
+ * the last failing call on the calling thread.  The library never aborts the process.
+ */
+#ifndef CHAOS_ULTRA_H
+#define CHAOS_ULTRA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHAOS_ABI_VERSION 1
+#if defined(__GNUC__)
+#define CHAOS_API __attribute__((visibility("default")))
+#else
+#define CHAOS_API
+#endif
+#define CHAOS_MAX_SUPER_SAMPLING 64 /* FractalRenderer.java:15 */
+
+typedef enum chaos_status {
+    CHAOS_OK = 0,
+    CHAOS_ERR_ILLEGAL_STATE = 1,    /* java.lang.IllegalStateException in the reference */
+    CHAOS_ERR_ILLEGAL_ARGUMENT = 2, /* java.lang.IllegalArgumentException */
+    CHAOS_ERR_CUDA_INIT = 3,        /* CudaInitializationException */
+    CHAOS_ERR_CUDA = 4,             /* jcuda.CudaException at launch/copy time */
+    CHAOS_ERR_RENDERER = 5          /* FractalRendererException (e.g. grid too large) */
+} chaos_status;
+
+/* util/FloatPrecision.java:3-10 */
+typedef enum chaos_precision {
+    CHAOS_PRECISION_SINGLE = 0,
+    CHAOS_PRECISION_DOUBLE = 1,
+    CHAOS_PRECISION_TOO_BIG = 2
+} chaos_precision;
+
+/* rendering/FractalRendererState.java */
+typedef enum chaos_state { CHAOS_STATE_NOT_INITIALIZED = 0, CHAOS_STATE_READY_TO_RENDER = 1 } chaos_state;
+
+/* where the composed RGBA8 frame is written */
+typedef enum chaos_output_mode {
+    CHAOS_OUTPUT_HOST = 0,  /* compose stores straight into library-owned pinned, mapped host memory */
+    CHAOS_OUTPUT_DEVICE = 1 /* compose stores to device memory; chaos_download_rgba() copies on demand */
+} chaos_output_mode;
+
+/* The getters of RenderingModel (rendering/model/*.java) that the renderer reads, plus the two
+ * values it writes back (sampleReuseCacheDirty, floatingPointPrecision). */
+typedef struct chaos_params {
+    uint32_t struct_size;       /* = sizeof(chaos_params) */
+    int32_t max_iterations;     /* IterationLimitModel; must be >= 1 (RenderingKernel.java:69) */
+    double segment[4];          /* PlaneSegment: leftBottom.x, leftBottom.y, rightTop.x, rightTop.y; finite */
+    float max_super_sampling;   /* SuperSamplingModel, [0, 64] (Model.java:166-168) */
+    uint8_t use_adaptive_super_sampling;
+    uint8_t visualise_sample_count;
+    uint8_t use_foveated_rendering;
+    uint8_t use_sample_reuse;
+    uint8_t is_zooming;
+    uint8_t is_zooming_in;
+    uint8_t sample_reuse_cache_dirty; /* in/out: cleared by a quality render (CudaFractalRenderer.java:205) */
+    uint8_t force_precision;    /* 0 = reference rule (CudaFractalRenderer.java:409-419); 1 = single; 2 = double */
+    int32_t mouse_focus[2];     /* FoveatedRenderingModel.getMouseFocus */
+    int32_t float_precision;    /* out: chaos_precision chosen for this frame */
+} chaos_params;
+
+/* DefaultFractalModel values a module supplies (modules/Module*.java supplyDefaultValues) */
+typedef struct chaos_defaults {
+    uint32_t struct_size;
+    uint8_t has_segment;        /* setPlaneSegmentFromCenter was called */
+    uint8_t has_max_iterations;
+    uint8_t has_max_super_sampling;
+    uint8_t reserved;
+    double center_x, center_y, zoom;
+    int32_t max_iterations;
+    float max_super_sampling;
+    char custom_params[256];    /* setFractalCustomParams text ("" if none) */
+} chaos_defaults;
+
+/* Device-side timings and exact work counters of the most recent render call. */
+typedef struct chaos_stats {
+    uint32_t struct_size;
+    uint32_t kernel_launches;        /* kernels of this library launched by the last render call */
+    float render_ms;                 /* iteration / reuse kernel, CUDA events on the render stream */
+    float compose_ms;                /* compose kernel */
+    uint64_t pixel_iterations;       /* sum of escape-loop trip counts over every evaluated sample */
+    uint64_t samples;                /* number of evaluated samples (orbits) */
+    uint64_t launches_total;         /* kernels launched since the renderer was opened */
+} chaos_stats;
+
+typedef struct chaos_provider chaos_provider;
+typedef struct chaos_renderer chaos_renderer;
+
+/* ---- provider: CudaFractalRendererProvider.java:14-91, FractalRenderingModule.java:38-56 ---- */
+/* kernels_dir plays the role of <user.dir>/<-DcudaKernelsDir>; modules are <dir>/<file>.cubin.
+ * device is the CUDA ordinal (the reference is hard-wired to 0, CudaHelpers.java:40). */
+CHAOS_API chaos_status chaos_provider_create(const char *kernels_dir, int device, chaos_provider **out);
+CHAOS_API chaos_status chaos_provider_destroy(chaos_provider *p);
+/* getAvailableFractals(): the registered display names, independent of which files exist. */
+CHAOS_API chaos_status chaos_list_fractals(chaos_provider *p, const char **names, uint32_t capacity, uint32_t *count);
+/* getRenderer(name, forceReload) :47-66 -- at most one active renderer per provider; same name and
+ * !force_reload returns the active one; otherwise the old one is closed (module unloaded) and the
+ * module file is read again. */
+CHAOS_API chaos_status chaos_open(chaos_provider *p, const char *fractal_name, int force_reload, chaos_renderer **out);
+
+/* ---- renderer: FractalRenderer.java:14-77 / CudaFractalRenderer.java ---- */
+/* initializeRendering(GLParams) :85-101.  palette_rgba: R in bits 0-7 (ImageHelpers.java:138-158); copied. */
+CHAOS_API chaos_status chaos_initialize(chaos_renderer *r, uint32_t width, uint32_t height,
+                              const uint32_t *palette_rgba, uint32_t palette_len, chaos_output_mode mode);
+CHAOS_API chaos_status chaos_free_resources(chaos_renderer *r);          /* freeRenderingResources :103-112 */
+CHAOS_API chaos_status chaos_render_quality(chaos_renderer *r, chaos_params *model); /* renderQuality :187-206 */
+CHAOS_API chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *model);    /* renderFast :159-184 */
+CHAOS_API chaos_status chaos_debug(chaos_renderer *r);                   /* launchDebugKernel :147-154 */
+CHAOS_API chaos_status chaos_set_custom_params(chaos_renderer *r, const char *text); /* setFractalCustomParams :388-391 */
+/* FractalRenderingModule.writeToConstantMemory :163-227: size-checked write to a named __constant__ */
+CHAOS_API chaos_status chaos_write_constant(chaos_renderer *r, const char *symbol, const void *data, size_t bytes);
+CHAOS_API chaos_status chaos_supply_defaults(chaos_renderer *r, chaos_defaults *out); /* supplyDefaultValues */
+CHAOS_API chaos_status chaos_close(chaos_renderer *r);                   /* close :381-386 */
+
+CHAOS_API chaos_state chaos_get_state(const chaos_renderer *r);
+CHAOS_API uint32_t chaos_get_width(const chaos_renderer *r);
+CHAOS_API uint32_t chaos_get_height(const chaos_renderer *r);
+CHAOS_API const char *chaos_fractal_name(const chaos_renderer *r);
+
+/* The composed frame: width*height RGBA8, row 0 = top of the plane segment (Model.java:23-32).
+ * HOST mode: pointer into pinned memory, valid until chaos_free_resources.  DEVICE mode: NULL. */
+CHAOS_API const uint32_t *chaos_output_rgba(const chaos_renderer *r);
+/* device address (as integer) of the RGBA frame in DEVICE mode, 0 otherwise; for NVLink gathers */
+CHAOS_API uint64_t chaos_output_rgba_device(const chaos_renderer *r);
+/* copy the composed frame (either mode) into caller memory */
+CHAOS_API chaos_status chaos_download_rgba(chaos_renderer *r, uint32_t *dst, size_t dst_bytes);
+/* copy the current primary pixel_info_t buffer (16 B/pixel, pitch removed) into caller memory;
+ * the debugging counterpart of copy2DFromDevToHost (CudaFractalRenderer.java:119-134) */
+CHAOS_API chaos_status chaos_download_records(chaos_renderer *r, void *dst, size_t dst_bytes);
+CHAOS_API chaos_status chaos_get_stats(const chaos_renderer *r, chaos_stats *out);
+
+/* Multi-GPU: this renderer renders and composes only the row bands b with b % part_count ==
+ * part_index, bands being band_rows pixel rows high (a multiple of 4).  part_count 1 = whole frame. */
+CHAOS_API chaos_status chaos_set_partition(chaos_renderer *r, uint32_t part_index, uint32_t part_count, uint32_t band_rows);
+
+CHAOS_API const char *chaos_last_error(void);
+CHAOS_API uint32_t chaos_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHAOS_ULTRA_H */

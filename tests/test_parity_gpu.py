@@ -1,0 +1,163 @@
+"""GPU parity: this backend, called through the C ABI, against (1) the CPU oracle, (2) the reference's own
+kernels run live on the same device (oracle/_ref via refrun), (3) the committed golden fixtures.
+Bar (BASELINE.json): records bit-exact, RGBA identical (<= 1 LSB allowed, 0 observed)."""
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+import helpers
+import oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+ENGINES = [0, 1]
+
+
+def _ids(cs):
+    return [c["name"] for c in cs]
+
+
+def _have_ref():
+    return oracle.REFRUN_LIB.exists() and (oracle.REF_DIR / "mandelbrot.src.cubin").exists()
+
+
+@pytest.fixture(params=ENGINES, ids=lambda e: "engine%d" % e)
+def engine(request, provider):
+    os.environ["CHAOS_ENGINE"] = str(request.param)
+    # the engine is read when a renderer is opened: force a reload
+    for name in ("mandelbrot",):
+        provider.getRenderer(name, True)
+    yield request.param
+    os.environ.pop("CHAOS_ENGINE", None)
+
+
+@pytest.mark.parametrize("case", cases.MAIN_CASES, ids=_ids(cases.MAIN_CASES))
+def test_main_matches_oracle(cu, provider, engine, case):
+    r = helpers.open_renderer(cu, provider, case)
+    m = helpers.model_for(cu, case)
+    r.renderQuality(m)
+    got = r.downloadRecords()
+    want = oracle.render_main(case["fractal"], case["W"], case["H"], case["image"], case["maxIter"], case["maxSS"],
+                              case["flags"], case["double"], julia_c=case["julia_c"], amplifier=case["amplifier"])
+    helpers.assert_records_equal(got, want.records, case["name"])
+    st = r.stats()
+    assert st.pixel_iterations == want.pixel_iterations
+    assert st.samples == want.samples
+    assert st.kernel_launches == 2
+    # compose: palette lookup must be identical
+    pal = cu.createDefaultColorPalette()
+    assert (r.outputRGBA() == oracle.compose(case["fractal"], want.records, pal, case["maxSS"])).all()
+    assert not m.sampleReuseCacheDirty
+
+
+@pytest.mark.skipif(not _have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", cases.MAIN_CASES, ids=_ids(cases.MAIN_CASES))
+def test_main_matches_live_reference(cu, provider, case):
+    r = helpers.open_renderer(cu, provider, case)
+    m = helpers.model_for(cu, case)
+    r.renderQuality(m)
+    got = r.downloadRecords()
+    rgba = r.outputRGBA().copy()
+    with oracle.RefRun(case["fractal"], "src") as rr:
+        if case["fractal"] == "julia":
+            rr.write_constant("julia_c", np.array(case["julia_c"], dtype=np.float64).tobytes())
+        if case["fractal"] == "test":
+            rr.write_constant("amplifier", np.array([case["amplifier"]], dtype=np.int32).tobytes())
+        want = rr.main(case["W"], case["H"], case["image"], case["maxIter"], case["maxSS"], case["flags"], case["double"])
+        want_rgba = rr.compose(want, cu.createDefaultColorPalette(), case["maxSS"], False)
+    helpers.assert_records_equal(got, want, case["name"] + " vs reference kernels")
+    assert (rgba == want_rgba).all()
+
+
+@pytest.mark.parametrize("case", cases.ADV_CASES, ids=_ids(cases.ADV_CASES))
+def test_advanced_matches_oracle(cu, provider, case):
+    img0, img1 = cases.adv_segments(case)
+    r = helpers.open_renderer(cu, provider, case)
+    m0 = helpers.model_for(cu, case, image=img0, maxSS=case["maxSS0"])
+    m0.sampleReuseCacheDirty = True
+    r.renderFast(m0)                      # nothing to reuse yet -> falls back to a quality render
+    assert not m0.sampleReuseCacheDirty
+    rec0 = r.downloadRecords()
+    want0 = oracle.render_main(case["fractal"], case["W"], case["H"], img0, case["maxIter"], case["maxSS0"],
+                               case["flags"], case["double"], julia_c=case["julia_c"])
+    helpers.assert_records_equal(rec0, want0.records, case["name"] + " frame 0")
+    m1 = helpers.model_for(cu, case, image=img1)
+    r.renderFast(m1)
+    got = r.downloadRecords()
+    want = oracle.render_advanced(case["fractal"], case["W"], case["H"], img1, case["maxIter"], case["maxSS"], case["flags"],
+                                  img0, want0.records, case["focus"], case["double"], julia_c=case["julia_c"])
+    helpers.assert_records_equal(got, want.records, case["name"] + " frame 1")
+    st = r.stats()
+    assert st.pixel_iterations == want.pixel_iterations
+    assert st.samples == want.samples
+    pal = cu.createDefaultColorPalette()
+    assert (r.outputRGBA() == oracle.compose(case["fractal"], want.records, pal, case["maxSS"])).all()
+
+
+@pytest.mark.skipif(not _have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", cases.ADV_CASES, ids=_ids(cases.ADV_CASES))
+def test_advanced_matches_live_reference(cu, provider, case):
+    img0, img1 = cases.adv_segments(case)
+    r = helpers.open_renderer(cu, provider, case)
+    m0 = helpers.model_for(cu, case, image=img0, maxSS=case["maxSS0"])
+    r.renderQuality(m0)
+    m1 = helpers.model_for(cu, case, image=img1)
+    r.renderFast(m1)
+    got = r.downloadRecords()
+    with oracle.RefRun(case["fractal"], "src") as rr:
+        if case["fractal"] == "julia":
+            rr.write_constant("julia_c", np.array(case["julia_c"], dtype=np.float64).tobytes())
+        rec0 = rr.main(case["W"], case["H"], img0, case["maxIter"], case["maxSS0"], case["flags"], case["double"])
+        want = rr.advanced(case["W"], case["H"], img1, case["maxIter"], case["maxSS"], case["flags"], img0, rec0,
+                           case["focus"], case["double"])
+    helpers.assert_records_equal(got, want, case["name"] + " vs reference kernels")
+
+
+def test_visualise_sample_count(cu, provider):
+    case = cases.MAIN_CASES[2]
+    r = helpers.open_renderer(cu, provider, case)
+    m = helpers.model_for(cu, case)
+    m.visualiseSampleCount = True
+    r.renderQuality(m)
+    want = oracle.render_main(case["fractal"], case["W"], case["H"], case["image"], case["maxIter"], case["maxSS"],
+                              case["flags"], case["double"])
+    pal = cu.createDefaultColorPalette()
+    assert (r.outputRGBA() == oracle.compose(case["fractal"], want.records, pal, case["maxSS"], True)).all()
+    m.visualiseSampleCount = False
+    r.renderQuality(m)
+    assert (r.outputRGBA() == oracle.compose(case["fractal"], want.records, pal, case["maxSS"], False)).all()
+
+
+def test_device_output_mode(cu, provider):
+    case = cases.MAIN_CASES[0]
+    r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+    m = helpers.model_for(cu, case)
+    r.renderQuality(m)
+    want = oracle.render_main(case["fractal"], case["W"], case["H"], case["image"], case["maxIter"], case["maxSS"],
+                              case["flags"], case["double"])
+    assert r.outputRGBADevicePointer() != 0
+    assert (r.outputRGBA() == oracle.compose(case["fractal"], want.records, cu.createDefaultColorPalette(), 1.0)).all()
+
+
+@pytest.mark.parametrize("case", cases.MAIN_CASES + cases.ADV_CASES, ids=_ids(cases.MAIN_CASES + cases.ADV_CASES))
+def test_matches_golden_fixture(cu, provider, case):
+    f = GOLDEN / (case["name"] + ".npz")
+    if not f.exists():
+        pytest.skip("fixture not generated yet")
+    g = np.load(f)
+    r = helpers.open_renderer(cu, provider, case)
+    if "focus" in case:
+        img0, img1 = cases.adv_segments(case)
+        r.renderQuality(helpers.model_for(cu, case, image=img0, maxSS=case["maxSS0"]))
+        r.renderFast(helpers.model_for(cu, case, image=img1))
+    else:
+        r.renderQuality(helpers.model_for(cu, case))
+    got = r.downloadRecords()
+    assert (got["value"].view(np.uint32) == g["src_value"].view(np.uint32)).all()
+    assert (got["weight"].view(np.uint32) == g["src_weight"].view(np.uint32)).all()
+    assert (got["isReused"] == g["src_isReused"]).all()
+    assert (got["weightOfNewSamples"].view(np.uint32) == g["src_wnew"].view(np.uint32)).all()
+    assert (r.outputRGBA() == g["src_rgba"]).all()
