@@ -20,6 +20,9 @@ struct TestImpl {
 };
 
 struct Fractal {
+    /* in the reference build of this module ptxas contracts c.y = rt.y - psy*(py+dy) into one FMA
+     * (SASS of oracle/_ref/test.src.cubin: DFMA R2, R2, -R16, UR6); mandelbrot/julia keep MUL + SUB */
+    static constexpr bool kFusedPlaneY = true;
     template <class Real> using Orbit = ClassicOrbit<TestImpl, Real>;
     static __device__ __forceinline__ uint32_t colorize(const uint32_t *palette, uint32_t len, float result)
     {

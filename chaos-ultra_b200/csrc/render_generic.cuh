@@ -41,13 +41,16 @@ template <class Real> struct frame_map {
     Real lbx, rty, psx, psy;
     __device__ __forceinline__ void init(const chaos_render_args &a);
     /* c = image_left_top + (1,-1) * (pixel + delta) * pixelSize  (:119-124) as nvcc 12.9 compiles it:
-     * c.x = fma(psx, dx + px, lb.x);  c.y = rt.y - rn(psy * (dy + py)) */
+     * c.x = fma(psx, dx + px, lb.x);  c.y = rt.y - rn(psy * (dy + py)).  kFusedY: modules in whose reference build
+     * ptxas contracted that mul+sub into one FMA (the `test` module; see its SASS) say so with
+     * `static constexpr bool kFusedPlaneY = true` */
+    template <bool kFusedY>
     __device__ __forceinline__ void plane_point(uint32_t px, uint32_t py, Real dx, Real dy, Real &cx, Real &cy) const
     {
         Real ax = op::add(dx, op::from_u32(px));
         Real ay = op::add(dy, op::from_u32(py));
         cx = op::fma(psx, ax, lbx);
-        cy = op::sub(rty, op::mul(psy, ay));
+        cy = kFusedY ? op::fma(psy, -ay, rty) : op::sub(rty, op::mul(psy, ay));
     }
 };
 template <> __device__ __forceinline__ void frame_map<double>::init(const chaos_render_args &a)
@@ -62,6 +65,10 @@ template <> __device__ __forceinline__ void frame_map<float>::init(const chaos_r
     psx = __fdiv_rn(__fsub_rn(a.imagef[2], a.imagef[0]), __uint2float_rn(a.width));
     psy = __fdiv_rn(__fsub_rn(a.imagef[3], a.imagef[1]), __uint2float_rn(a.height));
 }
+
+/* does the module declare kFusedPlaneY? (default: no) */
+template <class F, class = void> struct fused_plane_y { static constexpr bool value = false; };
+template <class F> struct fused_plane_y<F, decltype((void)F::kFusedPlaneY)> { static constexpr bool value = F::kFusedPlaneY; };
 
 /* sample offset inside the pixel for sample index i (:103-117).  scf is the float sample
  * budget the call started with (it is NOT the clamped integer count). */
@@ -184,7 +191,7 @@ static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_a
         if (participate) {
             Real dx, dy, cx, cy;
             sample_delta<Real>(i, spr, dx, dy);
-            fm.plane_point(px, py, dx, dy, cx, cy);
+            fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx, dy, cx, cy);
             Orbit o;
             o.start(cx, cy);
             uint32_t it = 0;
@@ -263,7 +270,7 @@ static __device__ __forceinline__ void foveation(uint32_t x0, uint32_t y0, uint3
     float den = __fsub_rn(60.f, thr);
     float k = __frcp_rn(den);
     float q = __fdiv_rn(__fmaf_rn(thr, -0.f, 60.f), den);
-    float lin = __fsub_rn(q, __fmul_rn(k, angle));
+    float lin = __fmaf_rn(-k, angle, q);   /* one FFMA in the reference build (ptxas contracts k*x+q) */
     float rq = __double2float_rn(fmin((double)lin, 1.0));
     advised = __fmul_rn(max_ss, rq);
     inside = false;
@@ -287,7 +294,7 @@ __device__ __forceinline__ void warp_origin<double>(const chaos_render_args &a, 
     double rely = __ddiv_rn(__dsub_rn(planey, a.image_reused[1]), __dsub_rn(a.image_reused[3], a.image_reused[1]));
     float fw = __uint2float_rn(a.width), fh = __uint2float_rn(a.height);
     ox = __fmul_rn(fw, __double2float_rn(relx));
-    oy = __fsub_rn(fh, __fmul_rn(fh, __double2float_rn(rely)));
+    oy = __fmaf_rn(fh, -__double2float_rn(rely), fh);   /* fh - fh*y is one FFMA in the reference build */
 }
 template <>
 __device__ __forceinline__ void warp_origin<float>(const chaos_render_args &a, uint32_t px, uint32_t py, float &ox, float &oy)
@@ -300,7 +307,7 @@ __device__ __forceinline__ void warp_origin<float>(const chaos_render_args &a, u
     float relx = __fdiv_rn(__fsub_rn(planex, a.image_reusedf[0]), __fsub_rn(a.image_reusedf[2], a.image_reusedf[0]));
     float rely = __fdiv_rn(__fsub_rn(planey, a.image_reusedf[1]), __fsub_rn(a.image_reusedf[3], a.image_reusedf[1]));
     ox = __fmul_rn(fw, relx);
-    oy = __fsub_rn(fh, __fmul_rn(fh, rely));
+    oy = __fmaf_rn(fh, -rely, fh);
 }
 
 /* 4-tap filter of value and weight at (ox,oy) (:259-302); only value/weight are read, as one

@@ -78,6 +78,7 @@ ADV_CASES = [
     _a("adv_lowss_f32", "mandelbrot", 160, 96, (-0.748, 0.1), 2.0, 300, 0.6, A | FOV | REUSE | ZOOMING | ZOOM_IN, False, (80, 48)),
     _a("adv_deep_f64", "mandelbrot", 128, 80, (-0.235125, 0.827215), 4.0e-5, 800, 2, A | FOV | REUSE | ZOOMING | ZOOM_IN, True, (64, 40), zooms=3),
     _a("adv_julia_f32", "julia", 160, 96, (0.0, 0.0), 4.0, 300, 2, A | FOV | REUSE | ZOOMING | ZOOM_IN, False, (80, 48), julia_c=(-0.4, 0.6)),
+    _a("adv_test_f32", "test", 96, 64, (0.1, -0.1), 3.0, 10, 3, A | FOV | REUSE | ZOOMING | ZOOM_IN, False, (40, 30), amplifier=7),
     _a("adv_ragged_f64", "mandelbrot", 61, 35, (-0.5, 0.0), 2.0, 200, 3, A | FOV | REUSE | ZOOMING | ZOOM_IN, True, (30, 17)),
 ]
 

@@ -82,13 +82,14 @@ def test_advanced_matches_oracle(cu, provider, case):
     assert not m0.sampleReuseCacheDirty
     rec0 = r.downloadRecords()
     want0 = oracle.render_main(case["fractal"], case["W"], case["H"], img0, case["maxIter"], case["maxSS0"],
-                               case["flags"], case["double"], julia_c=case["julia_c"])
+                               case["flags"], case["double"], julia_c=case["julia_c"], amplifier=case["amplifier"])
     helpers.assert_records_equal(rec0, want0.records, case["name"] + " frame 0")
     m1 = helpers.model_for(cu, case, image=img1)
     r.renderFast(m1)
     got = r.downloadRecords()
     want = oracle.render_advanced(case["fractal"], case["W"], case["H"], img1, case["maxIter"], case["maxSS"], case["flags"],
-                                  img0, want0.records, case["focus"], case["double"], julia_c=case["julia_c"])
+                                  img0, want0.records, case["focus"], case["double"], julia_c=case["julia_c"],
+                                  amplifier=case["amplifier"])
     helpers.assert_records_equal(got, want.records, case["name"] + " frame 1")
     st = r.stats()
     assert st.pixel_iterations == want.pixel_iterations
@@ -110,6 +111,8 @@ def test_advanced_matches_live_reference(cu, provider, case):
     with oracle.RefRun(case["fractal"], "src") as rr:
         if case["fractal"] == "julia":
             rr.write_constant("julia_c", np.array(case["julia_c"], dtype=np.float64).tobytes())
+        if case["fractal"] == "test":
+            rr.write_constant("amplifier", np.array([case["amplifier"]], dtype=np.int32).tobytes())
         rec0 = rr.main(case["W"], case["H"], img0, case["maxIter"], case["maxSS0"], case["flags"], case["double"])
         want = rr.advanced(case["W"], case["H"], img1, case["maxIter"], case["maxSS"], case["flags"], img0, rec0,
                            case["focus"], case["double"])
