@@ -227,6 +227,9 @@ struct chaos_renderer {
     /* module (FractalRenderingModule) */
     CUmodule module = nullptr;
     CUfunction k_main_f = nullptr, k_main_d = nullptr, k_adv_f = nullptr, k_adv_d = nullptr;
+    CUfunction k_main_f_sync = nullptr, k_main_d_sync = nullptr;   /* engine 0 (differential check) */
+    int blocks_main_f_sync = 0, blocks_main_d_sync = 0;
+    uint32_t refill_smem = 0;
     CUfunction k_compose = nullptr, k_undersampled = nullptr, k_debug = nullptr;
     int blocks_main_f = 0, blocks_main_d = 0, blocks_adv_f = 0, blocks_adv_d = 0;
     /* renderer state (CudaFractalRenderer) */
@@ -248,7 +251,8 @@ struct chaos_renderer {
     CUevent ev[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t part_index = 0, part_count = 1, band_rows = 64;
     chaos_stats stats;
-    uint32_t engine = 0;
+    uint32_t engine = 1;           /* 1 = lane-refill scheduler (default), 0 = tile-synchronous */
+    uint32_t block_iters = 0;      /* 0 = choose from maxIterations */
 };
 
 static chaos_status check_renderer(const chaos_renderer *r)
@@ -329,10 +333,10 @@ static void unload_module(chaos_renderer *r)
     if (r->module) { D->p_cuModuleUnload(r->module); r->module = nullptr; }
 }
 
-static int persistent_blocks(chaos_renderer *r, CUfunction fn, int threads)
+static int persistent_blocks(chaos_renderer *r, CUfunction fn, int threads, size_t smem = 0)
 {
     int per_sm = 0;
-    if (D->p_cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != CUDA_SUCCESS || per_sm < 1) per_sm = 1;
+    if (D->p_cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != CUDA_SUCCESS || per_sm < 1) per_sm = 1;
     return per_sm * r->provider->sm_count;   /* a whole number of CTAs per SM: 148 x resident CTAs */
 }
 
@@ -359,6 +363,7 @@ static chaos_status load_module(chaos_renderer *r)
         {"fractalRenderMainFloat", &r->k_main_f}, {"fractalRenderMainDouble", &r->k_main_d},
         {"fractalRenderAdvancedFloat", &r->k_adv_f}, {"fractalRenderAdvancedDouble", &r->k_adv_d},
         {"fractalRenderUnderSampled", &r->k_undersampled}, {"compose", &r->k_compose}, {"debug", &r->k_debug},
+        {"fractalRenderMainFloatSync", &r->k_main_f_sync}, {"fractalRenderMainDoubleSync", &r->k_main_d_sync},
     };
     for (auto &k : fns) {
         chaos_status st = get_function(r, k.name, k.fn);
@@ -372,8 +377,22 @@ static chaos_status load_module(chaos_renderer *r)
         unload_module(r);
         return fail(CHAOS_ERR_CUDA_INIT, "module %s was built for launch contract %u, this library speaks %u; rebuild the module", path.c_str(), abi, CHAOS_MODULE_ABI);
     }
-    r->blocks_main_f = persistent_blocks(r, r->k_main_f, 256);
-    r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256);
+    /* the lane-refill kernels keep their tile slots in dynamic shared memory; the module says how much */
+    CUdeviceptr smem_ptr = 0;
+    size_t smem_size = 0;
+    if (D->p_cuModuleGetGlobal(&smem_ptr, &smem_size, r->module, "CHAOS_REFILL_SMEM") != CUDA_SUCCESS || smem_size != 4 ||
+        D->p_cuMemcpyDtoH(&r->refill_smem, smem_ptr, 4) != CUDA_SUCCESS) {
+        unload_module(r);
+        return fail(CHAOS_ERR_CUDA_INIT, "module %s does not export CHAOS_REFILL_SMEM", path.c_str());
+    }
+    for (CUfunction fn : {r->k_main_f, r->k_main_d}) {
+        CUresult ea = D->p_cuFuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)r->refill_smem);
+        if (ea != CUDA_SUCCESS) { unload_module(r); return fail(CHAOS_ERR_CUDA_INIT, "cannot reserve %u B of shared memory: %s", r->refill_smem, cu_err_name(ea)); }
+    }
+    r->blocks_main_f = persistent_blocks(r, r->k_main_f, 256, r->refill_smem);
+    r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256, r->refill_smem);
+    r->blocks_main_f_sync = persistent_blocks(r, r->k_main_f_sync, 256);
+    r->blocks_main_d_sync = persistent_blocks(r, r->k_main_d_sync, 256);
     r->blocks_adv_f = persistent_blocks(r, r->k_adv_f, 256);
     r->blocks_adv_d = persistent_blocks(r, r->k_adv_d, 256);
     if (r->desc->on_initialize) {
@@ -403,8 +422,11 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     r->desc = desc;
     memset(&r->stats, 0, sizeof r->stats);
     r->stats.struct_size = sizeof(chaos_stats);
+    /* debugging knobs (not part of the reference's interface): engine 0 is the differential check of engine 1 */
     const char *eng = getenv("CHAOS_ENGINE");
-    r->engine = eng ? (uint32_t)atoi(eng) : 0u;
+    if (eng) r->engine = (uint32_t)atoi(eng) ? 1u : 0u;
+    const char *nb = getenv("CHAOS_BLOCK_ITERS");
+    if (nb) r->block_iters = ((uint32_t)atoi(nb) + 3u) & ~3u;
     chaos_status st = load_module(r);
     if (st != CHAOS_OK) { delete r; return st; }
     CUresult e = D->p_cuStreamCreate(&r->stream, CU_STREAM_NON_BLOCKING);
@@ -634,6 +656,9 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
     }
     a->n_tiles = owned_rows * a->tiles_x;
     a->engine = r->engine;
+    /* trips between scheduling points: long enough to amortise a scheduling pass, short enough that a lane whose
+     * orbit ended does not idle long; orbits are at most max_iter long */
+    a->block_iters = r->block_iters ? r->block_iters : 128u;
 }
 
 static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg)
@@ -716,7 +741,10 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
     if (a.n_tiles) {
-        st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, 0, &a);
+        if (r->engine == 0)
+            st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a);
+        else
+            st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, r->refill_smem, &a);
         if (st != CHAOS_OK) return st;
     }
     D->p_cuEventRecord(r->ev[1], r->stream);

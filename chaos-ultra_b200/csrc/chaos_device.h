@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 3u
+#define CHAOS_MODULE_ABI 4u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -59,6 +59,7 @@ struct chaos_render_args {
     uint32_t part_index, part_count, band_tile_rows;
     uint32_t n_tiles;       /* vote tiles owned by this launch */
     uint32_t engine;        /* 0 = tile-synchronous, 1 = lane-refill scheduler */
+    uint32_t block_iters;   /* engine 1: trips between two scheduling points (multiple of 4) */
 };
 
 struct chaos_compose_args {

@@ -13,6 +13,7 @@
  *       static constexpr bool kResumable = true;             // run() may be called repeatedly with growing limits
  *       __device__ void start(Real px, Real py);             // point of the plane to evaluate
  *       __device__ bool run(uint32_t &i, uint32_t limit);    // iterate while i < limit; true = terminated early
+ *       __device__ void force_exact();                       // drop any exactly-equivalent fast form (may be a no-op)
  *       __device__ uint32_t finish(uint32_t i, uint32_t maxIterations) const;
  *                                     // the value `uint escapeTime = computeFractal(..)` would take
  *     };
@@ -75,6 +76,7 @@ template <class Impl, class Real> struct ClassicOrbit {
     Real px, py;
     float result;
     __device__ __forceinline__ void start(Real x, Real y) { px = x; py = y; result = 0.f; }
+    __device__ __forceinline__ void force_exact() {}
     __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit)
     {
         uint32_t trips = 0;

@@ -3,7 +3,7 @@
  * Same results as src/main/cuda/fractals/julia.cu:3-31 (nvcc 12.9, sm_100a); inside points
  * report maxIterations (not 0).  Host half: modules/ModuleJulia.java:9-49.
  */
-#include "../fractal.cuh"
+#include "../quadratic.cuh"
 
 __constant__ double julia_c[2];
 
@@ -11,25 +11,13 @@ struct Fractal {
     template <class Real> struct Orbit {
         typedef real_ops<Real> op;
         static constexpr bool kResumable = true;
-        Real x, y, cx, cy;
+        quadratic_orbit<Real> q;
         __device__ __forceinline__ void start(Real px, Real py)
         {
-            cx = op::from_f64(julia_c[0]); cy = op::from_f64(julia_c[1]);
-            x = px; y = py;
+            q.init(px, py, op::from_f64(julia_c[0]), op::from_f64(julia_c[1]));   /* julia.cu:7 */
         }
-        __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit)
-        {
-            while (i < limit) {
-                Real xx = op::mul(x, x);
-                Real yy = op::mul(y, y);
-                if (!op::below4(op::add(xx, yy))) return true;
-                Real xn = op::add(cx, op::sub(xx, yy));
-                y = op::fma(op::add(x, x), y, cy);
-                x = xn;
-                ++i;
-            }
-            return false;
-        }
+        __device__ __forceinline__ void force_exact() { q.force_exact(); }
+        __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit) { return q.run(i, limit); }
         __device__ __forceinline__ uint32_t finish(uint32_t i, uint32_t) const
         {
             return __float2uint_rz(__uint2float_rn(i));

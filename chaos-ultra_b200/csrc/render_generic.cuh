@@ -30,6 +30,7 @@ __constant__ bool VISUALIZE_SAMPLE_COUNT = false;          /* fractalRendererGen
 __constant__ uint32_t CHAOS_MODULE_ABI_VERSION = CHAOS_MODULE_ABI;
 
 #define CHAOS_FULL_MASK 0xffffffffu
+#define CHAOS_RENDER_THREADS 256
 #define CHAOS_ADAPTIVE_THRESHOLD 10u                       /* :96 adaptiveTreshold */
 
 /* ------------------------------------------------------------------------------------------
@@ -194,6 +195,7 @@ static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_a
             fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx, dy, cx, cy);
             Orbit o;
             o.start(cx, cy);
+            o.force_exact();                                /* engine 0 always runs the reference's own operation sequence */
             uint32_t it = 0;
             o.run(it, a.max_iter);
             uint32_t et = o.finish(it, a.max_iter);
@@ -398,15 +400,26 @@ static __device__ void render_advanced_sync(const chaos_render_args &a)
 /* ==========================================================================================
  * entry points
  * ======================================================================================== */
-#define CHAOS_RENDER_THREADS 256
+#include "render_refill.cuh"
 
 extern "C" __global__ void init() {}
 
+/* engine 1 (default): lane-refill scheduler; dynamic shared memory = CHAOS_REFILL_SMEM_BYTES */
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
-fractalRenderMainFloat(const __grid_constant__ chaos_render_args a) { render_main_sync<float, Fractal>(a); }
+fractalRenderMainFloat(const __grid_constant__ chaos_render_args a) { render_main_refill<float, Fractal>(a); }
 
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
-fractalRenderMainDouble(const __grid_constant__ chaos_render_args a) { render_main_sync<double, Fractal>(a); }
+fractalRenderMainDouble(const __grid_constant__ chaos_render_args a) { render_main_refill<double, Fractal>(a); }
+
+/* engine 0: tile-synchronous, reference operation sequence; the differential check of engine 1 */
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
+fractalRenderMainFloatSync(const __grid_constant__ chaos_render_args a) { render_main_sync<float, Fractal>(a); }
+
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
+fractalRenderMainDoubleSync(const __grid_constant__ chaos_render_args a) { render_main_sync<double, Fractal>(a); }
+
+/* shared-memory need of the engine-1 kernels, read by the host at module load */
+__constant__ uint32_t CHAOS_REFILL_SMEM = (uint32_t)CHAOS_REFILL_SMEM_BYTES;
 
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
 fractalRenderAdvancedFloat(const __grid_constant__ chaos_render_args a) { render_advanced_sync<float, Fractal>(a); }

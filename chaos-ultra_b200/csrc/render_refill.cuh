@@ -1,0 +1,289 @@
+/*
+ * render_refill.cuh -- engine 1 of the main render kernel: persistent warps, work-stealing over vote
+ * tiles, finished lanes refilled with pending orbits.  Included by render_generic.cuh.
+ *
+ * Why: the escape loop runs 1 ... maxIterations trips per sample and neighbouring pixels differ by
+ * orders of magnitude near the set's boundary, so "one warp = one 8x4 tile, all lanes wait for the
+ * slowest" (the reference's mapping, fractalRendererGeneric.cu:36-53) leaves most FP64 lanes idle there.
+ * Here an ORBIT (one sample of one pixel) is the unit of work:
+ *
+ *   - every warp owns CHAOS_REFILL_SLOTS tile slots in shared memory (per pixel: running sum of escape
+ *     times + the first 10 samples, exactly the state sampleTheFractal keeps in registers, :96-127);
+ *   - tiles come from one global cursor (atomicAdd) -- whichever warp is free takes the next tile;
+ *   - lanes iterate in blocks of `block_iters` trips; at the end of a block the lanes whose orbit ended
+ *     are found with a ballot, retire their result into the slot, and take the next pending orbit of ANY
+ *     of the warp's slots (rank among idle lanes -> n-th set bit of the slot's pending mask);
+ *   - a slot's sample round i+1 may only start when all 32 orbits of round i have retired, because
+ *     the reference's early-termination decision (:128-150) is an ALL-vote over the tile.  When the last
+ *     orbit of a round retires the warp evaluates that decision cooperatively, lane p speaking for
+ *     pixel p, with the same predicates and the same votes as engine 0 -- so sample counts, sums and
+ *     therefore every stored record are identical to the reference's.
+ *
+ * With one sample per pixel (round(maxSuperSampling) == 1: configs c1, c4) no vote can change anything,
+ * orbits are independent, and a simpler variant without slots is used (render_main_independent).
+ */
+#ifndef CHAOS_RENDER_REFILL_CUH
+#define CHAOS_RENDER_REFILL_CUH
+
+#define CHAOS_REFILL_SLOTS 6
+#define CHAOS_REFILL_WARPS (CHAOS_RENDER_THREADS / 32)
+
+struct refill_slot_hdr {
+    uint32_t x0, y0;   /* tile origin */
+    uint32_t S;        /* current sample bound (sampleCount) */
+    uint32_t rnd;      /* sample index i of the round in flight */
+    uint32_t pend;     /* pixels whose orbit of this round has not been handed to a lane yet */
+    uint32_t left;     /* orbits of this round not yet retired */
+    uint32_t inb;      /* in-bounds pixels = the voters */
+    uint32_t active;
+};
+
+struct refill_warp_store {
+    uint32_t sum[CHAOS_REFILL_SLOTS][32];
+    float smp[CHAOS_REFILL_SLOTS][CHAOS_ADAPTIVE_THRESHOLD][32];
+    refill_slot_hdr hdr[CHAOS_REFILL_SLOTS];
+};
+
+#define CHAOS_REFILL_SMEM_BYTES (sizeof(refill_warp_store) * CHAOS_REFILL_WARPS)
+
+static __device__ __forceinline__ uint32_t lanemask_lt()
+{
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+static __device__ __forceinline__ void flush_counters(const chaos_render_args &a, unsigned long long iters, unsigned long long nsamples)
+{
+    for (int o = 16; o; o >>= 1) {
+        iters += __shfl_xor_sync(CHAOS_FULL_MASK, iters, o);
+        nsamples += __shfl_xor_sync(CHAOS_FULL_MASK, nsamples, o);
+    }
+    if ((threadIdx.x & 31u) == 0 && nsamples) {
+        atomicAdd(&a.counters->pixel_iterations, iters);
+        atomicAdd(&a.counters->samples, nsamples);
+    }
+}
+
+/* ---- one sample per pixel: independent orbits ------------------------------------------------ */
+template <class Real, class FractalT>
+static __device__ void render_main_independent(const chaos_render_args &a)
+{
+    typedef typename FractalT::template Orbit<Real> Orbit;
+    frame_map<Real> fm;
+    fm.init(a);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t max_iter = a.max_iter;
+    const uint32_t nb = a.block_iters;
+    Real dx0, dy0;
+    sample_delta<Real>(0u, 0.f, dx0, dy0);                  /* sample 0 sits at offset 0/3 */
+
+    Orbit o;
+    uint32_t it = 0, px = 0, py = 0;
+    bool busy = false, first = true, queue_empty = false;
+    uint32_t pend = 0, x0 = 0, y0 = 0;                       /* warp-uniform: the tile being handed out */
+    unsigned long long iters = 0, nsamples = 0;
+
+    for (;;) {
+        bool done = false;
+        if (busy) {
+            uint32_t lim = Orbit::kResumable ? min(it + nb, max_iter) : max_iter;
+            bool ended = o.run(it, lim);
+            done = ended || it >= max_iter;
+        }
+        if (!__any_sync(CHAOS_FULL_MASK, done) && !first) continue;
+        first = false;
+        if (done) {
+            uint32_t et = o.finish(it, max_iter);
+            iters += it;
+            nsamples += 1;
+            /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
+            store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
+            busy = false;
+        }
+        for (;;) {
+            uint32_t idle = __ballot_sync(CHAOS_FULL_MASK, !busy);
+            if (!idle) break;
+            if (!pend) {
+                if (queue_empty) break;
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(&a.counters->next_tile, 1u);
+                t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
+                if (t >= a.n_tiles) { queue_empty = true; break; }
+                tile_origin(a, t, x0, y0);
+                pend = __ballot_sync(CHAOS_FULL_MASK, (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height);
+            }
+            uint32_t rank = __popc(idle & lanemask_lt());
+            bool take = !busy && rank < (uint32_t)__popc(pend);
+            uint32_t mypix = 0;
+            if (take) {
+                mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
+                px = x0 + (mypix & 7u);
+                py = y0 + (mypix >> 3);
+                Real cx, cy;
+                fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx0, dy0, cx, cy);
+                o.start(cx, cy);
+                it = 0;
+                busy = true;
+            }
+            pend &= ~__reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
+        }
+        if (!__any_sync(CHAOS_FULL_MASK, busy)) break;
+    }
+    flush_counters(a, iters, nsamples);
+}
+
+/* ---- general case: sample rounds with tile-wide votes ----------------------------------------- */
+template <class Real, class FractalT>
+static __device__ void render_main_rounds(const chaos_render_args &a, refill_warp_store &ws)
+{
+    typedef typename FractalT::template Orbit<Real> Orbit;
+    constexpr int K = CHAOS_REFILL_SLOTS;
+    frame_map<Real> fm;
+    fm.init(a);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t max_iter = a.max_iter;
+    const uint32_t nb = a.block_iters;
+    const bool adaptive = (a.flags & CHAOS_FLAG_ADAPTIVE_SS) != 0u;
+    const float scf = a.max_ss;                               /* host guarantees >= 1 (:174) */
+    const uint32_t S0 = min(64u, __float2uint_rz(roundf(scf)));
+    const float spr = sqrtf(__fadd_rn(scf, -2.0f));
+
+    if (lane < K) {
+        refill_slot_hdr z = {0, 0, 0, 0, 0, 0, 0, 0};
+        ws.hdr[lane] = z;
+    }
+    __syncwarp();
+
+    Orbit o;
+    uint32_t it = 0, slot = 0, pix = 0;
+    bool busy = false, first = true, queue_empty = false;
+    unsigned long long iters = 0, nsamples = 0;
+
+    for (;;) {
+        /* (1) iterate: up to block_iters trips for every lane that holds an orbit */
+        bool done = false;
+        if (busy) {
+            uint32_t lim = Orbit::kResumable ? min(it + nb, max_iter) : max_iter;
+            bool ended = o.run(it, lim);
+            done = ended || it >= max_iter;
+        }
+        if (!__any_sync(CHAOS_FULL_MASK, done) && !first) continue;
+        first = false;
+
+        /* (2) retire finished orbits into their slot (:125-127) */
+        if (done) {
+            uint32_t et = o.finish(it, max_iter);
+            iters += it;
+            nsamples += 1;
+            uint32_t r = ws.hdr[slot].rnd;
+            ws.sum[slot][pix] += et;
+            if (r < CHAOS_ADAPTIVE_THRESHOLD) ws.smp[slot][r][pix] = __uint2float_rn(et);
+            atomicSub(&ws.hdr[slot].left, 1u);
+            busy = false;
+        }
+        __syncwarp();
+
+        /* (3) rounds that just completed: decide (:128-150), then next round, or finish the tile and take a new one */
+        for (int k = 0; k < K; ++k) {
+            refill_slot_hdr h = ws.hdr[k];
+            __syncwarp();                                   /* every lane has its copy before lane 0 rewrites the header */
+            if (h.active && h.left == 0u && h.pend == 0u) {
+                const uint32_t i = h.rnd;
+                uint32_t S = h.S;
+                const bool part = (h.inb >> lane) & 1u;
+                const uint32_t sum = ws.sum[k][lane];
+                if (decision_entered(adaptive, i, S)) {
+                    vote_preds p = {true, true, true};
+                    if (part) {
+                        float s[CHAOS_ADAPTIVE_THRESHOLD];
+#pragma unroll
+                        for (uint32_t j = 0; j < CHAOS_ADAPTIVE_THRESHOLD; ++j) s[j] = (j <= i) ? ws.smp[k][j][lane] : 0.f;
+                        p = decision_preds(s, i, sum);
+                    }
+                    bool all_eq = __all_sync(CHAOS_FULL_MASK, p.eq);
+                    bool all_lt = __all_sync(CHAOS_FULL_MASK, p.lt);
+                    bool all_le = __all_sync(CHAOS_FULL_MASK, p.le);
+                    S = decision_update(i, S, all_eq, all_lt, all_le);
+                }
+                if (i + 1u < S) {
+                    if (lane == 0) {
+                        ws.hdr[k].rnd = i + 1u;
+                        ws.hdr[k].S = S;
+                        ws.hdr[k].pend = h.inb;
+                        ws.hdr[k].left = __popc(h.inb);
+                    }
+                } else {
+                    if (part)
+                        store_record(record_at(a.out, a.out_pitch, h.x0 + (lane & 7u), h.y0 + (lane >> 3)),
+                                     __uint2float_rn(sum / S), __uint2float_rn(S), 0u, 0.f);
+                    if (lane == 0) ws.hdr[k].active = 0u;
+                    h.active = 0u;
+                }
+            }
+            if (!h.active && !queue_empty) {
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(&a.counters->next_tile, 1u);
+                t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
+                if (t >= a.n_tiles) {
+                    queue_empty = true;
+                } else {
+                    uint32_t x0, y0;
+                    tile_origin(a, t, x0, y0);
+                    uint32_t inb = __ballot_sync(CHAOS_FULL_MASK, (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height);
+                    ws.sum[k][lane] = 0u;
+                    if (lane == 0) {
+                        refill_slot_hdr n = {x0, y0, S0, 0u, inb, (uint32_t)__popc(inb), inb, 1u};
+                        ws.hdr[k] = n;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        /* (4) refill: idle lanes take pending orbits, from any slot */
+        for (int k = 0; k < K; ++k) {
+            uint32_t idle = __ballot_sync(CHAOS_FULL_MASK, !busy);
+            if (!idle) break;
+            const uint32_t pend = ws.hdr[k].pend;
+            if (!pend) continue;
+            uint32_t rank = __popc(idle & lanemask_lt());
+            bool take = !busy && rank < (uint32_t)__popc(pend);
+            uint32_t mypix = 0;
+            if (take) {
+                mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
+                slot = k;
+                pix = mypix;
+                Real dx, dy, cx, cy;
+                sample_delta<Real>(ws.hdr[k].rnd, spr, dx, dy);
+                fm.template plane_point<fused_plane_y<FractalT>::value>(ws.hdr[k].x0 + (mypix & 7u), ws.hdr[k].y0 + (mypix >> 3), dx, dy, cx, cy);
+                o.start(cx, cy);
+                it = 0;
+                busy = true;
+            }
+            uint32_t taken = __reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
+            __syncwarp();
+            if (lane == 0) ws.hdr[k].pend = pend & ~taken;
+            __syncwarp();
+        }
+
+        /* (5) nothing running after a full scheduling pass = no tile left anywhere for this warp */
+        if (!__any_sync(CHAOS_FULL_MASK, busy)) break;
+    }
+    flush_counters(a, iters, nsamples);
+}
+
+template <class Real, class FractalT>
+static __device__ __forceinline__ void render_main_refill(const chaos_render_args &a)
+{
+    extern __shared__ __align__(16) unsigned char chaos_dyn_smem[];
+    const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
+    if (S0 <= 1u) {
+        render_main_independent<Real, FractalT>(a);
+    } else {
+        refill_warp_store *stores = reinterpret_cast<refill_warp_store *>(chaos_dyn_smem);
+        render_main_rounds<Real, FractalT>(a, stores[threadIdx.x >> 5]);
+    }
+}
+
+#endif

@@ -164,3 +164,46 @@ def test_matches_golden_fixture(cu, provider, case):
     assert (got["isReused"] == g["src_isReused"]).all()
     assert (got["weightOfNewSamples"].view(np.uint32) == g["src_wnew"].view(np.uint32)).all()
     assert (r.outputRGBA() == g["src_rgba"]).all()
+
+
+# ---- full-size, size-independent property: the two engines are different programs (engine 0: one warp per tile in
+# ---- lock step, the reference's 7-operation trip; engine 1: lane refill + scaled 6-operation trip) and must agree
+# ---- bit for bit on every record and on the exact pixel-iteration total, at sizes the CPU oracle cannot reach.
+FULL_CASES = [
+    dict(name="full_c2_4k_a8_f64", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.5, 0.0, 2.0, 3840, 2160), maxIter=2000,
+         maxSS=8.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="full_c2ex2_4k_a8_f64", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.235125, 0.827215, 4.0e-5, 3840, 2160),
+         maxIter=3000, maxSS=8.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="full_c4_2k_1s_f64", fractal="mandelbrot", W=2048, H=2048,
+         image=cases.seg(-0.551042868375875, 0.62714332109057, 8.00592947491907e-9, 2048, 2048), maxIter=20000, maxSS=1.0, flags=0,
+         double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="full_c1_1k_1s_f64", fractal="mandelbrot", W=1024, H=1024, image=cases.seg(-0.5, 0.0, 2.0, 1024, 1024), maxIter=500,
+         maxSS=1.0, flags=0, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="full_c5_4k_a8_f64", fractal="julia", W=3840, H=2160, image=cases.seg(0.0, 0.0, 4.0, 3840, 2160), maxIter=900, maxSS=8.0,
+         flags=cases.A, double=True, julia_c=(-0.4, 0.6), amplifier=10),
+    dict(name="full_c2_4k_a5_f32", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.5, 0.0, 2.0, 3840, 2160), maxIter=1000,
+         maxSS=5.0, flags=cases.A, double=False, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="full_ragged_n3_f64", fractal="mandelbrot", W=1531, H=1077, image=cases.seg(-0.748, 0.1, 0.0014, 1531, 1077), maxIter=1600,
+         maxSS=3.0, flags=0, double=True, julia_c=(0.0, 0.0), amplifier=10),
+]
+
+
+@pytest.mark.parametrize("case", FULL_CASES, ids=_ids(FULL_CASES))
+def test_engines_agree_at_full_size(cu, provider, case):
+    out = {}
+    for eng in (0, 1):
+        os.environ["CHAOS_ENGINE"] = str(eng)
+        try:
+            provider.getRenderer("test", False)   # drop the active renderer so the engine choice is re-read
+            r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+            r.renderQuality(helpers.model_for(cu, case))
+            st = r.stats()
+            out[eng] = (r.downloadRecords(), st.pixel_iterations, st.samples, r.outputRGBA())
+        finally:
+            os.environ.pop("CHAOS_ENGINE", None)
+    helpers.assert_records_equal(out[1][0], out[0][0], case["name"] + " engine 1 vs engine 0")
+    assert out[1][1] == out[0][1] and out[1][2] == out[0][2]
+    assert (out[1][3] == out[0][3]).all()
+    # sanity of the exact counter: every sample contributes between 0 and maxIter trips
+    assert out[1][2] >= case["W"] * case["H"]
+    assert out[1][1] <= out[1][2] * case["maxIter"]
