@@ -228,6 +228,10 @@ struct chaos_renderer {
     CUmodule module = nullptr;
     CUfunction k_main_f = nullptr, k_main_d = nullptr, k_adv_f = nullptr, k_adv_d = nullptr;
     CUfunction k_main_f_sync = nullptr, k_main_d_sync = nullptr;   /* engine 0 (differential check) */
+    CUfunction k_classify = nullptr, k_order = nullptr;            /* between the two passes of engine 1 */
+    CUdeviceptr tile_key = 0, tile_order = 0;
+    uint32_t two_pass = 1;
+    uint32_t sync_below_iters = 2048;   /* see render_quality_locked */
     int blocks_main_f_sync = 0, blocks_main_d_sync = 0;
     uint32_t refill_smem = 0;
     CUfunction k_compose = nullptr, k_undersampled = nullptr, k_debug = nullptr;
@@ -364,6 +368,7 @@ static chaos_status load_module(chaos_renderer *r)
         {"fractalRenderAdvancedFloat", &r->k_adv_f}, {"fractalRenderAdvancedDouble", &r->k_adv_d},
         {"fractalRenderUnderSampled", &r->k_undersampled}, {"compose", &r->k_compose}, {"debug", &r->k_debug},
         {"fractalRenderMainFloatSync", &r->k_main_f_sync}, {"fractalRenderMainDoubleSync", &r->k_main_d_sync},
+        {"chaosClassifyTiles", &r->k_classify}, {"chaosOrderTiles", &r->k_order},
     };
     for (auto &k : fns) {
         chaos_status st = get_function(r, k.name, k.fn);
@@ -425,6 +430,10 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     /* debugging knobs (not part of the reference's interface): engine 0 is the differential check of engine 1 */
     const char *eng = getenv("CHAOS_ENGINE");
     if (eng) r->engine = (uint32_t)atoi(eng) ? 1u : 0u;
+    const char *sb = getenv("CHAOS_SYNC_BELOW");
+    if (sb) r->sync_below_iters = (uint32_t)atoi(sb);
+    const char *tp = getenv("CHAOS_TWO_PASS");
+    if (tp) r->two_pass = (uint32_t)atoi(tp) ? 1u : 0u;
     const char *nb = getenv("CHAOS_BLOCK_ITERS");
     if (nb) r->block_iters = ((uint32_t)atoi(nb) + 3u) & ~3u;
     chaos_status st = load_module(r);
@@ -451,6 +460,8 @@ static void free_frame_memory(chaos_renderer *r)
 {
     for (int i = 0; i < 2; ++i) if (r->buf[i].ptr) { D->p_cuMemFree(r->buf[i].ptr); r->buf[i].ptr = 0; r->buf[i].pitch = 0; }
     if (r->palette) { D->p_cuMemFree(r->palette); r->palette = 0; }
+    if (r->tile_key) { D->p_cuMemFree(r->tile_key); r->tile_key = 0; }
+    if (r->tile_order) { D->p_cuMemFree(r->tile_order); r->tile_order = 0; }
     if (r->rgba_host) { D->p_cuMemFreeHost(r->rgba_host); r->rgba_host = nullptr; r->rgba_dev = 0; }
     if (r->rgba_dev) { D->p_cuMemFree(r->rgba_dev); r->rgba_dev = 0; }
 }
@@ -475,7 +486,10 @@ extern "C" chaos_status chaos_initialize(chaos_renderer *r, uint32_t width, uint
         CUresult e = D->p_cuMemAllocPitch(&r->buf[i].ptr, &r->buf[i].pitch, (size_t)width * 16u, height, 16);
         if (e != CUDA_SUCCESS) { free_frame_memory(r); return fail(CHAOS_ERR_CUDA, "cuMemAllocPitch(%ux%u) failed: %s", width, height, cu_err_name(e)); }
     }
-    CUresult e = D->p_cuMemAlloc(&r->palette, (size_t)palette_len * 4u);
+    const size_t all_tiles = (size_t)((width + 7u) / 8u) * ((height + 3u) / 4u);
+    CUresult e = D->p_cuMemAlloc(&r->tile_key, all_tiles * 4u);
+    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->tile_order, all_tiles * 4u);
+    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->palette, (size_t)palette_len * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemcpyHtoD(r->palette, palette_rgba, (size_t)palette_len * 4u);
     size_t frame_bytes = (size_t)width * height * 4u;
     if (e == CUDA_SUCCESS) {
@@ -655,6 +669,8 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
             owned_rows += std::min(a->band_tile_rows, a->tile_rows - b * a->band_tile_rows);
     }
     a->n_tiles = owned_rows * a->tiles_x;
+    a->tile_key = (uint32_t *)r->tile_key;
+    a->tile_order = (uint32_t *)r->tile_order;
     a->engine = r->engine;
     /* trips between scheduling points: long enough to amortise a scheduling pass, short enough that a lane whose
      * orbit ended does not idle long; orbits are at most max_iter long */
@@ -741,10 +757,28 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
     if (a.n_tiles) {
-        if (r->engine == 0)
+        CUfunction k1 = dbl ? r->k_main_d : r->k_main_f;
+        const int b1 = dbl ? r->blocks_main_d : r->blocks_main_f;
+        const uint32_t S0 = (uint32_t)std::min(64.0f, roundf(m->max_super_sampling));
+        /* Short orbits (low iteration limit) with several samples: the per-orbit scheduling work of the refill
+         * engine costs more than the divergence it removes, so those frames take the tile-synchronous kernel
+         * (same arithmetic, same records).  CHAOS_ENGINE=0 forces it, with the reference's 7-operation trip. */
+        const bool sync_kernel = r->engine == 0 || (S0 >= 2u && a.max_iter < r->sync_below_iters);
+        a.force_exact = r->engine == 0 ? 1u : 0u;
+        if (sync_kernel) {
             st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a);
-        else
-            st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, r->refill_smem, &a);
+        } else if (S0 >= 2u && r->two_pass) {
+            /* pass A: sample 0 of every pixel; classify + order: expected-longest tiles first; pass B: the other rounds */
+            const int cap = r->provider->sm_count * 8;
+            a.phase = 1u;
+            st = launch(r, k1, b1, 256, r->refill_smem, &a);
+            if (st == CHAOS_OK) st = launch(r, r->k_classify, (int)std::min<uint64_t>((a.n_tiles + 7u) / 8u, (uint64_t)cap), 256, 0, &a);
+            if (st == CHAOS_OK) st = launch(r, r->k_order, (int)std::min<uint64_t>((a.n_tiles + 255u) / 256u, (uint64_t)cap), 256, 0, &a);
+            a.phase = 2u;
+            if (st == CHAOS_OK) st = launch(r, k1, b1, 256, r->refill_smem, &a);
+        } else {
+            st = launch(r, k1, b1, 256, r->refill_smem, &a);
+        }
         if (st != CHAOS_OK) return st;
     }
     D->p_cuEventRecord(r->ev[1], r->stream);

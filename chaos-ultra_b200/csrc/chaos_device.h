@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 4u
+#define CHAOS_MODULE_ABI 6u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -30,12 +30,14 @@ struct chaos_pixel_info {
 #define CHAOS_FLAG_ZOOMING_IN (1u << 5)
 
 /* device counters, one block per renderer (zeroed by the host before each render call) */
+#define CHAOS_COST_BUCKETS 37
 struct chaos_counters {
     unsigned int next_tile;             /* work-stealing cursor over vote tiles */
-    unsigned int next_tile_b;           /* second cursor (advanced kernel, sampling pass) */
+    unsigned int next_tile_b;           /* second cursor (pass B of a two-pass render) */
     unsigned long long pixel_iterations;
     unsigned long long samples;
-    unsigned int pad[2];
+    unsigned int bucket_count[CHAOS_COST_BUCKETS + 3];  /* tiles per cost class (chaosClassifyTiles) */
+    unsigned int bucket_cursor[CHAOS_COST_BUCKETS + 3]; /* fill position per class (chaosOrderTiles) */
 };
 
 struct chaos_render_args {
@@ -58,7 +60,11 @@ struct chaos_render_args {
     /* multi-GPU row-band partition: this launch covers bands b with b % part_count == part_index */
     uint32_t part_index, part_count, band_tile_rows;
     uint32_t n_tiles;       /* vote tiles owned by this launch */
+    uint32_t *tile_key;     /* [n_tiles] cost class of each tile after pass A */
+    uint32_t *tile_order;   /* [n_tiles] tiles sorted by descending expected cost: the order pass B takes them in */
+    uint32_t phase;         /* 0 = whole render in one launch; 1 = pass A (sample 0 of every pixel); 2 = pass B (the rest) */
     uint32_t engine;        /* 0 = tile-synchronous, 1 = lane-refill scheduler */
+    uint32_t force_exact;   /* 1 = always the reference's 7-operation trip (differential check) */
     uint32_t block_iters;   /* engine 1: trips between two scheduling points (multiple of 4) */
 };
 

@@ -195,7 +195,7 @@ static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_a
             fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx, dy, cx, cy);
             Orbit o;
             o.start(cx, cy);
-            o.force_exact();                                /* engine 0 always runs the reference's own operation sequence */
+            if (a.force_exact) o.force_exact();             /* engine 0 as differential check: the reference's own operation sequence */
             uint32_t it = 0;
             o.run(it, a.max_iter);
             uint32_t et = o.finish(it, a.max_iter);
@@ -405,10 +405,10 @@ static __device__ void render_advanced_sync(const chaos_render_args &a)
 extern "C" __global__ void init() {}
 
 /* engine 1 (default): lane-refill scheduler; dynamic shared memory = CHAOS_REFILL_SMEM_BYTES */
-extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
 fractalRenderMainFloat(const __grid_constant__ chaos_render_args a) { render_main_refill<float, Fractal>(a); }
 
-extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
 fractalRenderMainDouble(const __grid_constant__ chaos_render_args a) { render_main_refill<double, Fractal>(a); }
 
 /* engine 0: tile-synchronous, reference operation sequence; the differential check of engine 1 */
@@ -417,6 +417,10 @@ fractalRenderMainFloatSync(const __grid_constant__ chaos_render_args a) { render
 
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
 fractalRenderMainDoubleSync(const __grid_constant__ chaos_render_args a) { render_main_sync<double, Fractal>(a); }
+
+/* between pass A and pass B of a two-pass render (render_refill.cuh) */
+extern "C" __global__ void __launch_bounds__(256) chaosClassifyTiles(const __grid_constant__ chaos_render_args a) { classify_tiles(a); }
+extern "C" __global__ void __launch_bounds__(256) chaosOrderTiles(const __grid_constant__ chaos_render_args a) { order_tiles(a); }
 
 /* shared-memory need of the engine-1 kernels, read by the host at module load */
 __constant__ uint32_t CHAOS_REFILL_SMEM = (uint32_t)CHAOS_REFILL_SMEM_BYTES;

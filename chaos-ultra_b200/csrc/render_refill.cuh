@@ -21,11 +21,22 @@
  *
  * With one sample per pixel (round(maxSuperSampling) == 1: configs c1, c4) no vote can change anything,
  * orbits are independent, and a simpler variant without slots is used (render_main_independent).
+ *
+ * Two-pass order (the default when more than one sample is allowed).  A tile's rounds are sequential, so a
+ * tile with one never-escaping pixel and 8 rounds has a critical path of 8 x maxIterations dependent trips no
+ * matter how many lanes are free; if such a tile is started late the whole GPU waits for it.  Sample 0 of
+ * every pixel needs no vote (the decision block is not entered at i = 0 when S >= 2), so:
+ *   pass A  = sample 0 of every pixel as independent orbits (render_main_independent, kProbe): perfect refill,
+ *             leaves (escape time, trip count) in the pixel's output record;
+ *   classify/order = every tile gets a cost class from pass A's trip counts (never-escaping mixed tiles first,
+ *             then all-inside tiles, then by log2 of the longest orbit) and a counting sort builds the order;
+ *   pass B  = rounds 1.. of every tile, slots pre-loaded from the records, tiles taken longest-expected-first.
+ * Nothing is computed twice and no result depends on the order, only the tail of the launch does.
  */
 #ifndef CHAOS_RENDER_REFILL_CUH
 #define CHAOS_RENDER_REFILL_CUH
 
-#define CHAOS_REFILL_SLOTS 6
+#define CHAOS_REFILL_SLOTS 4
 #define CHAOS_REFILL_WARPS (CHAOS_RENDER_THREADS / 32)
 
 struct refill_slot_hdr {
@@ -66,7 +77,7 @@ static __device__ __forceinline__ void flush_counters(const chaos_render_args &a
 }
 
 /* ---- one sample per pixel: independent orbits ------------------------------------------------ */
-template <class Real, class FractalT>
+template <class Real, class FractalT, bool kProbe>
 static __device__ void render_main_independent(const chaos_render_args &a)
 {
     typedef typename FractalT::template Orbit<Real> Orbit;
@@ -97,8 +108,10 @@ static __device__ void render_main_independent(const chaos_render_args &a)
             uint32_t et = o.finish(it, max_iter);
             iters += it;
             nsamples += 1;
-            /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
-            store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
+            if (kProbe)   /* pass A: park (escape time, trips) in the record for chaosClassifyTiles and pass B */
+                store_record(record_at(a.out, a.out_pitch, px, py), __uint_as_float(et), __uint_as_float(it), 0u, 0.f);
+            else          /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
+                store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
             busy = false;
         }
         for (;;) {
@@ -134,7 +147,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
 }
 
 /* ---- general case: sample rounds with tile-wide votes ----------------------------------------- */
-template <class Real, class FractalT>
+template <class Real, class FractalT, bool kResume>
 static __device__ void render_main_rounds(const chaos_render_args &a, refill_warp_store &ws)
 {
     typedef typename FractalT::template Orbit<Real> Orbit;
@@ -223,17 +236,30 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
             }
             if (!h.active && !queue_empty) {
                 uint32_t t = 0;
-                if (lane == 0) t = atomicAdd(&a.counters->next_tile, 1u);
+                if (lane == 0) {
+                    t = atomicAdd(kResume ? &a.counters->next_tile_b : &a.counters->next_tile, 1u);
+                    if (kResume && t < a.n_tiles) t = a.tile_order[t];      /* longest expected first */
+                    else if (kResume) t = 0xffffffffu;
+                }
                 t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
                 if (t >= a.n_tiles) {
                     queue_empty = true;
                 } else {
                     uint32_t x0, y0;
                     tile_origin(a, t, x0, y0);
-                    uint32_t inb = __ballot_sync(CHAOS_FULL_MASK, (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height);
-                    ws.sum[k][lane] = 0u;
+                    const bool in = (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height;
+                    uint32_t inb = __ballot_sync(CHAOS_FULL_MASK, in);
+                    uint32_t first_round = 0u;
+                    if (kResume) {           /* sample 0 was taken by pass A; its escape time sits in the record */
+                        uint32_t et0 = in ? __float_as_uint(record_at(a.out, a.out_pitch, x0 + (lane & 7u), y0 + (lane >> 3))->value) : 0u;
+                        ws.sum[k][lane] = et0;
+                        ws.smp[k][0][lane] = __uint2float_rn(et0);
+                        first_round = 1u;
+                    } else {
+                        ws.sum[k][lane] = 0u;
+                    }
                     if (lane == 0) {
-                        refill_slot_hdr n = {x0, y0, S0, 0u, inb, (uint32_t)__popc(inb), inb, 1u};
+                        refill_slot_hdr n = {x0, y0, S0, first_round, inb, (uint32_t)__popc(inb), inb, 1u};
                         ws.hdr[k] = n;
                     }
                 }
@@ -278,11 +304,52 @@ static __device__ __forceinline__ void render_main_refill(const chaos_render_arg
 {
     extern __shared__ __align__(16) unsigned char chaos_dyn_smem[];
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
-    if (S0 <= 1u) {
-        render_main_independent<Real, FractalT>(a);
-    } else {
-        refill_warp_store *stores = reinterpret_cast<refill_warp_store *>(chaos_dyn_smem);
-        render_main_rounds<Real, FractalT>(a, stores[threadIdx.x >> 5]);
+    refill_warp_store *stores = reinterpret_cast<refill_warp_store *>(chaos_dyn_smem);
+    if (S0 <= 1u) render_main_independent<Real, FractalT, false>(a);
+    else if (a.phase == 1u) render_main_independent<Real, FractalT, true>(a);
+    else if (a.phase == 2u) render_main_rounds<Real, FractalT, true>(a, stores[threadIdx.x >> 5]);
+    else render_main_rounds<Real, FractalT, false>(a, stores[threadIdx.x >> 5]);
+}
+
+
+/* ---- cost classes between the two passes ------------------------------------------------------ */
+/* One warp per tile.  Expected critical path of the tile's remaining rounds, from pass A's trip counts:
+ * longest orbit x (S0 - 1) rounds if the pixels disagree (the tile will probably use its whole sample budget),
+ * x 1 if all 32 agree (the i == 1 vote will most likely end it after one more round).  class = 36 - floor(log2(est)):
+ * class 0 is taken first by pass B. */
+static __device__ void classify_tiles(const chaos_render_args &a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < a.n_tiles; t += warps) {
+        uint32_t x0, y0;
+        tile_origin(a, t, x0, y0);
+        const uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
+        const bool in = px < a.width && py < a.height;
+        const uint32_t trips = in ? __float_as_uint(record_at(a.out, a.out_pitch, px, py)->weight) : 0u;
+        const uint32_t tmax = __reduce_max_sync(CHAOS_FULL_MASK, trips);
+        const uint32_t tmin = __reduce_min_sync(CHAOS_FULL_MASK, in ? trips : 0xffffffffu);
+        const unsigned long long est = (unsigned long long)(tmax | 1u) * (tmax == tmin ? 1u : (S0 > 1u ? S0 - 1u : 1u));
+        const uint32_t key = (uint32_t)__clzll((long long)est) - 27u;      /* est < 2^37: clzll in [27,63] -> key in [0,36] */
+        if (lane == 0) {
+            a.tile_key[t] = key;
+            atomicAdd(&a.counters->bucket_count[key], 1u);
+        }
+    }
+}
+/* counting-sort scatter: one thread per tile */
+static __device__ void order_tiles(const chaos_render_args &a)
+{
+    __shared__ uint32_t base[CHAOS_COST_BUCKETS];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (uint32_t j = 0; j < CHAOS_COST_BUCKETS; ++j) { base[j] = acc; acc += a.counters->bucket_count[j]; }
+    }
+    __syncthreads();
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_tiles; t += gridDim.x * blockDim.x) {
+        const uint32_t key = a.tile_key[t];
+        a.tile_order[base[key] + atomicAdd(&a.counters->bucket_cursor[key], 1u)] = t;
     }
 }
 
