@@ -52,6 +52,10 @@ WORKLOADS = {
                   flags=A, double=True, desc="mandelbrot 3840x2160 maxIter 10000 adaptive SS (maxSS 8) FP64, 'M ex 2'"),
     "c2f32": dict(fractal="mandelbrot", W=3840, H=2160, center=(-0.5, 0.0), zoom=2.0, maxIter=10000, maxSS=8.0, flags=A,
                   double=False, desc="mandelbrot 3840x2160 maxIter 10000 adaptive SS (maxSS 8) FP32, full set"),
+    "c3": dict(kind="zoom", fractal="mandelbrot", W=3840, H=2160, center=(-0.748, 0.1), zoom=2.0, maxIter=1600, maxSS=2.0,
+               flags=A | FOV | REUSE | ZOOMING | ZOOM_IN, double=None, focus=(1920, 1080),
+               desc="zoom sequence 3840x2160: frame 0 quality, then fast frames (sample reuse + foveation + compose), "
+                    "zoomAt(centre, in) per frame, mandelbrot maxIter 1600 maxSS 2, precision by the reference's rule"),
     "c4": dict(fractal="mandelbrot", W=8192, H=8192, center=(-0.551042868375875, 0.62714332109057), zoom=8.00592947491907e-9,
                maxIter=200000, maxSS=1.0, flags=0, double=True, desc="mandelbrot 8192x8192 maxIter 200000 FP64 1 sample, 'M ex 5'"),
     "c5": dict(fractal="julia", W=3840, H=2160, center=(0.0, 0.0), zoom=4.0, maxIter=900, maxSS=8.0, flags=A, double=True,
@@ -197,22 +201,11 @@ def run_ours(args, wl, rank, world, local):
         def __init__(self, ptr):
             self.__cuda_array_interface__ = {"shape": (H, W), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
+    part = importlib.import_module("chaos-ultra_b200.partition")
+
     def gather_to_rank0(frame):
-        """real exchange step of the multi-GPU path: every rank sends the row bands it rendered to rank 0"""
-        ops = []
-        nb = (H + band_rows - 1) // band_rows
-        for b in range(nb):
-            owner = b % world
-            if owner == 0:
-                continue
-            rows = frame[b * band_rows:min(H, (b + 1) * band_rows)]
-            if rank == 0:
-                ops.append(dist.P2POp(dist.irecv, rows, owner))
-            elif rank == owner:
-                ops.append(dist.P2POp(dist.isend, rows, 0))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        """the one exchange step of the multi-GPU path: composed RGBA row bands -> rank 0, NCCL send/recv over NVLink"""
+        part.gather_bands(frame, rank, world, band_rows, dist)
 
     def timed_loop(mode, steps, warmup, sampler=None):
         if r.getState() == cu.STATE_READY_TO_RENDER:
@@ -402,6 +395,165 @@ def run_reference(args, wl, rank, world, local):
     return base
 
 
+# ---------------------------------------------------------------------------------------------------------
+# config c3: real-time zoom sequence (fast frames: reuse/reprojection + foveated resampling + compose)
+# ---------------------------------------------------------------------------------------------------------
+HBM_BYTES_PER_PIXEL_FAST_FRAME = 52   # reuse pass 16 R + 16 W, compose 16 R + 4 W
+
+
+def hbm_peak_gbs():
+    try:
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth on this pool)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s from B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def zoom_segments(cu, wl, n):
+    m = cu.RenderingModel(canvasWidth=wl["W"], canvasHeight=wl["H"])
+    m.setPlaneSegmentFromCenter(wl["center"][0], wl["center"][1], wl["zoom"])
+    segs = [list(m.planeSegment)]
+    for _ in range(n - 1):
+        m.zoomAt(wl["focus"], True)
+        segs.append(list(m.planeSegment))
+    return segs
+
+
+def zoom_model(cu, wl, segment):
+    m = cu.RenderingModel(canvasWidth=wl["W"], canvasHeight=wl["H"])
+    m.planeSegment = list(segment)
+    m.maxIterations = wl["maxIter"]
+    m.maxSuperSampling = wl["maxSS"]
+    fl = wl["flags"]
+    m.useAdaptiveSuperSampling = bool(fl & A)
+    m.useFoveatedRendering = bool(fl & FOV)
+    m.useSampleReuse = bool(fl & REUSE)
+    m.zooming = bool(fl & ZOOMING)
+    m.zoomingIn = bool(fl & ZOOM_IN)
+    m.mouseFocus = tuple(wl["focus"])
+    return m
+
+
+def run_zoom_ours(args, wl, rank, world, local):
+    """every rank renders the whole sequence (the reuse pass needs the previous frame around every pixel; the
+    sequence is not partitioned in this round): N > 1 = independent replicas, scaling weak"""
+    import torch
+    cu = importlib.import_module("chaos-ultra_b200")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H = wl["W"], wl["H"]
+    prov = cu.CudaFractalRendererProvider(device=local)
+    r = prov.getRenderer(wl["fractal"], False)
+    segs = zoom_segments(cu, wl, 1 + args.warmup + args.steps)
+
+    def loop(mode, sampler=None):
+        if r.getState() == cu.STATE_READY_TO_RENDER:
+            r.freeRenderingResources()
+        r.initializeRendering(W, H, None, mode)
+        m = zoom_model(cu, wl, segs[0])
+        m.maxSuperSampling = max(1.0, wl["maxSS"])
+        r.renderQuality(m)                                  # frame 0
+        acc = dict(iters=0, launches=0, render_ms=0.0, compose_ms=0.0, reuse_ms=0.0, precisions=set())
+        for f in range(1, 1 + args.warmup + args.steps):
+            if f == 1 + args.warmup:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                if sampler is not None:
+                    sampler.start()
+                t0 = time.perf_counter()
+                acc = dict(iters=0, launches=0, render_ms=0.0, compose_ms=0.0, reuse_ms=0.0, precisions=set())
+            m = zoom_model(cu, wl, segs[f])
+            r.renderFast(m)
+            st = r.stats()
+            acc["iters"] += st.pixel_iterations
+            acc["launches"] += st.kernel_launches
+            acc["render_ms"] += st.render_ms
+            acc["compose_ms"] += st.compose_ms
+            acc["reuse_ms"] += st.reuse_ms
+            acc["precisions"].add(m.floatingPointPrecision)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        acc["seconds"] = time.perf_counter() - t0
+        acc["clocks"] = sampler.stop() if sampler is not None else None
+        if world > 1:
+            t = torch.tensor([acc["seconds"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            acc["seconds"] = t.item()
+        return acc
+
+    dev = loop(cu.OUTPUT_DEVICE, ClockSampler(local) if rank == 0 else None)
+    e2e = loop(cu.OUTPUT_HOST)
+    out = None
+    if rank == 0:
+        px = W * H
+        peak, peak_src = hbm_peak_gbs()
+        mem_s = (dev["reuse_ms"] + dev["compose_ms"]) * 1e-3 / args.steps   # the two memory passes; the sampling pass is compute
+        achieved = HBM_BYTES_PER_PIXEL_FAST_FRAME * px / mem_s / 1e9
+        out = {
+            "metric": "4K frames/s (zoom sequence, fast frames)", "value": world * args.steps / dev["seconds"], "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev["seconds"] * 1e3 / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if dev["precisions"] == {0} else ("f64" if 0 not in dev["precisions"] else "f32+f64"), "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H, "max_iterations": wl["maxIter"],
+                       "max_super_sampling": wl["maxSS"], "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world,
+                       "pixel_iterations_per_step": dev["iters"] // args.steps,
+                       "l2": "each frame reads the previous frame's 133 MB record buffer and writes another 133 MB one (> 126 MB L2)"},
+            "e2e": {"value": world * args.steps / e2e["seconds"], "unit": "frames/s", "h2d_bytes_per_step": 512,
+                    "d2h_bytes_per_step": px * 4 + 32, "ms_per_step": e2e["seconds"] * 1e3 / args.steps,
+                    "note": "chaos_render_fast through the C ABI, composed RGBA8 frame written to pinned host memory every frame"},
+            "gpu_launches": dev["launches"], "clocks": dev["clocks"],
+            "device_ms_per_step": {"reuse_pass": dev["reuse_ms"] / args.steps, "sample_pass": (dev["render_ms"] - dev["reuse_ms"]) / args.steps,
+                                   "compose_kernel": dev["compose_ms"] / args.steps},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "chaosReusePass* + compose (the two memory passes of a fast frame)", "peak_source": peak_src,
+                         "algorithmic_bytes": "%d B/pixel x %d pixels per frame (reuse 16 R + 16 W, compose 16 R + 4 W)" % (HBM_BYTES_PER_PIXEL_FAST_FRAME, px),
+                         "note": "the foveal disc and the pixels without history are resampled by a separate compute-bound launch (sample_pass), not part of this figure"},
+        }
+    r.close()
+    prov.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def run_zoom_reference(args, wl, rank, world, local):
+    if rank != 0:
+        return None
+    import oracle
+    cu = importlib.import_module("chaos-ultra_b200")
+    W, H = wl["W"], wl["H"]
+    n = 1 + args.warmup + args.steps
+    segs = zoom_segments(cu, wl, n)
+    doubles = [oracle.choose_precision(sg, W, H) != 0 for sg in segs]
+    pal = oracle.default_palette()
+    with oracle.RefRun(wl["fractal"], args.ref_kind) as rr:
+        sampler = ClockSampler(0)
+        sampler.start()
+        wall, adv, comp, _ = rr.zoom(W, H, segs, doubles, wl["maxIter"], wl["maxSS"], wl["flags"], wl["focus"], pal, args.warmup, args.steps, True)
+        clocks = sampler.stop()
+        wall_d, adv_d, comp_d, _ = rr.zoom(W, H, segs, doubles, wl["maxIter"], wl["maxSS"], wl["flags"], wl["focus"], pal, args.warmup, args.steps, False)
+    peak, peak_src = hbm_peak_gbs()
+    achieved = HBM_BYTES_PER_PIXEL_FAST_FRAME * W * H / ((adv_d + comp_d) * 1e-3 / args.steps) / 1e9
+    return {"metric": "4K frames/s (zoom sequence, fast frames)", "value": args.steps / (wall_d * 1e-3), "unit": "frames/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_d / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if all(doubles) else ("f32" if not any(doubles) else "f32+f64"), "data": "synthetic",
+            "impl": "reference", "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H},
+            "e2e": {"value": args.steps / (wall * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 4,
+                    "ms_per_step": wall / args.steps},
+            "gpu_launches": 2 * args.steps, "clocks": clocks,
+            "device_ms_per_step": {"reuse_kernel": adv_d / args.steps, "compose_kernel": comp_d / args.steps},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src},
+            "cpu_baseline": {"value": args.steps / (wall * 1e-3), "unit": "frames/s", "cores": 0, "kind": "reference",
+                             "sample": "NOT a CPU run: the reference's own CUDA kernels (oracle/_ref/%s.%s.cubin) on the same B200 with the "
+                                       "Java host's fast-frame sequence (CudaFractalRenderer.renderFast); the reference ships no CPU path"
+                                       % (wl["fractal"], args.ref_kind)}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -418,10 +570,11 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank, world, local = dist_env()
     wl = WORKLOADS[args.workload]
+    zoom = wl.get("kind") == "zoom"
     if args.impl == "reference":
-        out = run_reference(args, wl, rank, world, local)
+        out = (run_zoom_reference if zoom else run_reference)(args, wl, rank, world, local)
     else:
-        out = run_ours(args, wl, rank, world, local)
+        out = (run_zoom_ours if zoom else run_ours)(args, wl, rank, world, local)
     if rank == 0 and out is not None:
         print(json.dumps(out))
 

@@ -111,6 +111,8 @@ class _Stats(C.Structure):
         ("kernel_launches", C.c_uint32),
         ("render_ms", C.c_float),
         ("compose_ms", C.c_float),
+        ("reuse_ms", C.c_float),
+        ("reserved", C.c_uint32),
         ("pixel_iterations", C.c_uint64),
         ("samples", C.c_uint64),
         ("launches_total", C.c_uint64),
@@ -279,6 +281,7 @@ class RenderStats:
     kernel_launches: int
     render_ms: float
     compose_ms: float
+    reuse_ms: float
     pixel_iterations: int
     samples: int
     launches_total: int
@@ -436,7 +439,7 @@ class CudaFractalRenderer:
         s = _Stats()
         s.struct_size = C.sizeof(_Stats)
         _check(self._lib, self._lib.chaos_get_stats(self._h, C.byref(s)))
-        return RenderStats(s.kernel_launches, s.render_ms, s.compose_ms, s.pixel_iterations, s.samples, s.launches_total)
+        return RenderStats(s.kernel_launches, s.render_ms, s.compose_ms, s.reuse_ms, s.pixel_iterations, s.samples, s.launches_total)
 
     def __enter__(self):
         return self

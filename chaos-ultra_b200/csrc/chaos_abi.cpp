@@ -229,6 +229,8 @@ struct chaos_renderer {
     CUfunction k_main_f = nullptr, k_main_d = nullptr, k_adv_f = nullptr, k_adv_d = nullptr;
     CUfunction k_main_f_sync = nullptr, k_main_d_sync = nullptr;   /* engine 0 (differential check) */
     CUfunction k_classify = nullptr, k_order = nullptr;            /* between the two passes of engine 1 */
+    CUfunction k_reuse_f = nullptr, k_reuse_d = nullptr;           /* pass R of a fast frame */
+    int blocks_reuse_f = 0, blocks_reuse_d = 0;
     CUdeviceptr tile_key = 0, tile_order = 0;
     uint32_t two_pass = 1;
     uint32_t sync_below_iters = 2048;   /* see render_quality_locked */
@@ -252,7 +254,7 @@ struct chaos_renderer {
     CUdeviceptr counters = 0;
     chaos_counters *counters_host = nullptr; /* pinned staging for the read-back */
     CUstream stream = nullptr;
-    CUevent ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    CUevent ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   /* render start/end, compose start/end, pass boundary */
     uint32_t part_index = 0, part_count = 1, band_rows = 64;
     chaos_stats stats;
     uint32_t engine = 1;           /* 1 = lane-refill scheduler (default), 0 = tile-synchronous */
@@ -369,6 +371,7 @@ static chaos_status load_module(chaos_renderer *r)
         {"fractalRenderUnderSampled", &r->k_undersampled}, {"compose", &r->k_compose}, {"debug", &r->k_debug},
         {"fractalRenderMainFloatSync", &r->k_main_f_sync}, {"fractalRenderMainDoubleSync", &r->k_main_d_sync},
         {"chaosClassifyTiles", &r->k_classify}, {"chaosOrderTiles", &r->k_order},
+        {"chaosReusePassFloat", &r->k_reuse_f}, {"chaosReusePassDouble", &r->k_reuse_d},
     };
     for (auto &k : fns) {
         chaos_status st = get_function(r, k.name, k.fn);
@@ -398,6 +401,8 @@ static chaos_status load_module(chaos_renderer *r)
     r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256, r->refill_smem);
     r->blocks_main_f_sync = persistent_blocks(r, r->k_main_f_sync, 256);
     r->blocks_main_d_sync = persistent_blocks(r, r->k_main_d_sync, 256);
+    r->blocks_reuse_f = persistent_blocks(r, r->k_reuse_f, 256);
+    r->blocks_reuse_d = persistent_blocks(r, r->k_reuse_d, 256);
     r->blocks_adv_f = persistent_blocks(r, r->k_adv_f, 256);
     r->blocks_adv_d = persistent_blocks(r, r->k_adv_d, 256);
     if (r->desc->on_initialize) {
@@ -439,7 +444,7 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     chaos_status st = load_module(r);
     if (st != CHAOS_OK) { delete r; return st; }
     CUresult e = D->p_cuStreamCreate(&r->stream, CU_STREAM_NON_BLOCKING);
-    for (int i = 0; i < 4 && e == CUDA_SUCCESS; ++i) e = D->p_cuEventCreate(&r->ev[i], CU_EVENT_DEFAULT);
+    for (int i = 0; i < 5 && e == CUDA_SUCCESS; ++i) e = D->p_cuEventCreate(&r->ev[i], CU_EVENT_DEFAULT);
     if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->counters, sizeof(chaos_counters));
     if (e == CUDA_SUCCESS) e = D->p_cuMemHostAlloc((void **)&r->counters_host, sizeof(chaos_counters), 0);
     if (e != CUDA_SUCCESS) {
@@ -531,7 +536,7 @@ extern "C" chaos_status chaos_close(chaos_renderer *r)
     free_frame_memory(r);
     if (r->counters) D->p_cuMemFree(r->counters);
     if (r->counters_host) D->p_cuMemFreeHost(r->counters_host);
-    for (int i = 0; i < 4; ++i) if (r->ev[i]) D->p_cuEventDestroy(r->ev[i]);
+    for (int i = 0; i < 5; ++i) if (r->ev[i]) D->p_cuEventDestroy(r->ev[i]);
     if (r->stream) D->p_cuStreamDestroy(r->stream);
     unload_module(r);
     if (r->provider && r->provider->active == r) r->provider->active = nullptr;
@@ -658,6 +663,12 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
                (m->use_foveated_rendering ? CHAOS_FLAG_FOVEATION : 0u) | (m->use_sample_reuse ? CHAOS_FLAG_SAMPLE_REUSE : 0u) |
                (m->is_zooming ? CHAOS_FLAG_IS_ZOOMING : 0u) | (m->is_zooming_in ? CHAOS_FLAG_ZOOMING_IN : 0u);
     a->focus_x = (uint32_t)m->mouse_focus[0]; a->focus_y = (uint32_t)m->mouse_focus[1];
+    {   /* pixel radius at which the visual angle reaches the foveal threshold (fractalRendererGeneric.cu:233-239);
+         * pass R only uses it to skip the exact evaluation far away from that circle */
+        double thr = m->max_super_sampling >= 1.0f ? 5.5 : (double)m->max_super_sampling * 5.5;
+        double rpx = tan(thr * 0.017453292519943295) * 60.0 / 0.02652;
+        a->focus_d2_thr = (float)(rpx * rpx);
+    }
     a->tiles_x = (r->width + 7u) / 8u;
     a->tile_rows = (r->height + 3u) / 4u;
     a->part_index = r->part_index; a->part_count = r->part_count; a->band_tile_rows = r->band_rows / 4u;
@@ -714,6 +725,7 @@ static chaos_status finish_frame(chaos_renderer *r)
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "Error just after launching a kernel:%s", cu_err_name(e));
     D->p_cuEventElapsedTime(&r->stats.render_ms, r->ev[0], r->ev[1]);
     D->p_cuEventElapsedTime(&r->stats.compose_ms, r->ev[2], r->ev[3]);
+    r->stats.reuse_ms = 0.f;
     r->stats.pixel_iterations = r->counters_host->pixel_iterations;
     r->stats.samples = r->counters_host->samples;
     return CHAOS_OK;
@@ -821,6 +833,7 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
     chaos_render_args a;
     fill_render_args(r, m, &a);
     for (int i = 0; i < 4; ++i) { a.image_reused[i] = r->last.segment[i]; a.image_reusedf[i] = (float)r->last.segment[i]; }
+    bool split = false;
     a.in = (const chaos_pixel_info *)r->buf[0].ptr; a.in_pitch = r->buf[0].pitch;   /* input = primary */
     a.out = (chaos_pixel_info *)r->buf[1].ptr; a.out_pitch = r->buf[1].pitch;       /* output = secondary */
     r->stats.kernel_launches = 0;
@@ -828,8 +841,17 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
     if (a.n_tiles) {
-        st = launch(r, dbl ? r->k_adv_d : r->k_adv_f, dbl ? r->blocks_adv_d : r->blocks_adv_f, 256, 0, &a);
+        /* pass R: reprojection of every tile that needs no new sample (memory-bound, static schedule);
+         * pass S: the tiles pass R listed (foveal disc, pixels without history) with dynamic scheduling */
+        CUfunction k = dbl ? r->k_adv_d : r->k_adv_f;
+        const int blocks = dbl ? r->blocks_adv_d : r->blocks_adv_f;
+        a.phase = 1u;
+        st = launch(r, dbl ? r->k_reuse_d : r->k_reuse_f, dbl ? r->blocks_reuse_d : r->blocks_reuse_f, 256, 0, &a);
+        D->p_cuEventRecord(r->ev[4], r->stream);
+        a.phase = 2u;
+        if (st == CHAOS_OK) st = launch(r, k, blocks, 256, 0, &a);
         if (st != CHAOS_OK) return st;
+        split = true;
     }
     D->p_cuEventRecord(r->ev[1], r->stream);
     std::swap(r->buf[0], r->buf[1]);                               /* switch2DBuffers :180 */
@@ -840,6 +862,7 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
     D->p_cuEventRecord(r->ev[3], r->stream);
     st = finish_frame(r);
     if (st != CHAOS_OK) return st;
+    if (split) D->p_cuEventElapsedTime(&r->stats.reuse_ms, r->ev[0], r->ev[4]);
     r->last = *m; r->have_last = true;
     return CHAOS_OK;
 }

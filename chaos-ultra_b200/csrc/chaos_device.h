@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 6u
+#define CHAOS_MODULE_ABI 8u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -55,6 +55,7 @@ struct chaos_render_args {
     float max_ss;
     uint32_t flags;
     uint32_t focus_x, focus_y;
+    float focus_d2_thr;     /* squared pixel radius of the focus area (host: (tan(thr) * 60 / 0.02652)^2), see pass R */
     uint32_t tiles_x;       /* ceil(width / 8) */
     uint32_t tile_rows;     /* ceil(height / 4) */
     /* multi-GPU row-band partition: this launch covers bands b with b % part_count == part_index */

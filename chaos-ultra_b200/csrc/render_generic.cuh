@@ -331,61 +331,229 @@ static __device__ __forceinline__ void gather_bilinear(const chaos_pixel_info *i
     weight = __fmaf_rn(w11, t11.y, __fmaf_rn(w01, t01.y, __fmaf_rn(w00, t00.y, __fmul_rn(w10, t10.y))));
 }
 
-/* fractalRenderAdvanced (:307-368), tile-synchronous form: one warp per vote tile */
+/*
+ * fractalRenderAdvanced (:307-368).  A fast frame is two very different kinds of work:
+ *   - almost every pixel only reprojects: 4-tap gather from the previous frame + one 16-byte store (HBM-bound);
+ *   - the foveal disc (resampled while zooming in) and the pixels without history (border ring) run escape loops.
+ * They are split into two launches so that neither waits for the other:
+ *   pass R (advanced_reuse_pass)  static grid-stride over all vote tiles, one warp per tile.  Tiles in which no
+ *          pixel needs a sample are finished here; the others are appended to a worklist (tile_order[]) untouched.
+ *   pass S (advanced_sample_pass) dynamic (one atomic per listed tile) over the worklist; does the whole
+ *          per-tile procedure of the reference, both call sites of sampleTheFractal with their own vote groups.
+ * kMode: 1 = pass R, 2 = pass S.
+ */
+template <class Real, class FractalT, int kMode>
+static __device__ __forceinline__ void advanced_tile(const chaos_render_args &a, const frame_map<Real> &fm, uint32_t t, uint32_t lane,
+                                                     bool use_fov, unsigned long long &iters, unsigned long long &nsamples)
+{
+    const uint32_t fl = a.flags;
+    uint32_t x0, y0;
+    tile_origin(a, t, x0, y0);
+    const uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
+    const bool inb = px < a.width && py < a.height;
+
+    float advised = a.max_ss;
+    bool inside = false;
+    if (use_fov) foveation(x0, y0, a.focus_x, a.focus_y, a.max_ss, advised, inside);
+
+    bool reusing = false;
+    float rv = 0.f, rw = 0.f;
+    if (inb && (fl & CHAOS_FLAG_SAMPLE_REUSE)) {
+        float ox, oy;
+        warp_origin<Real>(a, px, py, ox, oy);
+        int oix = __float2int_rz(roundf(ox)), oiy = __float2int_rz(roundf(oy));
+        if (!(oix < 2 || (uint32_t)oix >= a.width - 2u || oiy < 2 || (uint32_t)oiy >= a.height - 2u)) {
+            gather_bilinear(a.in, a.in_pitch, ox, oy, rv, rw);
+            reusing = !((double)rw < 0.1);
+        }
+    }
+    const bool resample = reusing && (fl & CHAOS_FLAG_ZOOMING_IN) && inside;    /* call site :351 */
+    const bool fresh = inb && !reusing;                                          /* call site :361 */
+    if (kMode == 1) {
+        if (__any_sync(CHAOS_FULL_MASK, resample || fresh)) {                    /* leave the whole tile to pass S */
+            if (lane == 0) a.tile_order[atomicAdd(&a.counters->bucket_count[0], 1u)] = t;
+            return;
+        }
+        if (inb) store_record(record_at(a.out, a.out_pitch, px, py), rv, rw, 1u, 0.f);
+        return;
+    }
+    float value = rv, weight = rw, wnew = 0.f;
+    uint32_t reused_flag = reusing ? 1u : 0u;
+    if (__any_sync(CHAOS_FULL_MASK, resample)) {
+        float scf = advised;
+        uint32_t s = sample_tile_sync<Real, FractalT>(a, fm, resample, px, py, scf, iters, nsamples);
+        if (resample) {
+            float wold = __fmul_rn(rw, 0.75f);
+            weight = __fadd_rn(wold, scf);
+            value = __fdiv_rn(__fmaf_rn(rv, wold, __fmul_rn(scf, __uint2float_rn(s))), weight);
+            wnew = scf;
+        }
+    }
+    if (__any_sync(CHAOS_FULL_MASK, fresh)) {
+        float scf = advised < 1.f ? 1.f : advised;
+        uint32_t s = sample_tile_sync<Real, FractalT>(a, fm, fresh, px, py, scf, iters, nsamples);
+        if (fresh) { value = __uint2float_rn(s); weight = scf; }
+    }
+    if (inb) store_record(record_at(a.out, a.out_pitch, px, py), value, weight, reused_flag, wnew);
+}
+
+/*
+ * pass R.  Memory-bound by design: per pixel 4 taps of 8 bytes gathered (about 16 B unique) and one 16-byte store.
+ * To keep it that way the instruction count per pixel has to be small, so the warp does not walk 8x4 tiles:
+ *   - a warp takes a strip of 4 horizontally adjacent vote tiles = 32 columns x 4 rows; lane = column;
+ *   - the reprojected x of a pixel depends only on its column and the reprojected y only on its row
+ *     (:194-203), so each lane computes ONE x (its column) and lanes 0..3 compute the four y, shared by shuffle:
+ *     4 divisions per lane per strip instead of 16, same operations per value as the reference;
+ *   - all 16 gathers of the lane's four pixels are issued before the first one is consumed;
+ *   - foveation (:226-257) is only needed as the predicate "inside the focus area", a monotone function of the
+ *     squared pixel distance d2 up to rounding; its ~150-instruction chain (sqrt, atanf, divisions) is evaluated
+ *     only within +-2 % of the threshold d2, elsewhere the comparison with the threshold decides (libdevice atanf
+ *     is accurate to 1 ulp and every other step to half an ulp, four orders of magnitude inside the guard band).
+ * A vote tile in which any pixel needs a sample is appended to the worklist and left untouched for pass S.
+ */
+static __device__ __forceinline__ bool inside_focus_area(uint32_t x0, uint32_t y0, uint32_t fx, uint32_t fy, float max_ss, float d2_thr)
+{
+    float dx = __fsub_rn(__uint2float_rn(fx), __uint2float_rn(x0));
+    float dy = __fsub_rn(__uint2float_rn(fy), __uint2float_rn(y0));
+    float d2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+    if (d2 < 0.98f * d2_thr) return true;
+    if (d2 > 1.02f * d2_thr) return false;
+    float adv;
+    bool inside;
+    foveation(x0, y0, fx, fy, max_ss, adv, inside);
+    return inside;
+}
+
+/* reprojected coordinate of column px (kY = false) or row py (kY = true), :194-203 */
+template <class Real, bool kY> static __device__ __forceinline__ float warp_origin_1d(const chaos_render_args &a, uint32_t p);
+template <> __device__ __forceinline__ float warp_origin_1d<double, false>(const chaos_render_args &a, uint32_t px)
+{
+    double rx = __ddiv_rn(__uint2double_rn(px), __uint2double_rn(a.width));
+    double plane = __fma_rn(__dsub_rn(a.image[2], a.image[0]), rx, a.image[0]);
+    double rel = __ddiv_rn(__dsub_rn(plane, a.image_reused[0]), __dsub_rn(a.image_reused[2], a.image_reused[0]));
+    return __fmul_rn(__uint2float_rn(a.width), __double2float_rn(rel));
+}
+template <> __device__ __forceinline__ float warp_origin_1d<double, true>(const chaos_render_args &a, uint32_t py)
+{
+    double ry = __ddiv_rn(__uint2double_rn(a.height - py), __uint2double_rn(a.height));
+    double plane = __fma_rn(__dsub_rn(a.image[3], a.image[1]), ry, a.image[1]);
+    double rel = __ddiv_rn(__dsub_rn(plane, a.image_reused[1]), __dsub_rn(a.image_reused[3], a.image_reused[1]));
+    float fh = __uint2float_rn(a.height);
+    return __fmaf_rn(fh, -__double2float_rn(rel), fh);
+}
+template <> __device__ __forceinline__ float warp_origin_1d<float, false>(const chaos_render_args &a, uint32_t px)
+{
+    float fw = __uint2float_rn(a.width);
+    float rx = __fdiv_rn(__uint2float_rn(px), fw);
+    float plane = __fmaf_rn(__fsub_rn(a.imagef[2], a.imagef[0]), rx, a.imagef[0]);
+    float rel = __fdiv_rn(__fsub_rn(plane, a.image_reusedf[0]), __fsub_rn(a.image_reusedf[2], a.image_reusedf[0]));
+    return __fmul_rn(fw, rel);
+}
+template <> __device__ __forceinline__ float warp_origin_1d<float, true>(const chaos_render_args &a, uint32_t py)
+{
+    float fh = __uint2float_rn(a.height);
+    float ry = __fdiv_rn(__uint2float_rn(a.height - py), fh);
+    float plane = __fmaf_rn(__fsub_rn(a.imagef[3], a.imagef[1]), ry, a.imagef[1]);
+    float rel = __fdiv_rn(__fsub_rn(plane, a.image_reusedf[1]), __fsub_rn(a.image_reusedf[3], a.image_reusedf[1]));
+    return __fmaf_rn(fh, -rel, fh);
+}
+
+template <class Real>
+static __device__ void advanced_reuse_pass(const chaos_render_args &a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t fl = a.flags;
+    const bool use_fov = (fl & CHAOS_FLAG_FOVEATION) && (fl & CHAOS_FLAG_IS_ZOOMING) && (fl & CHAOS_FLAG_ZOOMING_IN);
+    const bool reuse = (fl & CHAOS_FLAG_SAMPLE_REUSE) != 0u;
+    const bool resample_focus = use_fov && (fl & CHAOS_FLAG_ZOOMING_IN);
+    const float d2_thr = a.focus_d2_thr;
+    const uint32_t strips_x = (a.tiles_x + 3u) >> 2;
+    const uint32_t rows_owned = a.n_tiles / a.tiles_x;
+    const uint32_t n_strips = strips_x * rows_owned;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n_strips; u += warps) {
+        const uint32_t row = u / strips_x, g = u - row * strips_x;
+        const uint32_t tile = row * a.tiles_x + 4u * g + (lane >> 3);      /* the lane's vote tile */
+        const bool tile_ok = 4u * g + (lane >> 3) < a.tiles_x;
+        uint32_t x0 = 0, y0 = 0;
+        tile_origin(a, tile_ok ? tile : row * a.tiles_x, x0, y0);
+        const uint32_t px = 32u * g + lane;
+        const bool col_ok = px < a.width;
+        const bool inside = resample_focus && tile_ok && inside_focus_area(x0, y0, a.focus_x, a.focus_y, a.max_ss, d2_thr);
+
+        float ox = 0.f, oyv = 0.f;
+        int oix = 0;
+        if (reuse) {
+            ox = warp_origin_1d<Real, false>(a, px);
+            oyv = warp_origin_1d<Real, true>(a, y0 + (lane & 3u));          /* lanes 0..3 hold rows 0..3 */
+            oix = __float2int_rz(roundf(ox));
+        }
+        const bool x_in = reuse && col_ok && !(oix < 2 || (uint32_t)oix >= a.width - 2u);
+        const uint32_t i = __float2uint_rz(floorf(ox));
+        const float al = __fsub_rn(ox, __uint2float_rn(i));
+
+        bool tap[4];
+        float be[4];
+        float2 t00[4], t10[4], t01[4], t11[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float oy = __shfl_sync(CHAOS_FULL_MASK, oyv, r);
+            const int oiy = __float2int_rz(roundf(oy));
+            const uint32_t py = y0 + r;
+            tap[r] = x_in && py < a.height && !(oiy < 2 || (uint32_t)oiy >= a.height - 2u);
+            const uint32_t j = __float2uint_rz(floorf(oy));
+            be[r] = __fsub_rn(oy, __uint2float_rn(j));
+            t00[r] = t10[r] = t01[r] = t11[r] = make_float2(0.f, 0.f);
+            if (tap[r]) {
+                const char *row0 = (const char *)a.in + (size_t)j * a.in_pitch + (size_t)i * 16u;
+                const char *row1 = row0 + a.in_pitch;
+                t00[r] = __ldg(reinterpret_cast<const float2 *>(row0));
+                t10[r] = __ldg(reinterpret_cast<const float2 *>(row0 + 16));
+                t01[r] = __ldg(reinterpret_cast<const float2 *>(row1));
+                t11[r] = __ldg(reinterpret_cast<const float2 *>(row1 + 16));
+            }
+        }
+        float rv[4], rw[4];
+        bool needs = false;
+        const float na = __fsub_rn(1.f, al);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float nb = __fsub_rn(1.f, be[r]);
+            const float w00 = __fmul_rn(na, nb), w10 = __fmul_rn(al, nb), w01 = __fmul_rn(na, be[r]), w11 = __fmul_rn(al, be[r]);
+            rv[r] = __fmaf_rn(w11, t11[r].x, __fmaf_rn(w01, t01[r].x, __fmaf_rn(w00, t00[r].x, __fmul_rn(w10, t10[r].x))));
+            rw[r] = __fmaf_rn(w11, t11[r].y, __fmaf_rn(w01, t01[r].y, __fmaf_rn(w00, t00[r].y, __fmul_rn(w10, t10[r].y))));
+            const bool in_frame = col_ok && (y0 + r) < a.height;
+            const bool reusing = tap[r] && !((double)rw[r] < 0.1);
+            needs |= in_frame && (!reusing || inside);
+        }
+        /* any pixel of an 8x4 vote tile needs a sample -> the whole tile goes to pass S */
+        const uint32_t needs_mask = __ballot_sync(CHAOS_FULL_MASK, needs);
+        const bool tile_needs = ((needs_mask >> (lane & 24u)) & 0xffu) != 0u;
+        if (tile_needs) {
+            if ((lane & 7u) == 0u && tile_ok) a.tile_order[atomicAdd(&a.counters->bucket_count[0], 1u)] = tile;
+        } else if (col_ok) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (y0 + r < a.height) store_record(record_at(a.out, a.out_pitch, px, y0 + r), rv[r], rw[r], 1u, 0.f);
+        }
+    }
+}
+
 template <class Real, class FractalT>
-static __device__ void render_advanced_sync(const chaos_render_args &a)
+static __device__ void advanced_sample_pass(const chaos_render_args &a)
 {
     frame_map<Real> fm;
     fm.init(a);
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t fl = a.flags;
-    const bool use_fov = (fl & CHAOS_FLAG_FOVEATION) && (fl & CHAOS_FLAG_IS_ZOOMING) && (fl & CHAOS_FLAG_ZOOMING_IN);
+    const bool use_fov = (a.flags & CHAOS_FLAG_FOVEATION) && (a.flags & CHAOS_FLAG_IS_ZOOMING) && (a.flags & CHAOS_FLAG_ZOOMING_IN);
+    const uint32_t n_work = a.counters->bucket_count[0];       /* written by pass R, complete before this launch starts */
     unsigned long long iters = 0, nsamples = 0;
     for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(&a.counters->next_tile, 1u);
-        t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
-        if (t >= a.n_tiles) break;
-        uint32_t x0, y0;
-        tile_origin(a, t, x0, y0);
-        uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
-        bool inb = px < a.width && py < a.height;
-
-        float advised = a.max_ss;
-        bool inside = false;
-        if (use_fov) foveation(x0, y0, a.focus_x, a.focus_y, a.max_ss, advised, inside);
-
-        bool reusing = false;
-        float rv = 0.f, rw = 0.f;
-        if (inb && (fl & CHAOS_FLAG_SAMPLE_REUSE)) {
-            float ox, oy;
-            warp_origin<Real>(a, px, py, ox, oy);
-            int oix = __float2int_rz(roundf(ox)), oiy = __float2int_rz(roundf(oy));
-            if (!(oix < 2 || (uint32_t)oix >= a.width - 2u || oiy < 2 || (uint32_t)oiy >= a.height - 2u)) {
-                gather_bilinear(a.in, a.in_pitch, ox, oy, rv, rw);
-                reusing = !((double)rw < 0.1);
-            }
-        }
-        const bool resample = reusing && (fl & CHAOS_FLAG_ZOOMING_IN) && inside;    /* call site :351 */
-        const bool fresh = inb && !reusing;                                          /* call site :361 */
-        float value = rv, weight = rw, wnew = 0.f;
-        uint32_t reused_flag = reusing ? 1u : 0u;
-        if (__any_sync(CHAOS_FULL_MASK, resample)) {
-            float scf = advised;
-            uint32_t s = sample_tile_sync<Real, FractalT>(a, fm, resample, px, py, scf, iters, nsamples);
-            if (resample) {
-                float wold = __fmul_rn(rw, 0.75f);
-                weight = __fadd_rn(wold, scf);
-                value = __fdiv_rn(__fmaf_rn(rv, wold, __fmul_rn(scf, __uint2float_rn(s))), weight);
-                wnew = scf;
-            }
-        }
-        if (__any_sync(CHAOS_FULL_MASK, fresh)) {
-            float scf = advised < 1.f ? 1.f : advised;
-            uint32_t s = sample_tile_sync<Real, FractalT>(a, fm, fresh, px, py, scf, iters, nsamples);
-            if (fresh) { value = __uint2float_rn(s); weight = scf; }
-        }
-        if (inb) store_record(record_at(a.out, a.out_pitch, px, py), value, weight, reused_flag, wnew);
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(&a.counters->next_tile_b, 1u);
+        w = __shfl_sync(CHAOS_FULL_MASK, w, 0);
+        if (w >= n_work) break;
+        advanced_tile<Real, FractalT, 2>(a, fm, a.tile_order[w], lane, use_fov, iters, nsamples);
     }
     for (int o = 16; o; o >>= 1) {
         iters += __shfl_xor_sync(CHAOS_FULL_MASK, iters, o);
@@ -425,11 +593,18 @@ extern "C" __global__ void __launch_bounds__(256) chaosOrderTiles(const __grid_c
 /* shared-memory need of the engine-1 kernels, read by the host at module load */
 __constant__ uint32_t CHAOS_REFILL_SMEM = (uint32_t)CHAOS_REFILL_SMEM_BYTES;
 
-extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
-fractalRenderAdvancedFloat(const __grid_constant__ chaos_render_args a) { render_advanced_sync<float, Fractal>(a); }
+/* fast frame: pass R (chaosReusePass*) then pass S (fractalRenderAdvanced*) */
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosReusePassFloat(const __grid_constant__ chaos_render_args a) { advanced_reuse_pass<float>(a); }
+
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosReusePassDouble(const __grid_constant__ chaos_render_args a) { advanced_reuse_pass<double>(a); }
 
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
-fractalRenderAdvancedDouble(const __grid_constant__ chaos_render_args a) { render_advanced_sync<double, Fractal>(a); }
+fractalRenderAdvancedFloat(const __grid_constant__ chaos_render_args a) { advanced_sample_pass<float, Fractal>(a); }
+
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
+fractalRenderAdvancedDouble(const __grid_constant__ chaos_render_args a) { advanced_sample_pass<double, Fractal>(a); }
 
 /* the reference's fractalRenderUnderSampled (:478-503) is looked up but never launched
  * (SURVEY.md 2.2); the symbol is kept so the module contract is complete */

@@ -100,6 +100,8 @@ typedef struct chaos_stats {
     uint32_t kernel_launches;        /* kernels of this library launched by the last render call */
     float render_ms;                 /* iteration / reuse kernel, CUDA events on the render stream */
     float compose_ms;                /* compose kernel */
+    float reuse_ms;                  /* fast frames: the reprojection pass alone (part of render_ms), else 0 */
+    uint32_t reserved;
     uint64_t pixel_iterations;       /* sum of escape-loop trip counts over every evaluated sample */
     uint64_t samples;                /* number of evaluated samples (orbits) */
     uint64_t launches_total;         /* kernels launched since the renderer was opened */

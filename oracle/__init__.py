@@ -243,6 +243,9 @@ class RefRun:
         l.refrun_frames.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.c_uint32, C.c_float,
                                     C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
                                     C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]
+        l.refrun_zoom.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_uint32,
+                                  C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]
         self._l = l
         self._h = C.c_void_p()
         self._ok(l.refrun_open(str(path).encode(), device, C.byref(self._h)))
@@ -299,6 +302,21 @@ class RefRun:
                                        warmup, steps, int(to_host), C.byref(wall), C.byref(m), C.byref(c),
                                        out.ctypes.data if out is not None else None))
         return wall.value, m.value, c.value, out
+
+    def zoom(self, W, H, segments, doubles, maxIter, maxSS, flags, focus, palette, warmup=1, steps=1, to_host=True):
+        """The reference host's zoom loop (frame 0 quality, then fast frames); segments: list of 1+warmup+steps segments.
+        Returns (wall_ms, advanced_ms_sum, compose_ms_sum, last rgba|None)."""
+        n = 1 + warmup + steps
+        assert len(segments) == n and len(doubles) == n
+        seg = (C.c_double * (4 * n))(*[float(v) for sgm in segments for v in sgm])
+        dbl = (C.c_int * n)(*[int(bool(d)) for d in doubles])
+        pal = np.ascontiguousarray(palette, dtype=np.uint32)
+        wall, a, c = C.c_double(0), C.c_float(0), C.c_float(0)
+        out = np.zeros((H, W), dtype=np.uint32) if to_host else None
+        self._ok(self._l.refrun_zoom(self._h, W, H, seg, dbl, maxIter, maxSS, flags, int(focus[0]), int(focus[1]), pal.ctypes.data,
+                                     pal.size, warmup, steps, int(to_host), C.byref(wall), C.byref(a), C.byref(c),
+                                     out.ctypes.data if out is not None else None))
+        return wall.value, a.value, c.value, out
 
     def close(self):
         if self._h:

@@ -345,3 +345,114 @@ extern "C" int refrun_frames(refrun *r, int is_double, uint32_t W, uint32_t H, c
     cuMemFree(buf[1]);
     return 0;
 }
+
+/*
+ * Zoom sequence of the reference host (bench.py --impl reference --workload c3): frame 0 is a quality frame, then
+ * `steps` fast frames, each = CudaFractalRenderer.renderFast :159-184: advanced kernel (input = primary buffer,
+ * output = secondary, imageReused = previous frame's segment), cuCtxSynchronize twice, buffer swap, surfaces
+ * created, compose, cuCtxSynchronize, surfaces destroyed.  segments: (1 + warmup + steps) x 4 doubles, computed by
+ * the caller with RenderingController.zoomAt.  is_double_per_frame: the precision the reference's own rule picks.
+ */
+extern "C" int refrun_zoom(refrun *r, uint32_t W, uint32_t H, const double *segments, const int *is_double_per_frame,
+                           uint32_t maxIter, float maxSS, uint32_t flags, uint32_t focus_x, uint32_t focus_y,
+                           const uint32_t *palette, uint32_t palette_len, int warmup, int steps, int to_host,
+                           double *wall_ms, float *adv_ms_sum, float *compose_ms_sum, uint32_t *rgba_out)
+{
+    ctx_scope s(r->ctx);
+    unsigned char vis = 0;
+    if (refrun_write_constant(r, "VISUALIZE_SAMPLE_COUNT", &vis, 1) != 0) return -1;
+    CUdeviceptr buf[2];
+    size_t pitch[2];
+    for (int i = 0; i < 2; ++i) {
+        RR_TRY(cuMemAllocPitch(&buf[i], &pitch[i], (size_t)W * 16, H, 16));
+        RR_TRY(cuMemsetD8(buf[i], 0, pitch[i] * H));
+    }
+    CUarray a_out, a_pal;
+    CUDA_ARRAY3D_DESCRIPTOR d;
+    memset(&d, 0, sizeof d);
+    d.Width = W; d.Height = H; d.Format = CU_AD_FORMAT_UNSIGNED_INT8; d.NumChannels = 4; d.Flags = CUDA_ARRAY3D_SURFACE_LDST;
+    RR_TRY(cuArray3DCreate(&a_out, &d));
+    d.Width = palette_len; d.Height = 1;
+    RR_TRY(cuArray3DCreate(&a_pal, &d));
+    CUDA_MEMCPY2D c;
+    memset(&c, 0, sizeof c);
+    c.srcMemoryType = CU_MEMORYTYPE_HOST; c.srcHost = palette; c.srcPitch = (size_t)palette_len * 4;
+    c.dstMemoryType = CU_MEMORYTYPE_ARRAY; c.dstArray = a_pal;
+    c.WidthInBytes = (size_t)palette_len * 4; c.Height = 1;
+    RR_TRY(cuMemcpy2D(&c));
+    uint32_t *pinned = nullptr;
+    RR_TRY(cuMemHostAlloc((void **)&pinned, (size_t)W * H * 4, 0));
+    CUevent e[4];
+    for (int i = 0; i < 4; ++i) RR_TRY(cuEventCreate(&e[i], CU_EVENT_DEFAULT));
+    unsigned gx = (W + 31) / 32, gy = (H + 31) / 32;
+    uint32_t size[2] = {W, H}, focus[2] = {focus_x, focus_y};
+    float asum = 0, csum = 0;
+    std::chrono::steady_clock::time_point t0;
+    int prim = 0;
+    for (int f = 0; f < 1 + warmup + steps; ++f) {
+        if (f == 1 + warmup) { RR_TRY(cuCtxSynchronize()); t0 = std::chrono::steady_clock::now(); asum = csum = 0; }
+        const double *img = segments + 4 * f;
+        int dbl = is_double_per_frame[f];
+        float imf[4] = {(float)img[0], (float)img[1], (float)img[2], (float)img[3]};
+        long long p_out, p_in;
+        RR_TRY(cuEventRecord(e[0], 0));
+        if (f == 0) {
+            prim = 0;
+            p_out = (long long)pitch[0];
+            float ss0 = maxSS < 1.f ? 1.f : maxSS;
+            void *pm[7] = {&buf[0], &p_out, size, dbl ? (void *)img : (void *)imf, &maxIter, &ss0, &flags};
+            RR_TRY(cuLaunchKernel(dbl ? r->main_d : r->main_f, gx, gy, 1, 32, 32, 1, 0, 0, pm, nullptr));
+        } else {
+            const double *old = segments + 4 * (f - 1);
+            float oldf[4] = {(float)old[0], (float)old[1], (float)old[2], (float)old[3]};
+            int sec = 1 - prim;
+            p_out = (long long)pitch[sec]; p_in = (long long)pitch[prim];
+            void *pa[11] = {&buf[sec], &p_out, size, dbl ? (void *)img : (void *)imf, &maxIter, &maxSS, &flags,
+                            dbl ? (void *)old : (void *)oldf, &buf[prim], &p_in, focus};
+            RR_TRY(cuLaunchKernel(dbl ? r->adv_d : r->adv_f, gx, gy, 1, 32, 32, 1, 0, 0, pa, nullptr));
+            prim = sec;                                       /* switch2DBuffers */
+        }
+        RR_TRY(cuEventRecord(e[1], 0));
+        RR_TRY(cuCtxSynchronize());
+        RR_TRY(cuCtxSynchronize());
+        CUsurfObject s_out, s_pal;
+        CUDA_RESOURCE_DESC rd;
+        memset(&rd, 0, sizeof rd);
+        rd.resType = CU_RESOURCE_TYPE_ARRAY;
+        rd.res.array.hArray = a_out;
+        RR_TRY(cuSurfObjectCreate(&s_out, &rd));
+        rd.res.array.hArray = a_pal;
+        RR_TRY(cuSurfObjectCreate(&s_pal, &rd));
+        long long pp = (long long)pitch[prim], ps = (long long)pitch[1 - prim];
+        void *pc[10] = {&buf[prim], &pp, &buf[1 - prim], &ps, &s_out, &W, &H, &s_pal, &palette_len, &maxSS};
+        RR_TRY(cuEventRecord(e[2], 0));
+        RR_TRY(cuLaunchKernel(r->compose, gx, gy, 1, 32, 32, 1, 0, 0, pc, nullptr));
+        RR_TRY(cuEventRecord(e[3], 0));
+        RR_TRY(cuCtxSynchronize());
+        cuSurfObjectDestroy(s_out);
+        cuSurfObjectDestroy(s_pal);
+        if (to_host) {
+            memset(&c, 0, sizeof c);
+            c.srcMemoryType = CU_MEMORYTYPE_ARRAY; c.srcArray = a_out;
+            c.dstMemoryType = CU_MEMORYTYPE_HOST; c.dstHost = pinned; c.dstPitch = (size_t)W * 4;
+            c.WidthInBytes = (size_t)W * 4; c.Height = H;
+            RR_TRY(cuMemcpy2D(&c));
+        }
+        float t = 0;
+        cuEventElapsedTime(&t, e[0], e[1]); asum += t;
+        cuEventElapsedTime(&t, e[2], e[3]); csum += t;
+    }
+    RR_TRY(cuCtxSynchronize());
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (wall_ms) *wall_ms = ms;
+    if (adv_ms_sum) *adv_ms_sum = asum;
+    if (compose_ms_sum) *compose_ms_sum = csum;
+    if (rgba_out && to_host) memcpy(rgba_out, pinned, (size_t)W * H * 4);
+    for (int i = 0; i < 4; ++i) cuEventDestroy(e[i]);
+    cuMemFreeHost(pinned);
+    cuArrayDestroy(a_out);
+    cuArrayDestroy(a_pal);
+    cuMemFree(buf[0]);
+    cuMemFree(buf[1]);
+    return 0;
+}

@@ -69,7 +69,7 @@ def test_struct_layouts_match_header(cu):
       printf("%zu %zu %zu %zu %zu %zu\n", sizeof(chaos_params), offsetof(chaos_params, segment), offsetof(chaos_params, max_super_sampling),
              offsetof(chaos_params, mouse_focus), offsetof(chaos_params, float_precision), offsetof(chaos_params, force_precision));
       printf("%zu %zu %zu\n", sizeof(chaos_defaults), offsetof(chaos_defaults, center_x), offsetof(chaos_defaults, custom_params));
-      printf("%zu %zu %zu\n", sizeof(chaos_stats), offsetof(chaos_stats, pixel_iterations), offsetof(chaos_stats, launches_total));
+      printf("%zu %zu %zu %zu\n", sizeof(chaos_stats), offsetof(chaos_stats, pixel_iterations), offsetof(chaos_stats, launches_total), offsetof(chaos_stats, reuse_ms));
       return 0; }'''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -81,7 +81,7 @@ def test_struct_layouts_match_header(cu):
     assert list(map(int, lines[0].split())) == [ctypes.sizeof(P), P.segment.offset, P.max_super_sampling.offset,
                                                 P.mouse_focus.offset, P.float_precision.offset, P.force_precision.offset]
     assert list(map(int, lines[1].split())) == [ctypes.sizeof(D), D.center_x.offset, D.custom_params.offset]
-    assert list(map(int, lines[2].split())) == [ctypes.sizeof(S), S.pixel_iterations.offset, S.launches_total.offset]
+    assert list(map(int, lines[2].split())) == [ctypes.sizeof(S), S.pixel_iterations.offset, S.launches_total.offset, S.reuse_ms.offset]
 
 
 @pytest.mark.skipif(_has_gpu(), reason="only meaningful without a device")
