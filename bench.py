@@ -153,6 +153,12 @@ def measure_fma_peak(device: int, double: bool):
         cu.cuDevicePrimaryCtxRelease(dev)
 
 
+def quiet_nccl():
+    """the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout next to the JSON line"""
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -568,6 +574,7 @@ def main():
     args = ap.parse_args()
     args.e2e_host_copy = False
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    quiet_nccl()
     rank, world, local = dist_env()
     wl = WORKLOADS[args.workload]
     zoom = wl.get("kind") == "zoom"

@@ -32,6 +32,7 @@
 #include "../../include/chaos_ultra.h"
 #include "chaos_device.h"
 #include "cuda_driver.h"
+#include "mini_json.h"
 
 /* ------------------------------------------------------------------------------------------
  * errors
@@ -183,18 +184,89 @@ static void defaults_test(chaos_defaults *d)
     defaults_base(d);
     snprintf(d->custom_params, sizeof d->custom_params, "10");
 }
-static void defaults_plain(chaos_defaults *d) { defaults_base(d); }
+/* modules/ModuleNewtonWired.java:7-20 */
+static void defaults_newton_wired(chaos_defaults *d)
+{
+    defaults_base(d);
+    d->has_max_iterations = 1; d->max_iterations = 200;
+}
 
-/* the 7 names the reference registers (CudaFractalRendererProvider.java:21-27); a module whose
- * file is missing fails at chaos_open() with the path, like cuModuleLoad does there */
+/* modules/ModuleNewtonGeneric.java:34-74: {"coefficients":[a3,a2,a1,a0], "roots":[[re,im] x 3]}; the coefficient
+ * order is reversed between the user's text and the device array (:46-49) */
+static const char *k_newton_default_params =
+    "{ \"coefficients\" : [1, 0, 0, -1], \"roots\" : [ [1,0], [-0.5,0.86602540378] , [-0.5,-0.86602540378] ] }";
+static chaos_status newton_parse(const char *text, mj_value &json)
+{
+    mj_parser ps(text);
+    if (!ps.parse(json) || json.kind != mj_value::OBJ)
+        return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "JsonSyntaxException: cannot parse the fractal parameters: %s", text ? text : "");
+    return CHAOS_OK;
+}
+static chaos_status newton_generic_custom(chaos_renderer *r, const char *text)
+{
+    mj_value json;
+    chaos_status st = newton_parse(text, json);
+    if (st != CHAOS_OK) return st;
+    const mj_value *co = json.get("coefficients"), *ro = json.get("roots");
+    if (!co || co->kind != mj_value::ARR || !ro || ro->kind != mj_value::ARR)
+        return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "NullPointerException: the parameters need \"coefficients\" and \"roots\" arrays");
+    for (const mj_value &root : ro->arr)
+        if (root.kind != mj_value::ARR || root.arr.size() != 2)
+            return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Found a root that is not represented as [real, imag].");
+    if (co->arr.size() != 4) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "expecting 4 coefficients");
+    if (ro->arr.size() != 3) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "expecting 3 roots");
+    double roots[6], coefs[4];
+    for (int i = 0; i < 3; ++i) { roots[2 * i] = ro->arr[i].arr[0].num; roots[2 * i + 1] = ro->arr[i].arr[1].num; }
+    for (int i = 0; i < 4; ++i) coefs[3 - i] = co->arr[i].num;
+    st = write_constant(r, "roots", roots, sizeof roots, "double[] of size 6");
+    if (st != CHAOS_OK) return st;
+    return write_constant(r, "coefficients", coefs, sizeof coefs, "double[] of size 4");
+}
+static void defaults_newton_generic(chaos_defaults *d)
+{
+    defaults_base(d);
+    d->has_max_iterations = 1; d->max_iterations = 200;
+    snprintf(d->custom_params, sizeof d->custom_params, "%s", k_newton_default_params);
+}
+
+/* modules/ModuleNewtonIterations.java:9-33: the generic parameters plus an optional "colorMagnifier" */
+static chaos_status newton_iterations_custom(chaos_renderer *r, const char *text)
+{
+    chaos_status st = newton_generic_custom(r, text);
+    if (st != CHAOS_OK) return st;
+    mj_value json;
+    st = newton_parse(text, json);
+    if (st != CHAOS_OK) return st;
+    if (const mj_value *cm = json.get("colorMagnifier")) {
+        int v = (int)cm->num;
+        return write_constant(r, "colorMagnifier", &v, sizeof v, "double");
+    }
+    return CHAOS_OK;
+}
+static void defaults_newton_iterations(chaos_defaults *d)
+{
+    defaults_newton_generic(d);
+    /* "{\"colorMagnifier\": 11," + the generic text without its opening brace (:28-31) */
+    snprintf(d->custom_params, sizeof d->custom_params, "{\"colorMagnifier\": 11,%s", k_newton_default_params + 1);
+}
+
+/* modules/ModuleGoci.java:9-28 */
+static void defaults_goc(chaos_defaults *d)
+{
+    defaults_base(d);
+    d->has_max_iterations = 1; d->max_iterations = 900;
+    d->has_segment = 1; d->center_x = 1.1; d->center_y = -0.2; d->zoom = 0.20000000000000004;
+}
+
+/* the 7 names the reference registers (CudaFractalRendererProvider.java:21-27), display name -> module file */
 static const module_desc g_modules[] = {
     {"julia", "julia", julia_on_initialize, julia_custom, defaults_julia},
     {"mandelbrot", "mandelbrot", nullptr, custom_none, defaults_mandelbrot},
-    {"newton wired", "newton_wired", nullptr, custom_none, defaults_plain},
-    {"newton generic", "newton_generic", nullptr, custom_none, defaults_plain},
-    {"newton colored by iterations", "newton_iterations", nullptr, custom_none, defaults_plain},
+    {"newton wired", "newton_wired", nullptr, custom_none, defaults_newton_wired},
+    {"newton generic", "newton_generic", nullptr, newton_generic_custom, defaults_newton_generic},
+    {"newton colored by iterations", "newton_iterations", nullptr, newton_iterations_custom, defaults_newton_iterations},
     {"test", "test", nullptr, test_custom, defaults_test},
-    {"goc", "goc", nullptr, custom_none, defaults_plain},
+    {"goc", "goc", nullptr, custom_none, defaults_goc},
 };
 static const uint32_t g_n_modules = sizeof g_modules / sizeof g_modules[0];
 

@@ -1,0 +1,60 @@
+/*
+ * "newton colored by iterations": the same Newton iteration as newton_generic, but the value is the number of
+ * steps until any root is reached (tested after every step) and the colour comes from the palette, stretched by
+ * `colorMagnifier`.  Same results as src/main/cuda/fractals/newton_iterations.cu:7-84; host half
+ * modules/ModuleNewtonIterations.java:9-33.
+ */
+#include "newton_common.cuh"
+
+__constant__ double roots[6];
+__constant__ double coefficients[4];
+__constant__ int colorMagnifier;
+
+struct NewtonIterationsImpl {
+    template <class Real> static __device__ __forceinline__ thrust::complex<Real> step(thrust::complex<Real> x)
+    {
+        thrust::complex<Real> x_pow_2 = x * x;
+        thrust::complex<Real> x_pow_3 = x_pow_2 * x;
+        thrust::complex<Real> f_eval_x = coefficients[0] +
+                                         coefficients[1] * x +
+                                         coefficients[2] * x_pow_2 +
+                                         coefficients[3] * x_pow_3;
+        thrust::complex<Real> f_derivative_eval_x = coefficients[1] +
+                                                    coefficients[2] * 2 * x +
+                                                    coefficients[3] * 3 * x_pow_2;
+        return x - (f_eval_x / f_derivative_eval_x);
+    }
+    template <class Real> static __device__ __forceinline__ unsigned int root_of(thrust::complex<Real> x)
+    {
+        const thrust::complex<Real> root_a(roots[0], roots[1]);
+        const thrust::complex<Real> root_b(roots[2], roots[3]);
+        const thrust::complex<Real> root_c(roots[4], roots[5]);
+        return newton_convergence_root<Real>(x, root_a, root_b, root_c);
+    }
+    template <class Real> static __device__ float compute(uint32_t maxIterations, Real px, Real py, uint32_t &trips)
+    {
+        thrust::complex<Real> x(px, py);
+        unsigned int i = 0;
+        while (i < maxIterations) {
+            x = step<Real>(x);
+            ++i;
+            if (root_of<Real>(x) != 0) break;
+        }
+        trips = i;
+        return i;
+    }
+};
+
+struct Fractal {
+    /* no branch separates c.y's multiply and subtract in the reference build of this module: ptxas contracts them
+     * into one FMA (SASS of oracle/_ref/newton_iterations.src.cubin), see frame_map::plane_point */
+    static constexpr bool kFusedPlaneY = true;
+    template <class Real> using Orbit = ClassicOrbit<NewtonIterationsImpl, Real>;
+    static __device__ __forceinline__ uint32_t colorize(const uint32_t *palette, uint32_t len, float result)
+    {
+        return chaos_default_colorize(palette, len, result, (uint32_t)colorMagnifier);
+    }
+    static __device__ void debugFractal() {}
+};
+
+#include "../render_generic.cuh"

@@ -60,6 +60,37 @@ MAIN_CASES = [
     _c("m_maxiter1_f64", "mandelbrot", 40, 24, (-0.5, 0.0), 2.0, 1, 3, A, True),
 ]
 
+# Modules without a CPU oracle in this round (thrust::complex arithmetic): checked against the reference's own
+# kernels run live and against fixtures produced by them.  `params` is the custom-parameter text the GUI would send
+# (PresenterFX.java:335-364, ModuleNewtonGeneric.java:69-73).
+N_DEFAULT = '{ "coefficients" : [1, 0, 0, -1], "roots" : [ [1,0], [-0.5,0.86602540378] , [-0.5,-0.86602540378] ] }'
+N3 = ('{ "coefficients" : [1, 0, -2, 2], "roots" : [ [-1.7692923542386314,0], [0.884646177119315707620204,0.589742805022205501647280] , '
+      '[0.884646177119315707,-0.589742805022205501] ] }')
+N_ITER = '{"colorMagnifier": 11,' + N_DEFAULT[1:]
+EXTRA_MAIN_CASES = [
+    _c("nw_a2_f32", "newton_wired", 160, 96, (0.0, 0.0), 4.0, 200, 2, A, False),
+    _c("nw_a4_f64", "newton_wired", 120, 72, (0.1, -0.2), 1.5, 100, 4, A, True),
+    _c("nw_n1_deep_f64", "newton_wired", 96, 64, (1.8252568181102808e-4, -1.0538321727858829e-4), 6.94260652234243e-7, 100, 1, 0, True),
+    _c("ng_def_a2_f32", "newton_generic", 160, 96, (0.0, 0.0), 4.0, 200, 2, A, False, params=N_DEFAULT),
+    _c("ng_n3_a3_f64", "newton_generic", 120, 72, (0.0, 0.0), 4.0, 100, 3, A, True, params=N3),
+    _c("ni_def_a2_f32", "newton_iterations", 160, 96, (0.0, 0.0), 4.0, 200, 2, A, False, params=N_ITER),
+    _c("ni_n3_a5_f64", "newton_iterations", 120, 72, (0.3, 0.1), 2.0, 70, 5, A, True, params='{"colorMagnifier": 7,' + N3[1:]),
+    _c("goc_a2_f32", "goc", 96, 64, (1.1, -0.2), 0.20000000000000004, 40, 2, A, False),
+    _c("goc_1s_f64", "goc", 96, 64, (1.1, -0.2), 0.20000000000000004, 30, 1, 0, True),
+]
+DISPLAY_NAME = {"mandelbrot": "mandelbrot", "julia": "julia", "test": "test", "newton_wired": "newton wired",
+                "newton_generic": "newton generic", "newton_iterations": "newton colored by iterations", "goc": "goc"}
+
+
+def newton_constants(params_text):
+    """what ModuleNewtonGeneric/Iterations write to the device for a parameter text: (roots[6], coefficients[4], magnifier|None)"""
+    import json
+    j = json.loads(params_text)
+    roots = [float(v) for r in j["roots"] for v in r]
+    coefs = [float(v) for v in reversed(j["coefficients"])]
+    return roots, coefs, (int(j["colorMagnifier"]) if "colorMagnifier" in j else None)
+
+
 # Advanced (fast-frame) cases: frame 0 is a quality render of `image0`; frame 1 is the advanced kernel on the
 # segment after `zooms` applications of zoomAt(focus, into) (RenderingController.java:130-150).
 def _a(name, fractal, W, H, center, zoom, maxIter, maxSS, flags, double, focus, into=True, zooms=1, **kw):
@@ -79,6 +110,8 @@ ADV_CASES = [
     _a("adv_deep_f64", "mandelbrot", 128, 80, (-0.235125, 0.827215), 4.0e-5, 800, 2, A | FOV | REUSE | ZOOMING | ZOOM_IN, True, (64, 40), zooms=3),
     _a("adv_julia_f32", "julia", 160, 96, (0.0, 0.0), 4.0, 300, 2, A | FOV | REUSE | ZOOMING | ZOOM_IN, False, (80, 48), julia_c=(-0.4, 0.6)),
     _a("adv_test_f32", "test", 96, 64, (0.1, -0.1), 3.0, 10, 3, A | FOV | REUSE | ZOOMING | ZOOM_IN, False, (40, 30), amplifier=7),
+    _a("adv_newton_f32", "newton_generic", 120, 72, (0.0, 0.0), 3.0, 100, 3, A | FOV | REUSE | ZOOMING | ZOOM_IN, False, (60, 36), params=N3),
+    _a("adv_newton_iter_f64", "newton_iterations", 96, 64, (0.2, 0.1), 2.0, 80, 2, A | FOV | REUSE | ZOOMING | ZOOM_IN, True, (30, 40), params=N_ITER),
     _a("adv_ragged_f64", "mandelbrot", 61, 35, (-0.5, 0.0), 2.0, 200, 3, A | FOV | REUSE | ZOOMING | ZOOM_IN, True, (30, 17)),
 ]
 

@@ -21,7 +21,9 @@ sys.path.insert(0, str(ROOT / "tests"))
 import cases  # noqa: E402
 import oracle  # noqa: E402
 
-FILE_OF = {"mandelbrot": "mandelbrot", "julia": "julia", "test": "test"}
+import helpers  # noqa: E402
+
+FILE_OF = {k: k for k in cases.DISPLAY_NAME}
 
 
 def pack(rec):
@@ -30,10 +32,7 @@ def pack(rec):
 
 
 def setup(rr, case):
-    if case["fractal"] == "julia":
-        rr.write_constant("julia_c", np.array(case["julia_c"], dtype=np.float64).tobytes())
-    if case["fractal"] == "test":
-        rr.write_constant("amplifier", np.array([case["amplifier"]], dtype=np.int32).tobytes())
+    helpers.setup_reference(rr, case)
 
 
 def main(outdir):
@@ -42,7 +41,7 @@ def main(outdir):
     pal = oracle.default_palette()
     report = {}
     for kind in ("src", "ptx92"):
-        for case in cases.MAIN_CASES:
+        for case in cases.MAIN_CASES + cases.EXTRA_MAIN_CASES:
             with oracle.RefRun(FILE_OF[case["fractal"]], kind) as rr:
                 setup(rr, case)
                 rec = rr.main(case["W"], case["H"], case["image"], case["maxIter"], case["maxSS"], case["flags"], case["double"])

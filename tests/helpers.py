@@ -25,8 +25,7 @@ def model_for(cu, case, image=None, maxSS=None):
 
 
 def open_renderer(cu, provider, case, palette=None, mode=None):
-    names = {"mandelbrot": "mandelbrot", "julia": "julia", "test": "test"}
-    r = provider.getRenderer(names[case["fractal"]], False)
+    r = provider.getRenderer(cases.DISPLAY_NAME[case["fractal"]], False)
     if r.getState() == cu.STATE_READY_TO_RENDER:
         r.freeRenderingResources()
     r.initializeRendering(case["W"], case["H"], palette, cu.OUTPUT_HOST if mode is None else mode)
@@ -34,7 +33,24 @@ def open_renderer(cu, provider, case, palette=None, mode=None):
         r.setFractalCustomParams("%r;%r" % tuple(case["julia_c"]))
     if case["fractal"] == "test":
         r.setFractalCustomParams(str(case["amplifier"]))
+    if "params" in case:
+        r.setFractalCustomParams(case["params"])
     return r
+
+
+def setup_reference(rr, case):
+    """write the module constants the Java host would write for this case into a reference module"""
+    import numpy as np
+    if case["fractal"] == "julia":
+        rr.write_constant("julia_c", np.array(case["julia_c"], dtype=np.float64).tobytes())
+    if case["fractal"] == "test":
+        rr.write_constant("amplifier", np.array([case["amplifier"]], dtype=np.int32).tobytes())
+    if "params" in case:
+        roots, coefs, mag = cases.newton_constants(case["params"])
+        rr.write_constant("roots", np.array(roots, dtype=np.float64).tobytes())
+        rr.write_constant("coefficients", np.array(coefs, dtype=np.float64).tobytes())
+        if mag is not None:
+            rr.write_constant("colorMagnifier", np.array([mag], dtype=np.int32).tobytes())
 
 
 def assert_records_equal(got, want, what=""):

@@ -10,7 +10,7 @@ import cases
 import oracle
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-ALL = cases.MAIN_CASES + cases.ADV_CASES
+ALL = cases.MAIN_CASES + cases.EXTRA_MAIN_CASES + cases.ADV_CASES
 
 
 def _load(case):
@@ -49,7 +49,10 @@ def test_oracle_main_equals_reference_kernels(case):
     assert (oracle.compose(case["fractal"], res.records, pal, case["maxSS"], True) == g["src_vis"]).all()
 
 
-@pytest.mark.parametrize("case", cases.ADV_CASES, ids=[c["name"] for c in cases.ADV_CASES])
+ADV_ORACLE = [c for c in cases.ADV_CASES if c["fractal"] in oracle.FRACTAL_KINDS]
+
+
+@pytest.mark.parametrize("case", ADV_ORACLE, ids=[c["name"] for c in ADV_ORACLE])
 def test_oracle_advanced_equals_reference_kernels(case):
     g = _load(case)
     img0, img1 = cases.adv_segments(case)

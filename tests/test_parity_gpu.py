@@ -53,8 +53,11 @@ def test_main_matches_oracle(cu, provider, engine, case):
     assert not m.sampleReuseCacheDirty
 
 
+ALL_MAIN = cases.MAIN_CASES + cases.EXTRA_MAIN_CASES
+
+
 @pytest.mark.skipif(not _have_ref(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("case", cases.MAIN_CASES, ids=_ids(cases.MAIN_CASES))
+@pytest.mark.parametrize("case", ALL_MAIN, ids=_ids(ALL_MAIN))
 def test_main_matches_live_reference(cu, provider, case):
     r = helpers.open_renderer(cu, provider, case)
     m = helpers.model_for(cu, case)
@@ -62,17 +65,17 @@ def test_main_matches_live_reference(cu, provider, case):
     got = r.downloadRecords()
     rgba = r.outputRGBA().copy()
     with oracle.RefRun(case["fractal"], "src") as rr:
-        if case["fractal"] == "julia":
-            rr.write_constant("julia_c", np.array(case["julia_c"], dtype=np.float64).tobytes())
-        if case["fractal"] == "test":
-            rr.write_constant("amplifier", np.array([case["amplifier"]], dtype=np.int32).tobytes())
+        helpers.setup_reference(rr, case)
         want = rr.main(case["W"], case["H"], case["image"], case["maxIter"], case["maxSS"], case["flags"], case["double"])
         want_rgba = rr.compose(want, cu.createDefaultColorPalette(), case["maxSS"], False)
     helpers.assert_records_equal(got, want, case["name"] + " vs reference kernels")
     assert (rgba == want_rgba).all()
 
 
-@pytest.mark.parametrize("case", cases.ADV_CASES, ids=_ids(cases.ADV_CASES))
+ADV_ORACLE = [c for c in cases.ADV_CASES if c["fractal"] in oracle.FRACTAL_KINDS]
+
+
+@pytest.mark.parametrize("case", ADV_ORACLE, ids=_ids(ADV_ORACLE))
 def test_advanced_matches_oracle(cu, provider, case):
     img0, img1 = cases.adv_segments(case)
     r = helpers.open_renderer(cu, provider, case)
@@ -109,10 +112,7 @@ def test_advanced_matches_live_reference(cu, provider, case):
     r.renderFast(m1)
     got = r.downloadRecords()
     with oracle.RefRun(case["fractal"], "src") as rr:
-        if case["fractal"] == "julia":
-            rr.write_constant("julia_c", np.array(case["julia_c"], dtype=np.float64).tobytes())
-        if case["fractal"] == "test":
-            rr.write_constant("amplifier", np.array([case["amplifier"]], dtype=np.int32).tobytes())
+        helpers.setup_reference(rr, case)
         rec0 = rr.main(case["W"], case["H"], img0, case["maxIter"], case["maxSS0"], case["flags"], case["double"])
         want = rr.advanced(case["W"], case["H"], img1, case["maxIter"], case["maxSS"], case["flags"], img0, rec0,
                            case["focus"], case["double"])
@@ -145,7 +145,7 @@ def test_device_output_mode(cu, provider):
     assert (r.outputRGBA() == oracle.compose(case["fractal"], want.records, cu.createDefaultColorPalette(), 1.0)).all()
 
 
-@pytest.mark.parametrize("case", cases.MAIN_CASES + cases.ADV_CASES, ids=_ids(cases.MAIN_CASES + cases.ADV_CASES))
+@pytest.mark.parametrize("case", ALL_MAIN + cases.ADV_CASES, ids=_ids(ALL_MAIN + cases.ADV_CASES))
 def test_matches_golden_fixture(cu, provider, case):
     f = GOLDEN / (case["name"] + ".npz")
     if not f.exists():
