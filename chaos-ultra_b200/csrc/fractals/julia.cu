@@ -18,6 +18,10 @@ struct Fractal {
         }
         __device__ __forceinline__ void force_exact() { q.force_exact(); }
         __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit) { return q.run(i, limit); }
+        static __device__ __forceinline__ void run_pair(Orbit &a, uint32_t &ia, uint32_t la, bool &ea, Orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
+        {
+            quadratic_orbit<Real>::run_pair(a.q, ia, la, ea, b.q, ib, lb, eb);
+        }
         __device__ __forceinline__ uint32_t finish(uint32_t i, uint32_t) const
         {
             return __float2uint_rz(__uint2float_rn(i));

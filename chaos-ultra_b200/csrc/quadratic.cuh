@@ -52,6 +52,29 @@ template <class Real> struct quadratic_orbit {
         x = xn;
         return below;
     }
+    /* Two orbits stepped together (their dependency chains interleave).  An orbit that ended keeps being stepped
+     * -- its state is garbage nobody reads -- so that all lanes of a warp stay in this one loop instead of
+     * diverging into a single-orbit loop; the pair is left only when both ended or a live one reaches its limit
+     * (the caller finishes leftovers with run()). */
+    static __device__ __forceinline__ void run_pair(quadratic_orbit &a, uint32_t &ia, uint32_t la, bool &ea,
+                                                    quadratic_orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
+    {
+        /* groups of four trips both orbits can still take inside their limits; counts are settled once at the end
+         * (or at the group in which an orbit ended), the hot loop only counts groups */
+        const uint32_t n = min((la - ia) >> 2, (lb - ib) >> 2);
+        uint32_t g = 0;
+        while (g < n && (!ea | !eb)) {
+            bool a0 = a.step(), b0 = b.step(), a1 = a.step(), b1 = b.step(), a2 = a.step(), b2 = b.step(), a3 = a.step(), b3 = b.step();
+            const bool fa = !(a0 & a1 & a2 & a3) & !ea, fb = !(b0 & b1 & b2 & b3) & !eb;
+            if (fa | fb) {
+                if (fa) { ia += 4u * g + (a0 ? (a1 ? (a2 ? 3u : 2u) : 1u) : 0u); ea = true; }
+                if (fb) { ib += 4u * g + (b0 ? (b1 ? (b2 ? 3u : 2u) : 1u) : 0u); eb = true; }
+            }
+            ++g;
+        }
+        if (!ea) ia += 4u * g;
+        if (!eb) ib += 4u * g;
+    }
     /* advance while i < limit; true = the escape test failed at trip i (i is the exact count) */
     __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit)
     {
@@ -139,6 +162,35 @@ template <> struct quadratic_orbit<double> {
     __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit)
     {
         return scaled ? run_as<true>(i, limit) : run_as<false>(i, limit);
+    }
+    template <bool kScaled>
+    static __device__ __forceinline__ void run_pair_as(quadratic_orbit &a, uint32_t &ia, uint32_t la, bool &ea,
+                                                       quadratic_orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
+    {
+        /* groups of four trips both orbits can still take inside their limits; counts are settled once at the end
+         * (or at the group in which an orbit ended), the hot loop only counts groups */
+        const uint32_t n = min((la - ia) >> 2, (lb - ib) >> 2);
+        uint32_t g = 0;
+        while (g < n && (!ea | !eb)) {
+            bool a0 = a.step<kScaled>(), b0 = b.step<kScaled>(), a1 = a.step<kScaled>(), b1 = b.step<kScaled>();
+            bool a2 = a.step<kScaled>(), b2 = b.step<kScaled>(), a3 = a.step<kScaled>(), b3 = b.step<kScaled>();
+            const bool fa = !(a0 & a1 & a2 & a3) & !ea, fb = !(b0 & b1 & b2 & b3) & !eb;
+            if (fa | fb) {
+                if (fa) { ia += 4u * g + (a0 ? (a1 ? (a2 ? 3u : 2u) : 1u) : 0u); ea = true; }
+                if (fb) { ib += 4u * g + (b0 ? (b1 ? (b2 ? 3u : 2u) : 1u) : 0u); eb = true; }
+            }
+            ++g;
+        }
+        if (!ea) ia += 4u * g;
+        if (!eb) ib += 4u * g;
+    }
+    /* two orbits stepped together; a pair in different forms is brought to the 7-operation form first (exact) */
+    static __device__ __forceinline__ void run_pair(quadratic_orbit &a, uint32_t &ia, uint32_t la, bool &ea,
+                                                    quadratic_orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
+    {
+        if (a.scaled != b.scaled) { a.force_exact(); b.force_exact(); }
+        if (a.scaled) run_pair_as<true>(a, ia, la, ea, b, ib, lb, eb);
+        else run_pair_as<false>(a, ia, la, ea, b, ib, lb, eb);
     }
 };
 
