@@ -303,7 +303,7 @@ struct chaos_renderer {
     CUfunction k_classify = nullptr, k_order = nullptr;            /* between the two passes of engine 1 */
     CUfunction k_reuse_f = nullptr, k_reuse_d = nullptr;           /* pass R of a fast frame */
     int blocks_reuse_f = 0, blocks_reuse_d = 0;
-    CUdeviceptr tile_key = 0, tile_order = 0;
+    CUdeviceptr tile_key = 0, tile_order = 0, tile_tmax = 0, tile_tmin = 0;
     uint32_t two_pass = 1;
     uint32_t sync_below_iters = 2048;   /* see render_quality_locked */
     int blocks_main_f_sync = 0, blocks_main_d_sync = 0;
@@ -539,6 +539,8 @@ static void free_frame_memory(chaos_renderer *r)
     if (r->palette) { D->p_cuMemFree(r->palette); r->palette = 0; }
     if (r->tile_key) { D->p_cuMemFree(r->tile_key); r->tile_key = 0; }
     if (r->tile_order) { D->p_cuMemFree(r->tile_order); r->tile_order = 0; }
+    if (r->tile_tmax) { D->p_cuMemFree(r->tile_tmax); r->tile_tmax = 0; }
+    if (r->tile_tmin) { D->p_cuMemFree(r->tile_tmin); r->tile_tmin = 0; }
     if (r->rgba_host) { D->p_cuMemFreeHost(r->rgba_host); r->rgba_host = nullptr; r->rgba_dev = 0; }
     if (r->rgba_dev) { D->p_cuMemFree(r->rgba_dev); r->rgba_dev = 0; }
 }
@@ -566,6 +568,8 @@ extern "C" chaos_status chaos_initialize(chaos_renderer *r, uint32_t width, uint
     const size_t all_tiles = (size_t)((width + 7u) / 8u) * ((height + 3u) / 4u);
     CUresult e = D->p_cuMemAlloc(&r->tile_key, all_tiles * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->tile_order, all_tiles * 4u);
+    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->tile_tmax, all_tiles * 4u);
+    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->tile_tmin, all_tiles * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->palette, (size_t)palette_len * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemcpyHtoD(r->palette, palette_rgba, (size_t)palette_len * 4u);
     size_t frame_bytes = (size_t)width * height * 4u;
@@ -752,6 +756,8 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
             owned_rows += std::min(a->band_tile_rows, a->tile_rows - b * a->band_tile_rows);
     }
     a->n_tiles = owned_rows * a->tiles_x;
+    a->tile_tmax = (uint32_t *)r->tile_tmax;
+    a->tile_tmin = (uint32_t *)r->tile_tmin;
     a->tile_key = (uint32_t *)r->tile_key;
     a->tile_order = (uint32_t *)r->tile_order;
     a->engine = r->engine;
@@ -853,11 +859,15 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
             st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a);
         } else if (S0 >= 2u && r->two_pass) {
             /* pass A: sample 0 of every pixel; classify + order: expected-longest tiles first; pass B: the other rounds */
-            const int cap = r->provider->sm_count * 8;
+            const int cap = r->provider->sm_count * 4;
+            const int small_grid = (int)std::min<uint64_t>((a.n_tiles + 255u) / 256u, (uint64_t)cap);
+            CUresult em = D->p_cuMemsetD32Async(r->tile_tmax, 0u, a.n_tiles, r->stream);
+            if (em == CUDA_SUCCESS) em = D->p_cuMemsetD32Async(r->tile_tmin, 0xffffffffu, a.n_tiles, r->stream);
+            if (em != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed: %s", cu_err_name(em));
             a.phase = 1u;
             st = launch(r, k1, b1, 256, r->refill_smem, &a);
-            if (st == CHAOS_OK) st = launch(r, r->k_classify, (int)std::min<uint64_t>((a.n_tiles + 7u) / 8u, (uint64_t)cap), 256, 0, &a);
-            if (st == CHAOS_OK) st = launch(r, r->k_order, (int)std::min<uint64_t>((a.n_tiles + 255u) / 256u, (uint64_t)cap), 256, 0, &a);
+            if (st == CHAOS_OK) st = launch(r, r->k_classify, small_grid, 256, 0, &a);
+            if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &a);
             a.phase = 2u;
             if (st == CHAOS_OK) st = launch(r, k1, b1, 256, r->refill_smem, &a);
         } else {

@@ -142,12 +142,12 @@ static __device__ void render_main_independent(const chaos_render_args &a)
     sample_delta<Real>(0u, 0.f, dx0, dy0);                  /* sample 0 sits at offset 0/3 */
 
     Orbit o[U];
-    uint32_t it[U], px[U], py[U];
+    uint32_t it[U], px[U], py[U], tile[U];
     bool busy[U];
 #pragma unroll
-    for (int j = 0; j < U; ++j) { it[j] = 0; px[j] = py[j] = 0; busy[j] = false; }
+    for (int j = 0; j < U; ++j) { it[j] = 0; px[j] = py[j] = tile[j] = 0; busy[j] = false; }
     bool first = true, queue_empty = false;
-    uint32_t pend = 0, x0 = 0, y0 = 0;                       /* warp-uniform: the tile being handed out */
+    uint32_t pend = 0, x0 = 0, y0 = 0, cur_tile = 0;         /* warp-uniform: the tile being handed out */
     unsigned long long iters = 0, nsamples = 0;
 
     for (;;) {
@@ -164,8 +164,11 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                 uint32_t et = o[j].finish(it[j], max_iter);
                 iters += it[j];
                 nsamples += 1;
-                if (kProbe)   /* pass A: park (escape time, trips) in the record for chaosClassifyTiles and pass B */
+                if (kProbe) { /* pass A: park the escape time in the record for pass B, fold the trip count into the tile's statistics */
                     store_record(record_at(a.out, a.out_pitch, px[j], py[j]), __uint_as_float(et), __uint_as_float(it[j]), 0u, 0.f);
+                    atomicMax(&a.tile_tmax[tile[j]], it[j]);
+                    atomicMin(&a.tile_tmin[tile[j]], it[j]);
+                }
                 else          /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
                     store_record(record_at(a.out, a.out_pitch, px[j], py[j]), __uint2float_rn(et), 1.0f, 0u, 0.f);
                 busy[j] = false;
@@ -182,6 +185,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                     if (lane == 0) t = atomicAdd(&a.counters->next_tile, 1u);
                     t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
                     if (t >= a.n_tiles) { queue_empty = true; break; }
+                    cur_tile = t;
                     tile_origin(a, t, x0, y0);
                     pend = __ballot_sync(CHAOS_FULL_MASK, (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height);
                 }
@@ -192,6 +196,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                     mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
                     px[j] = x0 + (mypix & 7u);
                     py[j] = y0 + (mypix >> 3);
+                    tile[j] = cur_tile;
                     Real cx, cy;
                     fm.template plane_point<fused_plane_y<FractalT>::value>(px[j], py[j], dx0, dy0, cx, cy);
                     o[j].start(cx, cy);
@@ -388,43 +393,55 @@ static __device__ __forceinline__ void render_main_refill(const chaos_render_arg
 
 
 /* ---- cost classes between the two passes ------------------------------------------------------ */
-/* One warp per tile.  Expected critical path of the tile's remaining rounds, from pass A's trip counts:
- * longest orbit x (S0 - 1) rounds if the pixels disagree (the tile will probably use its whole sample budget),
- * x 1 if all 32 agree (the i == 1 vote will most likely end it after one more round).  class = 36 - floor(log2(est)):
- * class 0 is taken first by pass B. */
+/* Expected critical path of a tile's remaining rounds from pass A's trip counts (tile_tmax/tile_tmin):
+ *   longest orbit x (S0 - 1) rounds if the pixels disagree (the tile will probably use its whole sample budget),
+ *   x 1 if all agree (the i == 1 vote will most likely end it after one more round).
+ * (Also ranking a tile by its 8 neighbours' longest orbit -- to catch boundary tiles whose own sample-0 orbits all
+ * escaped -- was measured: it made c2 slower, 19.0 vs 17.7 ms, and is not done.)
+ * class = 36 - floor(log2(est)), class 0 is taken first by pass B.  One thread per tile; the histogram is
+ * accumulated per block in shared memory (one global atomic per class and block). */
 static __device__ void classify_tiles(const chaos_render_args &a)
 {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ uint32_t hist[CHAOS_COST_BUCKETS];
+    for (uint32_t k = threadIdx.x; k < CHAOS_COST_BUCKETS; k += blockDim.x) hist[k] = 0u;
+    __syncthreads();
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
-    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < a.n_tiles; t += warps) {
-        uint32_t x0, y0;
-        tile_origin(a, t, x0, y0);
-        const uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
-        const bool in = px < a.width && py < a.height;
-        const uint32_t trips = in ? __float_as_uint(record_at(a.out, a.out_pitch, px, py)->weight) : 0u;
-        const uint32_t tmax = __reduce_max_sync(CHAOS_FULL_MASK, trips);
-        const uint32_t tmin = __reduce_min_sync(CHAOS_FULL_MASK, in ? trips : 0xffffffffu);
-        const unsigned long long est = (unsigned long long)(tmax | 1u) * (tmax == tmin ? 1u : (S0 > 1u ? S0 - 1u : 1u));
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_tiles; t += gridDim.x * blockDim.x) {
+        const uint32_t own_max = a.tile_tmax[t], own_min = a.tile_tmin[t];
+        const uint32_t nmax = own_max;
+        const bool uniform = own_max == own_min;
+        const unsigned long long est = (unsigned long long)(nmax | 1u) * (uniform ? 1u : (S0 > 1u ? S0 - 1u : 1u));
         const uint32_t key = (uint32_t)__clzll((long long)est) - 27u;      /* est < 2^37: clzll in [27,63] -> key in [0,36] */
-        if (lane == 0) {
-            a.tile_key[t] = key;
-            atomicAdd(&a.counters->bucket_count[key], 1u);
-        }
+        a.tile_key[t] = key;
+        atomicAdd(&hist[key], 1u);
     }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < CHAOS_COST_BUCKETS; k += blockDim.x)
+        if (hist[k]) atomicAdd(&a.counters->bucket_count[k], hist[k]);
 }
-/* counting-sort scatter: one thread per tile */
+/* counting-sort scatter: one thread per tile; every block reserves one range per class */
 static __device__ void order_tiles(const chaos_render_args &a)
 {
-    __shared__ uint32_t base[CHAOS_COST_BUCKETS];
+    __shared__ uint32_t base[CHAOS_COST_BUCKETS], cnt[CHAOS_COST_BUCKETS], off[CHAOS_COST_BUCKETS];
+    for (uint32_t k = threadIdx.x; k < CHAOS_COST_BUCKETS; k += blockDim.x) cnt[k] = 0u;
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
         for (uint32_t j = 0; j < CHAOS_COST_BUCKETS; ++j) { base[j] = acc; acc += a.counters->bucket_count[j]; }
     }
     __syncthreads();
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_tiles; t += gridDim.x * blockDim.x) {
+    /* a block owns a contiguous chunk of tiles */
+    const uint32_t per_block = (a.n_tiles + gridDim.x - 1u) / gridDim.x;
+    const uint32_t t0 = blockIdx.x * per_block, t1 = min(a.n_tiles, t0 + per_block);
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) atomicAdd(&cnt[a.tile_key[t]], 1u);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < CHAOS_COST_BUCKETS; k += blockDim.x) {
+        off[k] = cnt[k] ? base[k] + atomicAdd(&a.counters->bucket_cursor[k], cnt[k]) : 0u;
+        cnt[k] = 0u;
+    }
+    __syncthreads();
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
         const uint32_t key = a.tile_key[t];
-        a.tile_order[base[key] + atomicAdd(&a.counters->bucket_cursor[key], 1u)] = t;
+        a.tile_order[off[key] + atomicAdd(&cnt[key], 1u)] = t;
     }
 }
 
