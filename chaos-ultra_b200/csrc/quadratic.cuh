@@ -8,8 +8,8 @@
  * and the trip COUNT must come out bit-identical.  Two things are done differently here, neither of
  * which can change a count:
  *
- * 1. Trips run in unrolled groups of four with the four "still below 4" predicates tested once per
- *    group.  After the first failing test the remaining steps of the group compute garbage
+ * 1. Trips run in unrolled groups (eight in the FP64 loop, four elsewhere) with the "still below 4" predicates
+ *    tested once per group.  After the first failing test the remaining steps of the group compute garbage
  *    (inf/NaN, no traps) that is never looked at; the count is the index of the first failure.
  *
  * 2. FP64 only: the orbit is carried as X = 2x, Y = 2y with CX = 2cx, CY = 2cy:
@@ -145,6 +145,15 @@ template <> struct quadratic_orbit<double> {
     template <bool kScaled> __device__ __forceinline__ bool step() { return kScaled ? step_scaled() : step_exact(); }
     template <bool kScaled> __device__ __forceinline__ bool run_as(uint32_t &i, uint32_t limit)
     {
+        while (i + 8u <= limit) {      /* groups of eight trips: one branch per 48 FP64 instructions (16 measured no better) */
+            bool p0 = step<kScaled>(), p1 = step<kScaled>(), p2 = step<kScaled>(), p3 = step<kScaled>();
+            bool p4 = step<kScaled>(), p5 = step<kScaled>(), p6 = step<kScaled>(), p7 = step<kScaled>();
+            if (!(p0 & p1 & p2 & p3 & p4 & p5 & p6 & p7)) {
+                i += p0 ? (p1 ? (p2 ? (p3 ? (p4 ? (p5 ? (p6 ? 7u : 6u) : 5u) : 4u) : 3u) : 2u) : 1u) : 0u;
+                return true;
+            }
+            i += 8u;
+        }
         while (i + 4u <= limit) {
             bool p0 = step<kScaled>(), p1 = step<kScaled>(), p2 = step<kScaled>(), p3 = step<kScaled>();
             if (!(p0 & p1 & p2 & p3)) {
