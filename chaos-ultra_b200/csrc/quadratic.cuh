@@ -78,6 +78,14 @@ template <class Real> struct quadratic_orbit {
     /* advance while i < limit; true = the escape test failed at trip i (i is the exact count) */
     __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit)
     {
+        while (i + 8u <= limit) {
+            bool p0 = step(), p1 = step(), p2 = step(), p3 = step(), p4 = step(), p5 = step(), p6 = step(), p7 = step();
+            if (!(p0 & p1 & p2 & p3 & p4 & p5 & p6 & p7)) {
+                i += p0 ? (p1 ? (p2 ? (p3 ? (p4 ? (p5 ? (p6 ? 7u : 6u) : 5u) : 4u) : 3u) : 2u) : 1u) : 0u;
+                return true;
+            }
+            i += 8u;
+        }
         while (i + 4u <= limit) {
             bool p0 = step(), p1 = step(), p2 = step(), p3 = step();
             if (!(p0 & p1 & p2 & p3)) {
