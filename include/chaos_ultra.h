@@ -62,7 +62,7 @@ typedef enum chaos_output_mode {
     CHAOS_OUTPUT_DEVICE = 1 /* compose stores to device memory; chaos_download_rgba() copies on demand */
 } chaos_output_mode;
 
-/* The getters of RenderingModel (rendering/model/*.java) that the renderer reads, plus the two
+/* The getters of RenderingModel (the interfaces under rendering/model/) that the renderer reads, plus the two
  * values it writes back (sampleReuseCacheDirty, floatingPointPrecision). */
 typedef struct chaos_params {
     uint32_t struct_size;       /* = sizeof(chaos_params) */
@@ -81,7 +81,7 @@ typedef struct chaos_params {
     int32_t float_precision;    /* out: chaos_precision chosen for this frame */
 } chaos_params;
 
-/* DefaultFractalModel values a module supplies (modules/Module*.java supplyDefaultValues) */
+/* DefaultFractalModel values a module supplies (supplyDefaultValues of the classes under cudarenderer/modules/) */
 typedef struct chaos_defaults {
     uint32_t struct_size;
     uint8_t has_segment;        /* setPlaneSegmentFromCenter was called */

@@ -207,3 +207,65 @@ def test_engines_agree_at_full_size(cu, provider, case):
     # sanity of the exact counter: every sample contributes between 0 and maxIter trips
     assert out[1][2] >= case["W"] * case["H"]
     assert out[1][1] <= out[1][2] * case["maxIter"]
+
+
+# ---- BASELINE.json's own shapes against the reference's own kernels, run live on the same device ---------------------
+# (the reference has no CPU path, but its kernels are fast enough on a B200 to serve as the full-size checker)
+REF_FULL = [
+    dict(name="ref_c1_1024_f64", fractal="mandelbrot", W=1024, H=1024, image=cases.seg(-0.5, 0.0, 2.0, 1024, 1024), maxIter=500,
+         maxSS=1.0, flags=0, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ref_c2_4k_a8_f64", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.5, 0.0, 2.0, 3840, 2160), maxIter=10000,
+         maxSS=8.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ref_c2ex2_4k_a8_f64", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.235125, 0.827215, 4.0e-5, 3840, 2160),
+         maxIter=2500, maxSS=8.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ref_c2_4k_a8_f32", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.5, 0.0, 2.0, 3840, 2160), maxIter=2500,
+         maxSS=8.0, flags=cases.A, double=False, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ref_c4_2k_1s_f64", fractal="mandelbrot", W=2048, H=2048,
+         image=cases.seg(-0.551042868375875, 0.62714332109057, 8.00592947491907e-9, 2048, 2048), maxIter=20000, maxSS=1.0, flags=0,
+         double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ref_c5_4k_a8_f64", fractal="julia", W=3840, H=2160, image=cases.seg(0.0, 0.0, 4.0, 3840, 2160), maxIter=900, maxSS=8.0,
+         flags=cases.A, double=True, julia_c=(-0.4, 0.6), amplifier=10),
+    dict(name="ref_julia_real_c_4k_f64", fractal="julia", W=3840, H=2160, image=cases.seg(0.0, 0.0, 0.68, 3840, 2160), maxIter=900, maxSS=4.0,
+         flags=cases.A, double=True, julia_c=(-1.77578, 0.0), amplifier=10),   # c.im == 0: every orbit takes the 7-operation form
+    dict(name="ref_newton_4k_f32", fractal="newton_generic", W=3840, H=2160, image=cases.seg(0.0, 0.0, 4.0, 3840, 2160), maxIter=100, maxSS=3.0,
+         flags=cases.A, double=False, julia_c=(0.0, 0.0), amplifier=10, params=cases.N3),
+]
+
+
+@pytest.mark.skipif(not _have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", REF_FULL, ids=_ids(REF_FULL))
+def test_full_size_frame_matches_live_reference(cu, provider, case):
+    r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+    r.renderQuality(helpers.model_for(cu, case))
+    got, rgba = r.downloadRecords(), r.outputRGBA()
+    with oracle.RefRun(case["fractal"], "src") as rr:
+        helpers.setup_reference(rr, case)
+        want = rr.main(case["W"], case["H"], case["image"], case["maxIter"], case["maxSS"], case["flags"], case["double"])
+        want_rgba = rr.compose(want, cu.createDefaultColorPalette(), case["maxSS"], False)
+    helpers.assert_records_equal(got, want, case["name"])
+    assert (rgba == want_rgba).all()
+
+
+@pytest.mark.skipif(not _have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("double", [False, True], ids=["f32", "f64"])
+def test_zoom_sequence_4k_matches_live_reference(cu, provider, double):
+    """config c3 shape: frame 0 quality, then fast frames, every frame compared with the reference's kernels fed with the
+    reference's own previous frame (so errors cannot hide by accumulating identically)."""
+    W, H, focus = 3840, 2160, (1920, 1080)
+    flags = cases.A | cases.FOV | cases.REUSE | cases.ZOOMING | cases.ZOOM_IN
+    base = dict(name="zoom4k", fractal="mandelbrot", W=W, H=H, maxIter=1600, maxSS=2.0, flags=flags, double=double,
+                julia_c=(0.0, 0.0), amplifier=10, focus=focus)
+    seg = cases.seg(-0.748, 0.1, 2.0 if not double else 1.0e-4, W, H)
+    r = helpers.open_renderer(cu, provider, dict(base, image=seg), mode=cu.OUTPUT_DEVICE)
+    r.renderQuality(helpers.model_for(cu, dict(base, image=seg)))
+    with oracle.RefRun("mandelbrot", "src") as rr:
+        ref_prev = rr.main(W, H, seg, 1600, 2.0, flags, double)
+        helpers.assert_records_equal(r.downloadRecords(), ref_prev, "frame 0")
+        for f in range(1, 5):
+            new_seg = cases.zoom_at(seg, W, H, focus, True)
+            r.renderFast(helpers.model_for(cu, dict(base, image=new_seg)))
+            got = r.downloadRecords()
+            want = rr.advanced(W, H, new_seg, 1600, 2.0, flags, seg, ref_prev, focus, double)
+            helpers.assert_records_equal(got, want, "frame %d" % f)
+            assert got["isReused"].mean() > 0.9 and (got["weightOfNewSamples"] > 0).sum() > 10000
+            seg, ref_prev = new_seg, want
