@@ -28,6 +28,55 @@ static __device__ __forceinline__ unsigned int newton_convergence_root(thrust::c
     return 0;
 }
 
+/* one Newton step x - p(x)/p'(x) for p = c[0] + c[1] x + c[2] x^2 + c[3] x^3 (c in double, mixed with complex<Real>
+ * exactly as newton_generic.cu:12-26 mixes them: products are promoted to complex<double>, the result is narrowed) */
+template <class Real>
+static __device__ __forceinline__ thrust::complex<Real> newton_step_cubic(const double *c, thrust::complex<Real> x)
+{
+    thrust::complex<Real> x_pow_2 = x * x;
+    thrust::complex<Real> x_pow_3 = x_pow_2 * x;
+    thrust::complex<Real> f_eval_x = c[0] +
+                                     c[1] * x +
+                                     c[2] * x_pow_2 +
+                                     c[3] * x_pow_3;
+    thrust::complex<Real> f_derivative_eval_x = c[1] +
+                                                c[2] * 2 * x +
+                                                c[3] * 3 * x_pow_2;
+    return x - (f_eval_x / f_derivative_eval_x);
+}
+
+/* the same for the hard-wired polynomial x^3 - 1 (newton_wired.cu:8-16) */
+template <class Real>
+static __device__ __forceinline__ thrust::complex<Real> newton_step_unity(thrust::complex<Real> x)
+{
+    thrust::complex<Real> x_pow_2 = x * x;
+    thrust::complex<Real> x_pow_3 = x_pow_2 * x;
+    thrust::complex<Real> f_eval_x = x_pow_3 - 1;
+    thrust::complex<Real> f_derivative_eval_x = 3 * x_pow_2;
+    return x - (f_eval_x / f_derivative_eval_x);
+}
+
+/* Iterate Step until Root says "converged", testing after 10 steps and then every maxIterations/10 further steps
+ * (newton_wired.cu:52-66 = newton_generic.cu:56-70); the value is the root index (0 = none) */
+template <class Real, class Step, class Root>
+static __device__ __forceinline__ float newton_root_search(uint32_t maxIterations, Real px, Real py, uint32_t &trips, Step step, Root root_of)
+{
+    thrust::complex<Real> x(px, py);
+    unsigned int i = 0;
+    unsigned int check_at = 10;
+    while (i < maxIterations) {
+        x = step(x);
+        ++i;
+        if (i == check_at) {
+            unsigned int root = root_of(x);
+            if (root != 0) { trips = i; return root; }
+            check_at += maxIterations / 10;
+        }
+    }
+    trips = i;
+    return root_of(x);
+}
+
 /* fixed colours of the root-coloured modules (helpers.cuh:150-162, R in the low byte) */
 static __device__ __forceinline__ uint32_t newton_root_colour(float result)
 {

@@ -11,34 +11,15 @@ __constant__ double coefficients[4];
 __constant__ int colorMagnifier;
 
 struct NewtonIterationsImpl {
-    template <class Real> static __device__ __forceinline__ thrust::complex<Real> step(thrust::complex<Real> x)
-    {
-        thrust::complex<Real> x_pow_2 = x * x;
-        thrust::complex<Real> x_pow_3 = x_pow_2 * x;
-        thrust::complex<Real> f_eval_x = coefficients[0] +
-                                         coefficients[1] * x +
-                                         coefficients[2] * x_pow_2 +
-                                         coefficients[3] * x_pow_3;
-        thrust::complex<Real> f_derivative_eval_x = coefficients[1] +
-                                                    coefficients[2] * 2 * x +
-                                                    coefficients[3] * 3 * x_pow_2;
-        return x - (f_eval_x / f_derivative_eval_x);
-    }
-    template <class Real> static __device__ __forceinline__ unsigned int root_of(thrust::complex<Real> x)
-    {
-        const thrust::complex<Real> root_a(roots[0], roots[1]);
-        const thrust::complex<Real> root_b(roots[2], roots[3]);
-        const thrust::complex<Real> root_c(roots[4], roots[5]);
-        return newton_convergence_root<Real>(x, root_a, root_b, root_c);
-    }
     template <class Real> static __device__ float compute(uint32_t maxIterations, Real px, Real py, uint32_t &trips)
     {
-        thrust::complex<Real> x(px, py);
+        typedef thrust::complex<Real> cplx;
+        cplx x(px, py);
         unsigned int i = 0;
         while (i < maxIterations) {
-            x = step<Real>(x);
+            x = newton_step_cubic<Real>(coefficients, x);
             ++i;
-            if (root_of<Real>(x) != 0) break;
+            if (newton_convergence_root<Real>(x, cplx(roots[0], roots[1]), cplx(roots[2], roots[3]), cplx(roots[4], roots[5])) != 0) break;
         }
         trips = i;
         return i;

@@ -5,38 +5,13 @@
 #include "newton_common.cuh"
 
 struct NewtonWiredImpl {
-    template <class Real> static __device__ __forceinline__ thrust::complex<Real> step(thrust::complex<Real> x)
-    {
-        thrust::complex<Real> x_pow_2 = x * x;
-        thrust::complex<Real> x_pow_3 = x_pow_2 * x;
-        thrust::complex<Real> f_eval_x = x_pow_3 - 1;
-        thrust::complex<Real> f_derivative_eval_x = 3 * x_pow_2;
-        return x - (f_eval_x / f_derivative_eval_x);
-    }
-    template <class Real> static __device__ __forceinline__ unsigned int root_of(thrust::complex<Real> x)
-    {
-        const thrust::complex<Real> root_a(1, 0);
-        const thrust::complex<Real> root_b(-0.5, 0.86602540378);
-        const thrust::complex<Real> root_c(-0.5, -0.86602540378);
-        return newton_convergence_root<Real>(x, root_a, root_b, root_c);
-    }
-    /* convergence is tested after 10 steps and then every maxIterations/10 further steps (:52-66) */
     template <class Real> static __device__ float compute(uint32_t maxIterations, Real px, Real py, uint32_t &trips)
     {
-        thrust::complex<Real> x(px, py);
-        unsigned int i = 0;
-        unsigned int check_at = 10;
-        while (i < maxIterations) {
-            x = step<Real>(x);
-            ++i;
-            if (i == check_at) {
-                unsigned int root = root_of<Real>(x);
-                if (root != 0) { trips = i; return root; }
-                check_at += maxIterations / 10;
-            }
-        }
-        trips = i;
-        return root_of<Real>(x);
+        typedef thrust::complex<Real> cplx;
+        auto root_of = [](cplx x) {
+            return newton_convergence_root<Real>(x, cplx(1, 0), cplx(-0.5, 0.86602540378), cplx(-0.5, -0.86602540378));
+        };
+        return newton_root_search<Real>(maxIterations, px, py, trips, [](cplx x) { return newton_step_unity<Real>(x); }, root_of);
     }
 };
 
