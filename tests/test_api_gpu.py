@@ -256,3 +256,28 @@ def test_partitioned_fast_frame_equals_whole_frame(cu, provider):
         for r0, r1 in part.rows_owned(rank, 2, case["H"], 8):
             out[r0:r1] = got[r0:r1]
     helpers.assert_records_equal(out, whole, "fast frame rows")
+
+
+def test_frame_driver_zoom_session_on_the_gpu(cu, provider, tmp_path):
+    """the reference's closed loop (FSM + automatic quality) around the real renderer; frames end up as PNG"""
+    import importlib
+    drv = importlib.import_module("chaos-ultra_b200.driver")
+    io = importlib.import_module("chaos-ultra_b200.imageio")
+    W, H = 640, 360
+    r = provider.getRenderer("mandelbrot", False)
+    if r.getState() == cu.STATE_READY_TO_RENDER:
+        r.freeRenderingResources()
+    r.initializeRendering(W, H)
+    m = cu.RenderingModel(canvasWidth=W, canvasHeight=H)
+    m.resetRenderingValuesToDefault()
+    r.supplyDefaultValues(m)
+    d = drv.FrameDriver(r, m)
+    h0 = m.planeSegment[3] - m.planeSegment[1]
+    n = d.run_zoom_session((W // 2, H // 2), True, frames=20)
+    assert n >= 21 and d.state.isWaiting()
+    assert [k for _, k, _, _ in d.log[:20]] == ["fast"] * 20 and d.log[-1][1] == "quality"
+    assert abs((m.planeSegment[3] - m.planeSegment[1]) / h0 - float(np.float32(0.977)) ** 20) < 1e-9
+    assert 1.0 <= m.maxSuperSampling <= 64.0
+    io.save_png(tmp_path / "last.png", r.outputRGBA())
+    assert (io.decode_png_rgba8((tmp_path / "last.png").read_bytes()) == r.outputRGBA()).all()
+    r.freeRenderingResources()

@@ -1,0 +1,118 @@
+"""CPU: the frame driver (rendering-mode FSM + automatic quality) against the reference's rules, with a stub renderer
+whose frame time is a known function of the sample budget (the role FractalRendererNullObjectVerbose plays there)."""
+import importlib
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+cu = importlib.import_module("chaos-ultra_b200")
+drv = importlib.import_module("chaos-ultra_b200.driver")
+
+
+class StubRenderer:
+    """frame time = ms_per_sample * maxSuperSampling (+1 ms), advanced on a fake clock"""
+
+    def __init__(self, clock, ms_per_sample):
+        self.clock, self.k, self.calls = clock, ms_per_sample, []
+
+    def renderFast(self, m):
+        self.calls.append(("fast", m.maxSuperSampling, m.zooming, m.zoomingIn, list(m.planeSegment)))
+        self.clock.t += 1 + self.k * m.maxSuperSampling
+
+    def renderQuality(self, m):
+        self.calls.append(("quality", m.maxSuperSampling, m.zooming, m.zoomingIn, list(m.planeSegment)))
+        self.clock.t += 1 + self.k * m.maxSuperSampling
+
+
+class Clock:
+    t = 0.0
+
+    def __call__(self):
+        return self.t
+
+
+def test_fsm_transitions_match_the_reference():
+    f = drv.RenderingModeFSM()
+    assert f.isWaiting() and not f.isZooming()
+    f.startZooming(True)
+    assert f.isZooming() and f.getZoomingDirection() and f.isDifferentThanLast()
+    f.step()
+    assert f.current == drv.ZOOMING_AUTO and not f.isDifferentThanLast()
+    f.stopZooming()
+    assert f.isWaiting() and f.last == drv.ZOOMING_AUTO
+    f.step()                                   # Waiting after ZoomingAuto -> progressive rendering, level 0
+    assert f.isProgressiveRendering() and f.getProgressiveRenderingLevel() == 0
+    for lvl in range(1, 7):
+        f.step()
+        assert f.getProgressiveRenderingLevel() == lvl
+    f.step()                                   # level 6 reached -> Waiting
+    assert f.isWaiting()
+    f.doZoomingManualOnce(False)
+    assert f.isZooming() and not f.getZoomingDirection()
+    f.step()
+    assert f.isProgressiveRendering()
+    f.startZoomingAndMoving(True)
+    assert f.isZooming() and f.isMoving()
+    f.stopZooming()
+    assert f.current == drv.MOVING and not f.isZooming()
+    f.stopMoving()
+    assert f.isWaiting()
+
+
+def test_automatic_quality_converges_to_the_frame_time_target():
+    clock = Clock()
+    m = cu.RenderingModel(canvasWidth=320, canvasHeight=180)
+    m.resetRenderingValuesToDefault()
+    r = StubRenderer(clock, ms_per_sample=3.0)
+    d = drv.FrameDriver(r, m, clock)
+    n = d.run_zoom_session((160, 90), True, frames=12)
+    fast = [c for c in r.calls if c[0] == "fast"]
+    assert len(fast) == 12 and all(c[2] and c[3] for c in fast)
+    assert fast[0][1] == 1.0                                  # mode changed -> "RESET SS" (GLRenderer.java:208-212)
+    # closed loop: SS * 15 / lastFrameTime; with t = 1 + 3 SS the fixed point is SS = 14/3
+    assert abs(fast[-1][1] - 14.0 / 3.0) < 0.35
+    assert 13 <= d.log[11][3] <= 16
+    # every zooming frame moved the segment by ZOOM_COEFF about the mouse position
+    h0 = fast[0][4][3] - fast[0][4][1]
+    h1 = fast[1][4][3] - fast[1][4][1]
+    assert abs(h1 / h0 - float(__import__("numpy").float32(0.977))) < 1e-12
+    # after release: progressive refinement with quality frames whose budget grows until a frame would exceed 1 s or SS hits 64
+    quality = [c for c in r.calls if c[0] == "quality"]
+    assert quality and not any(c[2] for c in quality)
+    ss = [c[1] for c in quality]
+    assert ss[0] == 1.0 and all(b >= a for a, b in zip(ss[1:], ss[2:])) and max(ss) <= 64.0
+    assert d.state.isWaiting() and n == len(r.calls)
+
+
+def test_automatic_quality_off_keeps_the_budget():
+    clock = Clock()
+    m = cu.RenderingModel(canvasWidth=320, canvasHeight=180)
+    m.resetRenderingValuesToDefault()
+    m.setMaxSuperSampling(7)
+    r = StubRenderer(clock, ms_per_sample=1.0)
+    d = drv.FrameDriver(r, m, clock, automatic_quality=False)
+    d.run_zoom_session((10, 10), False, frames=3)
+    assert all(c[1] == 7.0 for c in r.calls)
+    assert [c[0] for c in r.calls[:3]] == ["fast"] * 3 and not any(c[3] for c in r.calls[:3])   # zooming out
+
+
+def test_png_export_round_trip(tmp_path):
+    import numpy as np
+    io = importlib.import_module("chaos-ultra_b200.imageio")
+    pal = cu.createDefaultColorPalette()
+    frame = pal[(np.arange(48 * 64).reshape(48, 64) * 7) % pal.size].astype(np.uint32)
+    p = tmp_path / "frame.png"
+    io.save_png(p, frame)
+    data = p.read_bytes()
+    assert (io.decode_png_rgba8(data) == frame).all()
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    img = np.asarray(Image.open(p).convert("RGBA")).astype(np.uint32)     # an independent decoder agrees on the channel order
+    back = img[..., 0] | (img[..., 1] << 8) | (img[..., 2] << 16) | (img[..., 3] << 24)
+    assert (back == frame).all()
+    # reference palettes are PNGs read the other way round (ImageHelpers.loadColorPaletteFromFile)
+    io.save_png(tmp_path / "pal.png", pal.reshape(1, -1))
+    assert (cu.loadColorPaletteFromFile(tmp_path / "pal.png") == pal).all()
