@@ -112,10 +112,11 @@ class _Stats(C.Structure):
         ("render_ms", C.c_float),
         ("compose_ms", C.c_float),
         ("reuse_ms", C.c_float),
-        ("reserved", C.c_uint32),
+        ("frame_ms", C.c_float),
         ("pixel_iterations", C.c_uint64),
         ("samples", C.c_uint64),
         ("launches_total", C.c_uint64),
+        ("skipped_iterations", C.c_uint64),
     ]
 
 
@@ -285,6 +286,8 @@ class RenderStats:
     pixel_iterations: int
     samples: int
     launches_total: int
+    skipped_iterations: int = 0   # part of pixel_iterations proven (exact recurrence) instead of executed
+    frame_ms: float = 0.0         # device time of the whole frame (render kernels + compose)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -439,7 +442,7 @@ class CudaFractalRenderer:
         s = _Stats()
         s.struct_size = C.sizeof(_Stats)
         _check(self._lib, self._lib.chaos_get_stats(self._h, C.byref(s)))
-        return RenderStats(s.kernel_launches, s.render_ms, s.compose_ms, s.reuse_ms, s.pixel_iterations, s.samples, s.launches_total)
+        return RenderStats(s.kernel_launches, s.render_ms, s.compose_ms, s.reuse_ms, s.pixel_iterations, s.samples, s.launches_total, s.skipped_iterations, s.frame_ms)
 
     def __enter__(self):
         return self

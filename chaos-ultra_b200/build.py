@@ -62,7 +62,8 @@ def build_module(src: Path, force: bool = False) -> Path:
     deps = [src] + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [Path(__file__)]
     if not force and _newer(out, deps):
         return out
-    cmd = [_nvcc(), "-cubin", *ARCH_FLAGS, *NVCC_FLAGS, "-I", str(CSRC), str(src), "-o", str(out)]
+    extra = os.environ.get("CHAOS_NVCC_EXTRA", "").split()    # experiments only, e.g. -DCHAOS_REFILL_SLOTS=6
+    cmd = [_nvcc(), "-cubin", *ARCH_FLAGS, *NVCC_FLAGS, *extra, "-I", str(CSRC), str(src), "-o", str(out)]
     _run(cmd, log=KERNELS_DIR / (src.stem + ".ptxas.log"))
     return out
 

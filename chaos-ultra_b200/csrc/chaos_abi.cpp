@@ -310,6 +310,7 @@ struct chaos_renderer {
     uint32_t refill_smem = 0;
     CUfunction k_compose = nullptr, k_undersampled = nullptr, k_debug = nullptr;
     int blocks_main_f = 0, blocks_main_d = 0, blocks_adv_f = 0, blocks_adv_d = 0;
+    int blocks_indep_f = 0, blocks_indep_d = 0;   /* the same main kernels launched without slot memory (independent orbits) */
     /* renderer state (CudaFractalRenderer) */
     chaos_state state = CHAOS_STATE_NOT_INITIALIZED;
     uint32_t width = 0, height = 0;
@@ -331,6 +332,7 @@ struct chaos_renderer {
     chaos_stats stats;
     uint32_t engine = 1;           /* 1 = lane-refill scheduler (default), 0 = tile-synchronous */
     uint32_t block_iters = 0;      /* 0 = choose from maxIterations */
+    uint32_t shortcuts = CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE;   /* count-preserving shortcuts of the escape loop */
 };
 
 static chaos_status check_renderer(const chaos_renderer *r)
@@ -471,6 +473,8 @@ static chaos_status load_module(chaos_renderer *r)
     }
     r->blocks_main_f = persistent_blocks(r, r->k_main_f, 256, r->refill_smem);
     r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256, r->refill_smem);
+    r->blocks_indep_f = persistent_blocks(r, r->k_main_f, 256, 0);
+    r->blocks_indep_d = persistent_blocks(r, r->k_main_d, 256, 0);
     r->blocks_main_f_sync = persistent_blocks(r, r->k_main_f_sync, 256);
     r->blocks_main_d_sync = persistent_blocks(r, r->k_main_d_sync, 256);
     r->blocks_reuse_f = persistent_blocks(r, r->k_reuse_f, 256);
@@ -513,6 +517,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (tp) r->two_pass = (uint32_t)atoi(tp) ? 1u : 0u;
     const char *nb = getenv("CHAOS_BLOCK_ITERS");
     if (nb) r->block_iters = ((uint32_t)atoi(nb) + 3u) & ~3u;
+    const char *sc = getenv("CHAOS_SHORTCUTS");   /* 0 = every trip executed and tested, as the reference does */
+    if (sc) r->shortcuts = (uint32_t)atoi(sc) & (CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE);
     chaos_status st = load_module(r);
     if (st != CHAOS_OK) { delete r; return st; }
     CUresult e = D->p_cuStreamCreate(&r->stream, CU_STREAM_NON_BLOCKING);
@@ -764,6 +770,7 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
     /* trips between scheduling points: long enough to amortise a scheduling pass, short enough that a lane whose
      * orbit ended does not idle long; orbits are at most max_iter long */
     a->block_iters = r->block_iters ? r->block_iters : 128u;
+    a->shortcuts = r->shortcuts;
 }
 
 static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg)
@@ -803,9 +810,16 @@ static chaos_status finish_frame(chaos_renderer *r)
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "Error just after launching a kernel:%s", cu_err_name(e));
     D->p_cuEventElapsedTime(&r->stats.render_ms, r->ev[0], r->ev[1]);
     D->p_cuEventElapsedTime(&r->stats.compose_ms, r->ev[2], r->ev[3]);
+    D->p_cuEventElapsedTime(&r->stats.frame_ms, r->ev[0], r->ev[3]);
     r->stats.reuse_ms = 0.f;
     r->stats.pixel_iterations = r->counters_host->pixel_iterations;
     r->stats.samples = r->counters_host->samples;
+    r->stats.skipped_iterations = r->counters_host->skipped_iterations;
+    if (getenv("CHAOS_PROFILE_PRINT")) {
+        const unsigned long long *q = r->counters_host->prof;
+        fprintf(stderr, "chaos profile: untested blocks %llu (busy lanes %.1f), tested blocks %llu (busy lanes %.1f), scheduling passes %llu, lanes waiting for a tested block %llu\n",
+                q[0], q[0] ? (double)q[2] / q[0] : 0.0, q[1], q[1] ? (double)q[3] / q[1] : 0.0, q[4], q[5]);
+    }
     return CHAOS_OK;
 }
 
@@ -849,6 +863,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     if (a.n_tiles) {
         CUfunction k1 = dbl ? r->k_main_d : r->k_main_f;
         const int b1 = dbl ? r->blocks_main_d : r->blocks_main_f;
+        const int bi = dbl ? r->blocks_indep_d : r->blocks_indep_f;
         const uint32_t S0 = (uint32_t)std::min(64.0f, roundf(m->max_super_sampling));
         /* Short orbits (low iteration limit) with several samples: the per-orbit scheduling work of the refill
          * engine costs more than the divergence it removes, so those frames take the tile-synchronous kernel
@@ -865,11 +880,13 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
             if (em == CUDA_SUCCESS) em = D->p_cuMemsetD32Async(r->tile_tmin, 0xffffffffu, a.n_tiles, r->stream);
             if (em != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed: %s", cu_err_name(em));
             a.phase = 1u;
-            st = launch(r, k1, b1, 256, r->refill_smem, &a);
+            st = launch(r, k1, bi, 256, 0, &a);                    /* independent orbits: no slot memory */
             if (st == CHAOS_OK) st = launch(r, r->k_classify, small_grid, 256, 0, &a);
             if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &a);
             a.phase = 2u;
             if (st == CHAOS_OK) st = launch(r, k1, b1, 256, r->refill_smem, &a);
+        } else if (S0 <= 1u) {
+            st = launch(r, k1, bi, 256, 0, &a);
         } else {
             st = launch(r, k1, b1, 256, r->refill_smem, &a);
         }

@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 9u
+#define CHAOS_MODULE_ABI 10u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -29,6 +29,10 @@ struct chaos_pixel_info {
 #define CHAOS_FLAG_IS_ZOOMING (1u << 4)
 #define CHAOS_FLAG_ZOOMING_IN (1u << 5)
 
+/* count-preserving shortcuts of the escape loop (quadratic.cuh items 3 and 4) */
+#define CHAOS_SHORTCUT_DEFER_TEST (1u << 0)  /* test the escape condition once per group of trips, replay on failure */
+#define CHAOS_SHORTCUT_RECURRENCE (1u << 1)  /* an orbit whose state recurs bit for bit is reported as never escaping */
+
 /* device counters, one block per renderer (zeroed by the host before each render call) */
 #define CHAOS_COST_BUCKETS 37
 struct chaos_counters {
@@ -36,8 +40,10 @@ struct chaos_counters {
     unsigned int next_tile_b;           /* second cursor (pass B of a two-pass render) */
     unsigned long long pixel_iterations;
     unsigned long long samples;
+    unsigned long long skipped_iterations; /* part of pixel_iterations that was proven, not executed (exact recurrence) */
     unsigned int bucket_count[CHAOS_COST_BUCKETS + 3];  /* tiles per cost class (chaosClassifyTiles) */
     unsigned int bucket_cursor[CHAOS_COST_BUCKETS + 3]; /* fill position per class (chaosOrderTiles) */
+    unsigned long long prof[8];         /* scheduler statistics of the rounds engine, filled only by -DCHAOS_PROFILE builds */
 };
 
 struct chaos_render_args {
@@ -69,6 +75,7 @@ struct chaos_render_args {
     uint32_t engine;        /* 0 = tile-synchronous, 1 = lane-refill scheduler */
     uint32_t force_exact;   /* 1 = always the reference's 7-operation trip (differential check) */
     uint32_t block_iters;   /* engine 1: trips between two scheduling points (multiple of 4) */
+    uint32_t shortcuts;     /* CHAOS_SHORTCUT_* bits an Orbit may use; 0 with force_exact */
 };
 
 struct chaos_compose_args {

@@ -11,9 +11,18 @@
  *   struct Fractal {
  *     template <class Real> struct Orbit {
  *       static constexpr bool kResumable = true;             // run() may be called repeatedly with growing limits
- *       __device__ void start(Real px, Real py);             // point of the plane to evaluate
- *       __device__ bool run(uint32_t &i, uint32_t limit);    // iterate while i < limit; true = terminated early
+ *       __device__ void start(Real px, Real py, const orbit_ctx &ctx);   // point of the plane to evaluate
+ *       __device__ bool run(uint32_t &i, uint32_t limit, bool tested);
+ *                                     // iterate while i < limit; true = the loop is over: the orbit terminated at
+ *                                     // trip i, or it PROVED that the reference's loop runs to ctx.max_iter and set
+ *                                     // i to that (only if ctx.shortcuts allows it).  `tested` is uniform over the
+ *                                     // warp.  An orbit may use a cheaper instruction stream when tested == false
+ *                                     // that cannot tell the exact trip at which it ends; it then steps back,
+ *                                     // returns false with i < limit, and reports wants_tested() until it is
+ *                                     // called with tested == true (which must always be able to finish the job)
+ *       __device__ bool wants_tested() const;
  *       __device__ void force_exact();                       // drop any exactly-equivalent fast form (may be a no-op)
+ *       __device__ uint32_t skipped() const;                 // trips such a proof replaced (0 if none)
  *       __device__ uint32_t finish(uint32_t i, uint32_t maxIterations) const;
  *                                     // the value `uint escapeTime = computeFractal(..)` would take
  *     };
@@ -34,6 +43,12 @@
 
 #include <stdint.h>
 #include "chaos_device.h"
+
+/* what an orbit may know about the frame */
+struct orbit_ctx {
+    uint32_t max_iter;   /* maxIterations of the frame */
+    uint32_t shortcuts;  /* CHAOS_SHORTCUT_* the host allows */
+};
 
 template <class Real> struct real_ops;
 
@@ -75,9 +90,11 @@ template <class Impl, class Real> struct ClassicOrbit {
     static constexpr bool kResumable = false; /* the engine calls run() once with limit = maxIterations */
     Real px, py;
     float result;
-    __device__ __forceinline__ void start(Real x, Real y) { px = x; py = y; result = 0.f; }
+    __device__ __forceinline__ void start(Real x, Real y, const orbit_ctx &) { px = x; py = y; result = 0.f; }
     __device__ __forceinline__ void force_exact() {}
-    __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit)
+    __device__ __forceinline__ uint32_t skipped() const { return 0u; }
+    __device__ __forceinline__ bool wants_tested() const { return false; }
+    __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit, bool)
     {
         uint32_t trips = 0;
         result = Impl::template compute<Real>(limit, px, py, trips);

@@ -12,16 +12,14 @@ struct Fractal {
         typedef real_ops<Real> op;
         static constexpr bool kResumable = true;
         quadratic_orbit<Real> q;
-        __device__ __forceinline__ void start(Real px, Real py)
+        __device__ __forceinline__ void start(Real px, Real py, const orbit_ctx &ctx)
         {
-            q.init(px, py, op::from_f64(julia_c[0]), op::from_f64(julia_c[1]));   /* julia.cu:7 */
+            q.init(px, py, op::from_f64(julia_c[0]), op::from_f64(julia_c[1]), ctx);   /* julia.cu:7 */
         }
         __device__ __forceinline__ void force_exact() { q.force_exact(); }
-        __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit) { return q.run(i, limit); }
-        static __device__ __forceinline__ void run_pair(Orbit &a, uint32_t &ia, uint32_t la, bool &ea, Orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
-        {
-            quadratic_orbit<Real>::run_pair(a.q, ia, la, ea, b.q, ib, lb, eb);
-        }
+        __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit, bool tested) { return q.run(i, limit, tested); }
+        __device__ __forceinline__ bool wants_tested() const { return q.wants_tested(); }
+        __device__ __forceinline__ uint32_t skipped() const { return q.skipped(); }
         __device__ __forceinline__ uint32_t finish(uint32_t i, uint32_t) const
         {
             return __float2uint_rz(__uint2float_rn(i));

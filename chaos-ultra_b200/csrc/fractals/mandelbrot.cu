@@ -9,13 +9,11 @@ struct Fractal {
     template <class Real> struct Orbit {
         static constexpr bool kResumable = true;
         quadratic_orbit<Real> q;
-        __device__ __forceinline__ void start(Real px, Real py) { q.init((Real)0, (Real)0, px, py); }
+        __device__ __forceinline__ void start(Real px, Real py, const orbit_ctx &ctx) { q.init((Real)0, (Real)0, px, py, ctx); }
         __device__ __forceinline__ void force_exact() { q.force_exact(); }
-        __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit) { return q.run(i, limit); }
-        static __device__ __forceinline__ void run_pair(Orbit &a, uint32_t &ia, uint32_t la, bool &ea, Orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
-        {
-            quadratic_orbit<Real>::run_pair(a.q, ia, la, ea, b.q, ib, lb, eb);
-        }
+        __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit, bool tested) { return q.run(i, limit, tested); }
+        __device__ __forceinline__ bool wants_tested() const { return q.wants_tested(); }
+        __device__ __forceinline__ uint32_t skipped() const { return q.skipped(); }
         /* mandelbrot.cu:22-24: points that never left report 0 */
         __device__ __forceinline__ uint32_t finish(uint32_t i, uint32_t max_iterations) const
         {

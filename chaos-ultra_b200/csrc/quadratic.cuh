@@ -5,12 +5,13 @@
  * sm_100a (and as in the shipped PTX, mandelbrot.ptx:982-996) one trip is
  *     xx = rn(x*x); yy = rn(y*y); leave unless rn(xx+yy) < 4;
  *     xn = rn(cx + rn(xx-yy)); y = fma(rn(x+x), y, cy); x = xn            -- 2 MUL + 4 ADD + 1 FMA
- * and the trip COUNT must come out bit-identical.  Two things are done differently here, neither of
- * which can change a count:
+ * and the trip COUNT must come out bit-identical.  Four things are done differently here, none of which can
+ * change a count; (3) and (4) are switched by chaos_render_args::shortcuts and are off in the differential
+ * check (force_exact), so every one of them is tested against the plain form on full frames.
  *
- * 1. Trips run in unrolled groups (eight in the FP64 loop, four elsewhere) with the "still below 4" predicates
- *    tested once per group.  After the first failing test the remaining steps of the group compute garbage
- *    (inf/NaN, no traps) that is never looked at; the count is the index of the first failure.
+ * 1. Trips run in unrolled groups of eight (four near a limit) with the "still below 4" predicates tested once
+ *    per group.  After the first failing test the remaining steps of the group compute garbage (inf/NaN, no
+ *    traps) that is never looked at; the count is the index of the first failure.
  *
  * 2. FP64 only: the orbit is carried as X = 2x, Y = 2y with CX = 2cx, CY = 2cy:
  *        XX = rn(X*X) = 4xx;  YY = rn(Y*Y) = 4yy;  leave unless rn(XX+YY) < 16;
@@ -20,10 +21,44 @@
  *    happen before the escape test fails (|z| < 2).  Subnormals are excluded by construction: the
  *    scaled form is used only when cx and cy are non-zero with 2^-400 <= |c| <= 2^400 and the start
  *    point's components are zero or in the same range.  Then every later x is 0 or >= ulp(cx)/2 >=
- *    2^-453 (a sum of two doubles one of which is cx), every later y is 0 or >= 2^-106 |cy| >= 2^-506
- *    (an exactly formed product-plus-cy), so xx, yy are 0 or >= 2^-1012: normal.  Differences of
- *    nearby normal numbers (xx-yy) are exact in both forms.  Any other orbit takes the 7-operation
- *    form.  The GPU parity tests compare both engines against the oracle and the reference kernels.
+ *    2^-453 (a sum of two doubles one of which is cx), every later y is 0 or >= 2^-107 |cy| >= 2^-507
+ *    (an exactly formed product-plus-cy), so xx, yy are 0 or >= 2^-1014: normal.  Differences of
+ *    nearby normal numbers (xx-yy) are exact in both forms.  Any other orbit takes the 7-operation form.
+ *
+ * 3. Deferred escape test (kDeferTest).  For |c|^2 < 3.6 the test is monotone along the COMPUTED orbit: if it
+ *    fails at trip k it fails at every later trip.  Proof sketch (u = unit round-off): a failing test means
+ *    rn(rn(x^2)+rn(y^2)) >= 4 or NaN.  NaN/inf are sticky through the update.  Otherwise r^2 = x^2+y^2 >=
+ *    4(1-3u); the computed successor z' differs from z^2+c by at most 3u r^2 + 2u|z'| (three roundings in x',
+ *    one in y'), hence |z'| >= r^2(1-3u) - |c| - tiny >= 4(1-3u)^2 - 1.8974 > 2.10, and the next test sees
+ *    |z'|^2 (1-u)^2 > 4.4 >= 4 -- by induction for all later trips (overflow gives inf/NaN: fails too; an
+ *    underflowing square contributes an absolute error < 2^-148, nothing against a margin of 0.1).
+ *    So a group of kGroup = 32 trips runs WITHOUT the sum and the compare (5 FP64 instructions per trip in the
+ *    scaled form, 6 in the plain one) and only the state after the group is tested: passing proves all skipped
+ *    tests passed; failing restores the state saved before the group, and the group is replayed with a test per
+ *    trip, which finds the exact trip.  The squares computed for the test are the first two operations of the
+ *    next group.
+ *    Two hardware facts shape this (tools/loopbench.cu, measured on B200):
+ *    - the end of a group costs about 35 integer-side instructions (test, compare with the kept state,
+ *      bookkeeping) and the FP64 pipe takes a warp instruction every other issue slot, so with groups of 8 the
+ *      issue port, not the pipe, is the limit: 2.56 T trips/s at 8 warps per scheduler against 3.08 T with groups
+ *      of 32 (2.50 T with a test per trip);
+ *    - a replay executed by one lane while the other 31 wait costs the whole warp its length.  Replaying inside
+ *      run() made c4 (an orbit of some lane ends every ~47 trips) 70 % SLOWER with groups of 32.  Hence run() is
+ *      PHASED: the caller says, uniformly for the warp, whether a call is a tested phase or an untested one.  In an
+ *      untested phase an orbit whose group fails only steps back and raises wants_tested(); the engines answer
+ *      with a short tested phase for the whole warp, in which every lane keeps advancing (with tests), so the
+ *      replay is ordinary productive work of one instruction stream.  New orbits start in a tested phase: most
+ *      orbits of a frame end within a few trips.
+ *
+ * 4. Exact recurrence (kDetectCycle).  The update is a pure function of (x, y) for a fixed c.  If the state after
+ *    a group equals, bit for bit, a state seen earlier on the same orbit, and every test in between passed, the
+ *    computed orbit is periodic and every future test passes: the reference's loop would run to maxIterations.
+ *    The orbit reports i = maxIterations at once -- the very value the reference arrives at, not an
+ *    approximation; an orbit that does not close exactly (chaotic boundary points, |multiplier| close to 1)
+ *    simply runs on.  One earlier state is kept, replaced at trip counts growing by 1.25x (Brent's scheme), and
+ *    compared once per group on the integer pipe.  A cycle of period p is seen when the distance to the kept
+ *    state is a common multiple of p and kGroup.  skipped() tells the engine how many trips were proven
+ *    instead of executed, so executed work is reported separately from the reference-equivalent count.
  *
  * The "below 4" test itself reads the high word of the sum on the integer pipe (see real_ops).
  */
@@ -32,183 +67,167 @@
 
 #include "fractal.cuh"
 
-template <class Real> struct quadratic_orbit {
-    typedef real_ops<Real> op;
-    static constexpr bool kResumable = true;
-    Real x, y, cx, cy;
-
-    __device__ __forceinline__ void init(Real zx, Real zy, Real pcx, Real pcy)
-    {
-        x = zx; y = zy; cx = pcx; cy = pcy;
-    }
-    __device__ __forceinline__ void force_exact() {}
-    __device__ __forceinline__ bool step()
-    {
-        Real xx = op::mul(x, x);
-        Real yy = op::mul(y, y);
-        bool below = op::below4(op::add(xx, yy));
-        Real xn = op::add(cx, op::sub(xx, yy));
-        y = op::fma(op::add(x, x), y, cy);
-        x = xn;
-        return below;
-    }
-    /* Two orbits stepped together (their dependency chains interleave).  An orbit that ended keeps being stepped
-     * -- its state is garbage nobody reads -- so that all lanes of a warp stay in this one loop instead of
-     * diverging into a single-orbit loop; the pair is left only when both ended or a live one reaches its limit
-     * (the caller finishes leftovers with run()). */
-    static __device__ __forceinline__ void run_pair(quadratic_orbit &a, uint32_t &ia, uint32_t la, bool &ea,
-                                                    quadratic_orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
-    {
-        /* groups of four trips both orbits can still take inside their limits; counts are settled once at the end
-         * (or at the group in which an orbit ended), the hot loop only counts groups */
-        const uint32_t n = min((la - ia) >> 2, (lb - ib) >> 2);
-        uint32_t g = 0;
-        while (g < n && (!ea | !eb)) {
-            bool a0 = a.step(), b0 = b.step(), a1 = a.step(), b1 = b.step(), a2 = a.step(), b2 = b.step(), a3 = a.step(), b3 = b.step();
-            const bool fa = !(a0 & a1 & a2 & a3) & !ea, fb = !(b0 & b1 & b2 & b3) & !eb;
-            if (fa | fb) {
-                if (fa) { ia += 4u * g + (a0 ? (a1 ? (a2 ? 3u : 2u) : 1u) : 0u); ea = true; }
-                if (fb) { ib += 4u * g + (b0 ? (b1 ? (b2 ? 3u : 2u) : 1u) : 0u); eb = true; }
-            }
-            ++g;
-        }
-        if (!ea) ia += 4u * g;
-        if (!eb) ib += 4u * g;
-    }
-    /* advance while i < limit; true = the escape test failed at trip i (i is the exact count) */
-    __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit)
-    {
-        while (i + 8u <= limit) {
-            bool p0 = step(), p1 = step(), p2 = step(), p3 = step(), p4 = step(), p5 = step(), p6 = step(), p7 = step();
-            if (!(p0 & p1 & p2 & p3 & p4 & p5 & p6 & p7)) {
-                i += p0 ? (p1 ? (p2 ? (p3 ? (p4 ? (p5 ? (p6 ? 7u : 6u) : 5u) : 4u) : 3u) : 2u) : 1u) : 0u;
-                return true;
-            }
-            i += 8u;
-        }
-        while (i + 4u <= limit) {
-            bool p0 = step(), p1 = step(), p2 = step(), p3 = step();
-            if (!(p0 & p1 & p2 & p3)) {
-                i += p0 ? (p1 ? (p2 ? 3u : 2u) : 1u) : 0u;
-                return true;
-            }
-            i += 4u;
-        }
-        while (i < limit) {
-            if (!step()) return true;
-            ++i;
-        }
-        return false;
-    }
+template <class Real> struct quad_bits;
+template <> struct quad_bits<float> {
+    static constexpr bool kCanScale = false;
+    static __device__ __forceinline__ bool in_safe_range(float) { return false; }
+    static __device__ __forceinline__ bool below16(float s) { return s < 16.0f; }
+    static __device__ __forceinline__ bool same(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
+    static __device__ __forceinline__ float never() { return __uint_as_float(0x7fc00000u); }
 };
-
-/* FP64: adds the exactly-scaled 6-operation form */
-template <> struct quadratic_orbit<double> {
-    static constexpr bool kResumable = true;
-    double x, y, cx, cy;   /* scaled: 2x, 2y, 2cx, 2cy */
-    bool scaled;
-
+template <> struct quad_bits<double> {
+    static constexpr bool kCanScale = true;
     static __device__ __forceinline__ bool in_safe_range(double v)
     {
         uint32_t e = ((uint32_t)__double2hiint(v) >> 20) & 0x7ffu;
         return (e - (1023u - 400u)) <= 800u;
     }
-    static __device__ __forceinline__ bool zero_or_safe(double v) { return v == 0.0 || in_safe_range(v); }
-
-    __device__ __forceinline__ void init(double zx, double zy, double pcx, double pcy)
+    static __device__ __forceinline__ bool below16(double s) { return (uint32_t)__double2hiint(s) < 0x40300000u; }
+    static __device__ __forceinline__ bool same(double a, double b)
     {
-        scaled = in_safe_range(pcx) && in_safe_range(pcy) && zero_or_safe(zx) && zero_or_safe(zy);
-        const double k = scaled ? 2.0 : 1.0;   /* exact */
-        x = __dmul_rn(zx, k); y = __dmul_rn(zy, k); cx = __dmul_rn(pcx, k); cy = __dmul_rn(pcy, k);
+        return ((__double2hiint(a) ^ __double2hiint(b)) | (__double2loint(a) ^ __double2loint(b))) == 0;
     }
-    /* back to the reference's 7-operation form (halving is exact); the tile-synchronous engine uses this so
-     * that it stays an independent implementation to test the scaled form against */
+    static __device__ __forceinline__ double never() { return __hiloint2double(0x7ff80000, 0); }
+};
+
+template <class Real> struct quadratic_orbit {
+    typedef real_ops<Real> op;
+    typedef quad_bits<Real> qb;
+    static constexpr bool kResumable = true;
+    static constexpr uint32_t kScaled = 1u, kDeferTest = 2u, kDetectCycle = 4u, kPeriodic = 8u, kReplay = 16u;
+    static constexpr uint32_t kGroup = 32u;        /* untested trips per group (power of two) */
+
+    Real x, y, cx, cy;      /* kScaled: 2x, 2y, 2cx, 2cy */
+    Real sx, sy;            /* the earlier state the orbit is compared with (kDetectCycle) */
+    uint32_t next_save;     /* trip count at which (sx, sy) is replaced next; after kPeriodic: the trip of the proof */
+    uint32_t mode;
+    uint32_t max_iter;
+
+    static __device__ __forceinline__ bool zero_or_safe(Real v) { return v == (Real)0 || qb::in_safe_range(v); }
+
+    __device__ __forceinline__ void init(Real zx, Real zy, Real pcx, Real pcy, const orbit_ctx &ctx)
+    {
+        mode = 0u;
+        max_iter = ctx.max_iter;
+        if (qb::kCanScale && qb::in_safe_range(pcx) && qb::in_safe_range(pcy) && zero_or_safe(zx) && zero_or_safe(zy)) mode |= kScaled;
+        /* |c|^2 < 3.6 (any rounding of this sum is fine, the proof has 5 % to spare) */
+        if ((ctx.shortcuts & CHAOS_SHORTCUT_DEFER_TEST) && op::fma(pcx, pcx, op::mul(pcy, pcy)) < (Real)3.6) {
+            mode |= kDeferTest;
+            if (ctx.shortcuts & CHAOS_SHORTCUT_RECURRENCE) mode |= kDetectCycle;
+        }
+        const Real k = (mode & kScaled) ? (Real)2 : (Real)1;   /* exact */
+        x = op::mul(zx, k); y = op::mul(zy, k); cx = op::mul(pcx, k); cy = op::mul(pcy, k);
+        sx = sy = qb::never();
+        next_save = 0u;
+    }
+    /* back to the reference's 7-operation trip with a test per trip (halving is exact); the differential check
+     * (engine 0 with force_exact) runs this so that it stays an independent implementation */
     __device__ __forceinline__ void force_exact()
     {
-        if (scaled) {
-            x = __dmul_rn(x, 0.5); y = __dmul_rn(y, 0.5); cx = __dmul_rn(cx, 0.5); cy = __dmul_rn(cy, 0.5);
-            scaled = false;
+        if (mode & kScaled) {
+            x = op::mul(x, (Real)0.5); y = op::mul(y, (Real)0.5); cx = op::mul(cx, (Real)0.5); cy = op::mul(cy, (Real)0.5);
         }
+        mode = 0u;
     }
-    __device__ __forceinline__ bool step_exact()
+    /* trips proven instead of executed (exact recurrence) */
+    __device__ __forceinline__ uint32_t skipped() const { return (mode & kPeriodic) ? max_iter - next_save : 0u; }
+
+    template <bool kS> __device__ __forceinline__ bool below(Real s) const { return kS ? qb::below16(s) : op::below4(s); }
+    /* one trip with its test */
+    template <bool kS> __device__ __forceinline__ bool step()
     {
-        double xx = __dmul_rn(x, x);
-        double yy = __dmul_rn(y, y);
-        bool below = (uint32_t)__double2hiint(__dadd_rn(xx, yy)) < 0x40100000u;   /* < 4.0 */
-        double xn = __dadd_rn(cx, __dsub_rn(xx, yy));
-        y = __fma_rn(__dadd_rn(x, x), y, cy);
+        Real xx = op::mul(x, x);
+        Real yy = op::mul(y, y);
+        bool ok = below<kS>(op::add(xx, yy));
+        Real xn = kS ? op::fma(op::sub(xx, yy), (Real)0.5, cx) : op::add(cx, op::sub(xx, yy));
+        y = kS ? op::fma(x, y, cy) : op::fma(op::add(x, x), y, cy);
         x = xn;
-        return below;
+        return ok;
     }
-    __device__ __forceinline__ bool step_scaled()
+    /* one trip without its test; xx, yy are the squares of the current state on entry and on exit */
+    template <bool kS> __device__ __forceinline__ void advance(Real &xx, Real &yy)
     {
-        double xx = __dmul_rn(x, x);
-        double yy = __dmul_rn(y, y);
-        bool below = (uint32_t)__double2hiint(__dadd_rn(xx, yy)) < 0x40300000u;   /* < 16.0 */
-        double xn = __fma_rn(__dsub_rn(xx, yy), 0.5, cx);
-        y = __fma_rn(x, y, cy);
+        Real xn = kS ? op::fma(op::sub(xx, yy), (Real)0.5, cx) : op::add(cx, op::sub(xx, yy));
+        y = kS ? op::fma(x, y, cy) : op::fma(op::add(x, x), y, cy);
         x = xn;
-        return below;
+        xx = op::mul(x, x);
+        yy = op::mul(y, y);
     }
-    template <bool kScaled> __device__ __forceinline__ bool step() { return kScaled ? step_scaled() : step_exact(); }
-    template <bool kScaled> __device__ __forceinline__ bool run_as(uint32_t &i, uint32_t limit)
+
+    /* trips with a test each, while i < stop; true = a test failed at trip i */
+    template <bool kS> __device__ __forceinline__ bool run_tested(uint32_t &i, uint32_t stop)
     {
-        while (i + 8u <= limit) {      /* groups of eight trips: one branch per 48 FP64 instructions (16 measured no better) */
-            bool p0 = step<kScaled>(), p1 = step<kScaled>(), p2 = step<kScaled>(), p3 = step<kScaled>();
-            bool p4 = step<kScaled>(), p5 = step<kScaled>(), p6 = step<kScaled>(), p7 = step<kScaled>();
+        while (i + 8u <= stop) {      /* one branch per group of eight tested trips (16 measured no better) */
+            bool p0 = step<kS>(), p1 = step<kS>(), p2 = step<kS>(), p3 = step<kS>();
+            bool p4 = step<kS>(), p5 = step<kS>(), p6 = step<kS>(), p7 = step<kS>();
             if (!(p0 & p1 & p2 & p3 & p4 & p5 & p6 & p7)) {
                 i += p0 ? (p1 ? (p2 ? (p3 ? (p4 ? (p5 ? (p6 ? 7u : 6u) : 5u) : 4u) : 3u) : 2u) : 1u) : 0u;
                 return true;
             }
             i += 8u;
         }
-        while (i + 4u <= limit) {
-            bool p0 = step<kScaled>(), p1 = step<kScaled>(), p2 = step<kScaled>(), p3 = step<kScaled>();
+        while (i + 4u <= stop) {
+            bool p0 = step<kS>(), p1 = step<kS>(), p2 = step<kS>(), p3 = step<kS>();
             if (!(p0 & p1 & p2 & p3)) {
                 i += p0 ? (p1 ? (p2 ? 3u : 2u) : 1u) : 0u;
                 return true;
             }
             i += 4u;
         }
-        while (i < limit) {
-            if (!step<kScaled>()) return true;
+        while (i < stop) {
+            if (!step<kS>()) return true;
             ++i;
         }
         return false;
     }
-    __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit)
+    template <bool kS> __device__ __forceinline__ bool run_as(uint32_t &i, uint32_t limit, bool tested)
     {
-        return scaled ? run_as<true>(i, limit) : run_as<false>(i, limit);
-    }
-    template <bool kScaled>
-    static __device__ __forceinline__ void run_pair_as(quadratic_orbit &a, uint32_t &ia, uint32_t la, bool &ea,
-                                                       quadratic_orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
-    {
-        /* groups of four trips both orbits can still take inside their limits; counts are settled once at the end
-         * (or at the group in which an orbit ended), the hot loop only counts groups */
-        const uint32_t n = min((la - ia) >> 2, (lb - ib) >> 2);
-        uint32_t g = 0;
-        while (g < n && (!ea | !eb)) {
-            bool a0 = a.step<kScaled>(), b0 = b.step<kScaled>(), a1 = a.step<kScaled>(), b1 = b.step<kScaled>();
-            bool a2 = a.step<kScaled>(), b2 = b.step<kScaled>(), a3 = a.step<kScaled>(), b3 = b.step<kScaled>();
-            const bool fa = !(a0 & a1 & a2 & a3) & !ea, fb = !(b0 & b1 & b2 & b3) & !eb;
-            if (fa | fb) {
-                if (fa) { ia += 4u * g + (a0 ? (a1 ? (a2 ? 3u : 2u) : 1u) : 0u); ea = true; }
-                if (fb) { ib += 4u * g + (b0 ? (b1 ? (b2 ? 3u : 2u) : 1u) : 0u); eb = true; }
-            }
-            ++g;
+        if (tested || !(mode & kDeferTest)) {
+            mode &= ~kReplay;
+            return run_tested<kS>(i, limit);
         }
-        if (!ea) ia += 4u * g;
-        if (!eb) ib += 4u * g;
+        if (mode & kReplay) return false;           /* waits for a tested phase */
+        Real xx = op::mul(x, x), yy = op::mul(y, y);
+        while (i + kGroup <= limit) {
+            const Real bx = x, by = y;
+#pragma unroll 1
+            for (uint32_t r = 0; r < kGroup / 8u; ++r) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) advance<kS>(xx, yy);
+            }
+            if (!below<kS>(op::add(xx, yy))) {      /* a test among trips i .. i+kGroup fails: back to the state before the group */
+                x = bx; y = by;
+                mode |= kReplay;
+                return false;
+            }
+            i += kGroup;
+            if (mode & kDetectCycle) {
+                if (qb::same(x, sx) && qb::same(y, sy)) {   /* exactly periodic: the loop runs to maxIterations */
+                    mode |= kPeriodic;
+                    next_save = i;
+                    i = max_iter;
+                    return true;
+                }
+                if (i >= next_save) {
+                    sx = x; sy = y;
+                    next_save = i + max(kGroup, (i >> 2) & ~(kGroup - 1u));
+                }
+            }
+        }
+        if (i < limit) mode |= kReplay;             /* a tail shorter than a group needs its tests */
+        return false;
     }
-    /* two orbits stepped together; a pair in different forms is brought to the 7-operation form first (exact) */
-    static __device__ __forceinline__ void run_pair(quadratic_orbit &a, uint32_t &ia, uint32_t la, bool &ea,
-                                                    quadratic_orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
+    /* One phase of the loop, while i < limit.  `tested` must be uniform over the warp: all lanes then execute ONE
+     * instruction stream.  tested = true: every trip with its test (the first trips of an orbit, the replay of a
+     * failed group, tails).  tested = false: untested groups; an orbit whose group fails goes back to the state
+     * before that group, asks for a tested phase (wants_tested()) and does nothing until it gets one.
+     * true = the loop is over: the test failed at trip i, or i = maxIterations was proven. */
+    __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit, bool tested)
     {
-        if (a.scaled != b.scaled) { a.force_exact(); b.force_exact(); }
-        if (a.scaled) run_pair_as<true>(a, ia, la, ea, b, ib, lb, eb);
-        else run_pair_as<false>(a, ia, la, ea, b, ib, lb, eb);
+        if (qb::kCanScale && (mode & kScaled)) return run_as<true>(i, limit, tested);
+        return run_as<false>(i, limit, tested);
     }
+    __device__ __forceinline__ bool wants_tested() const { return (mode & kReplay) != 0u; }
 };
 
 #endif

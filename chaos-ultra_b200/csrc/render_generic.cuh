@@ -170,6 +170,34 @@ static __device__ __forceinline__ void store_record(chaos_pixel_info *p, float v
     *reinterpret_cast<float4 *>(p) = v;
 }
 
+/* exact work counters: warp-reduce, then one atomic per warp and counter */
+static __device__ __forceinline__ void flush_counters(const chaos_render_args &a, unsigned long long iters, unsigned long long nsamples,
+                                                      unsigned long long skipped)
+{
+    for (int o = 16; o; o >>= 1) {
+        iters += __shfl_xor_sync(CHAOS_FULL_MASK, iters, o);
+        nsamples += __shfl_xor_sync(CHAOS_FULL_MASK, nsamples, o);
+        skipped += __shfl_xor_sync(CHAOS_FULL_MASK, skipped, o);
+    }
+    if ((threadIdx.x & 31u) == 0 && nsamples) {
+        atomicAdd(&a.counters->pixel_iterations, iters);
+        atomicAdd(&a.counters->samples, nsamples);
+        if (skipped) atomicAdd(&a.counters->skipped_iterations, skipped);
+    }
+}
+
+/* A whole orbit in warp-uniform phases (see Orbit::run in fractal.cuh): the first trips tested (most orbits end
+ * there), then untested until every lane is through or stuck on a failed group, then one tested phase in which
+ * all stuck lanes replay their group together.  Lanes that are done sit the phases out. */
+#define CHAOS_SYNC_TESTED_HEAD 64u
+template <class Orbit>
+static __device__ __forceinline__ void run_whole(Orbit &o, uint32_t &it, uint32_t max_iter)
+{
+    bool ended = o.run(it, Orbit::kResumable ? min(max_iter, CHAOS_SYNC_TESTED_HEAD) : max_iter, true);
+    if (!ended && it < max_iter) ended = o.run(it, max_iter, false);
+    if (!ended && it < max_iter) o.run(it, max_iter, true);
+}
+
 /* ==========================================================================================
  * Engine 0: tile-synchronous.  One warp = one vote tile, lane = pixel (lane = 8*row + col),
  * all lanes step through the sample rounds together.  Simple; kept as the differential
@@ -178,9 +206,11 @@ static __device__ __forceinline__ void store_record(chaos_pixel_info *p, float v
 template <class Real, class FractalT>
 static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_args &a, const frame_map<Real> &fm,
                                                             bool participate, uint32_t px, uint32_t py, float &scf,
-                                                            unsigned long long &iters, unsigned long long &nsamples)
+                                                            unsigned long long &iters, unsigned long long &nsamples,
+                                                            unsigned long long &skipped)
 {
     typedef typename FractalT::template Orbit<Real> Orbit;
+    const orbit_ctx ctx = {a.max_iter, a.force_exact ? 0u : a.shortcuts};
     if (scf < 1.f) { scf = 0.f; return 0u; }                           /* :87-90 (tile-uniform) */
     uint32_t S = min(64u, __float2uint_rz(roundf(scf)));
     const float spr = sqrtf(__fadd_rn(scf, -2.0f));
@@ -194,12 +224,13 @@ static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_a
             sample_delta<Real>(i, spr, dx, dy);
             fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx, dy, cx, cy);
             Orbit o;
-            o.start(cx, cy);
+            o.start(cx, cy, ctx);
             if (a.force_exact) o.force_exact();             /* engine 0 as differential check: the reference's own operation sequence */
             uint32_t it = 0;
-            o.run(it, a.max_iter);
+            run_whole(o, it, a.max_iter);
             uint32_t et = o.finish(it, a.max_iter);
             iters += it;
+            skipped += o.skipped();
             nsamples += 1;
             sum += et;
             if (i < CHAOS_ADAPTIVE_THRESHOLD) {
@@ -229,7 +260,7 @@ static __device__ void render_main_sync(const chaos_render_args &a)
     frame_map<Real> fm;
     fm.init(a);
     const uint32_t lane = threadIdx.x & 31u;
-    unsigned long long iters = 0, nsamples = 0;
+    unsigned long long iters = 0, nsamples = 0, skipped = 0;
     for (;;) {
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(&a.counters->next_tile, 1u);
@@ -240,18 +271,10 @@ static __device__ void render_main_sync(const chaos_render_args &a)
         uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
         bool inb = px < a.width && py < a.height;
         float scf = a.max_ss;
-        uint32_t v = sample_tile_sync<Real, FractalT>(a, fm, inb, px, py, scf, iters, nsamples);
+        uint32_t v = sample_tile_sync<Real, FractalT>(a, fm, inb, px, py, scf, iters, nsamples, skipped);
         if (inb) store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(v), scf, 0u, 0.f);
     }
-    /* exact work counters: warp-reduce then one atomic per warp */
-    for (int o = 16; o; o >>= 1) {
-        iters += __shfl_xor_sync(CHAOS_FULL_MASK, iters, o);
-        nsamples += __shfl_xor_sync(CHAOS_FULL_MASK, nsamples, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&a.counters->pixel_iterations, iters);
-        atomicAdd(&a.counters->samples, nsamples);
-    }
+    flush_counters(a, iters, nsamples, skipped);     /* exact work counters: warp-reduce then one atomic per warp */
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -344,7 +367,8 @@ static __device__ __forceinline__ void gather_bilinear(const chaos_pixel_info *i
  */
 template <class Real, class FractalT, int kMode>
 static __device__ __forceinline__ void advanced_tile(const chaos_render_args &a, const frame_map<Real> &fm, uint32_t t, uint32_t lane,
-                                                     bool use_fov, unsigned long long &iters, unsigned long long &nsamples)
+                                                     bool use_fov, unsigned long long &iters, unsigned long long &nsamples,
+                                                     unsigned long long &skipped)
 {
     const uint32_t fl = a.flags;
     uint32_t x0, y0;
@@ -381,7 +405,7 @@ static __device__ __forceinline__ void advanced_tile(const chaos_render_args &a,
     uint32_t reused_flag = reusing ? 1u : 0u;
     if (__any_sync(CHAOS_FULL_MASK, resample)) {
         float scf = advised;
-        uint32_t s = sample_tile_sync<Real, FractalT>(a, fm, resample, px, py, scf, iters, nsamples);
+        uint32_t s = sample_tile_sync<Real, FractalT>(a, fm, resample, px, py, scf, iters, nsamples, skipped);
         if (resample) {
             float wold = __fmul_rn(rw, 0.75f);
             weight = __fadd_rn(wold, scf);
@@ -391,7 +415,7 @@ static __device__ __forceinline__ void advanced_tile(const chaos_render_args &a,
     }
     if (__any_sync(CHAOS_FULL_MASK, fresh)) {
         float scf = advised < 1.f ? 1.f : advised;
-        uint32_t s = sample_tile_sync<Real, FractalT>(a, fm, fresh, px, py, scf, iters, nsamples);
+        uint32_t s = sample_tile_sync<Real, FractalT>(a, fm, fresh, px, py, scf, iters, nsamples, skipped);
         if (fresh) { value = __uint2float_rn(s); weight = scf; }
     }
     if (inb) store_record(record_at(a.out, a.out_pitch, px, py), value, weight, reused_flag, wnew);
@@ -547,22 +571,15 @@ static __device__ void advanced_sample_pass(const chaos_render_args &a)
     const uint32_t lane = threadIdx.x & 31u;
     const bool use_fov = (a.flags & CHAOS_FLAG_FOVEATION) && (a.flags & CHAOS_FLAG_IS_ZOOMING) && (a.flags & CHAOS_FLAG_ZOOMING_IN);
     const uint32_t n_work = a.counters->bucket_count[0];       /* written by pass R, complete before this launch starts */
-    unsigned long long iters = 0, nsamples = 0;
+    unsigned long long iters = 0, nsamples = 0, skipped = 0;
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(&a.counters->next_tile_b, 1u);
         w = __shfl_sync(CHAOS_FULL_MASK, w, 0);
         if (w >= n_work) break;
-        advanced_tile<Real, FractalT, 2>(a, fm, a.tile_order[w], lane, use_fov, iters, nsamples);
+        advanced_tile<Real, FractalT, 2>(a, fm, a.tile_order[w], lane, use_fov, iters, nsamples, skipped);
     }
-    for (int o = 16; o; o >>= 1) {
-        iters += __shfl_xor_sync(CHAOS_FULL_MASK, iters, o);
-        nsamples += __shfl_xor_sync(CHAOS_FULL_MASK, nsamples, o);
-    }
-    if (lane == 0 && nsamples) {
-        atomicAdd(&a.counters->pixel_iterations, iters);
-        atomicAdd(&a.counters->samples, nsamples);
-    }
+    flush_counters(a, iters, nsamples, skipped);
 }
 
 /* ==========================================================================================

@@ -36,7 +36,9 @@
 #ifndef CHAOS_RENDER_REFILL_CUH
 #define CHAOS_RENDER_REFILL_CUH
 
+#ifndef CHAOS_REFILL_SLOTS
 #define CHAOS_REFILL_SLOTS 4
+#endif
 #define CHAOS_REFILL_WARPS (CHAOS_RENDER_THREADS / 32)
 
 struct refill_slot_hdr {
@@ -64,67 +66,26 @@ static __device__ __forceinline__ uint32_t lanemask_lt()
     return m;
 }
 
-static __device__ __forceinline__ void flush_counters(const chaos_render_args &a, unsigned long long iters, unsigned long long nsamples)
-{
-    for (int o = 16; o; o >>= 1) {
-        iters += __shfl_xor_sync(CHAOS_FULL_MASK, iters, o);
-        nsamples += __shfl_xor_sync(CHAOS_FULL_MASK, nsamples, o);
-    }
-    if ((threadIdx.x & 31u) == 0 && nsamples) {
-        atomicAdd(&a.counters->pixel_iterations, iters);
-        atomicAdd(&a.counters->samples, nsamples);
-    }
-}
-
-/* ---- orbits per lane ------------------------------------------------------------------------------- */
-/* One trip of z^2+c is a chain of three dependent FP64 operations, so carrying CHAOS_ILP = 2 independent orbits
- * per lane (stepped together by Orbit::run_pair, chains interleaved) was tried as a way to need fewer warps.
- * Measured on B200 (round 1): no gain where every lane holds two orbits (c4: 42.9 ms vs 42.2 ms -- with 8 warps
- * per scheduler the FP64 pipe is already the limit, not the dependency latency) and a loss with sample rounds
- * (c2: 22.2 ms vs 18.0 ms -- there are not enough pending orbits per warp to fill 64 contexts, and half-filled
- * pairs still issue both chains).  The engine stays generic over CHAOS_ILP; the default is 1.
- * A module's Orbit may provide
- *     static void run_pair(Orbit &a, uint32_t &ia, uint32_t la, bool &ea, Orbit &b, uint32_t &ib, uint32_t lb, bool &eb)
- * which advances both while both are below their limits; the engine finishes whatever is left with run(). */
-#ifndef CHAOS_ILP
-#define CHAOS_ILP 1
-#endif
-
-template <class O, class = void> struct has_run_pair { static constexpr bool value = false; };
-template <class O>
-struct has_run_pair<O, decltype(O::run_pair(*(O *)0, *(uint32_t *)0, 0u, *(bool *)0, *(O *)0, *(uint32_t *)0, 0u, *(bool *)0))> {
-    static constexpr bool value = true;
-};
-
-template <class O, bool kHas> struct run_pair_if {
-    static __device__ __forceinline__ void go(O &, uint32_t &, uint32_t, bool &, O &, uint32_t &, uint32_t, bool &) {}
-};
-template <class O> struct run_pair_if<O, true> {
-    static __device__ __forceinline__ void go(O &a, uint32_t &ia, uint32_t la, bool &ea, O &b, uint32_t &ib, uint32_t lb, bool &eb)
-    {
-        O::run_pair(a, ia, la, ea, b, ib, lb, eb);
-    }
-};
+/* ---- phases ------------------------------------------------------------------------------------------
+ * All lanes of a warp run the escape loop together for a BLOCK of trips, then meet at a scheduling point.
+ * A block is either TESTED (every trip carries its escape test; short: CHAOS_TESTED_BLOCK trips) or UNTESTED
+ * (args.block_iters trips of the orbits' cheaper instruction stream, see Orbit::run in fractal.cuh).  The kind is
+ * uniform over the warp, so the warp executes one instruction stream either way:
+ *   - a block is tested if any lane holds a new orbit (most orbits end within a few trips; they then give the
+ *     lane back after a short block instead of a long one) or any lane asks for tests (its untested group failed:
+ *     the tested block finds the exact trip while every other lane keeps advancing);
+ *   - otherwise it is untested.
+ * (Two orbits per lane with interleaved chains was measured in round 1 and removed: no gain once the loop is
+ * pipe-bound, a loss with sample rounds.) */
+#define CHAOS_TESTED_BLOCK 40u   /* >= quadratic_orbit::kGroup + 1: the replay of a failed group ends inside one tested block */
 
 template <class Orbit>
-static __device__ __forceinline__ void run_lane_orbits(Orbit (&o)[CHAOS_ILP], uint32_t (&it)[CHAOS_ILP], const bool (&busy)[CHAOS_ILP],
-                                                       bool (&done)[CHAOS_ILP], uint32_t nb, uint32_t max_iter)
+static __device__ __forceinline__ bool run_block(Orbit &o, uint32_t &it, bool busy, bool tested, uint32_t nb, uint32_t max_iter)
 {
-    uint32_t lim[CHAOS_ILP];
-    bool ended[CHAOS_ILP];
-#pragma unroll
-    for (int j = 0; j < CHAOS_ILP; ++j) {
-        lim[j] = Orbit::kResumable ? min(it[j] + nb, max_iter) : max_iter;
-        ended[j] = false;
-    }
-    if (has_run_pair<Orbit>::value && CHAOS_ILP == 2) {
-        if (busy[0] && busy[1]) run_pair_if<Orbit, has_run_pair<Orbit>::value>::go(o[0], it[0], lim[0], ended[0], o[1], it[1], lim[1], ended[1]);
-    }
-#pragma unroll
-    for (int j = 0; j < CHAOS_ILP; ++j) {
-        if (busy[j] && !ended[j] && it[j] < lim[j]) ended[j] = o[j].run(it[j], lim[j]);
-        done[j] = busy[j] && (ended[j] || it[j] >= max_iter);
-    }
+    if (!busy) return false;
+    const uint32_t lim = Orbit::kResumable ? min(it + (tested ? CHAOS_TESTED_BLOCK : nb), max_iter) : max_iter;
+    const bool ended = o.run(it, lim, tested);
+    return ended || it >= max_iter;
 }
 
 /* ---- one sample per pixel: independent orbits ------------------------------------------------ */
@@ -132,86 +93,75 @@ template <class Real, class FractalT, bool kProbe>
 static __device__ void render_main_independent(const chaos_render_args &a)
 {
     typedef typename FractalT::template Orbit<Real> Orbit;
-    constexpr int U = CHAOS_ILP;
     frame_map<Real> fm;
     fm.init(a);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t max_iter = a.max_iter;
     const uint32_t nb = a.block_iters;
+    const orbit_ctx ctx = {a.max_iter, a.shortcuts};
     Real dx0, dy0;
     sample_delta<Real>(0u, 0.f, dx0, dy0);                  /* sample 0 sits at offset 0/3 */
 
-    Orbit o[U];
-    uint32_t it[U], px[U], py[U], tile[U];
-    bool busy[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) { it[j] = 0; px[j] = py[j] = tile[j] = 0; busy[j] = false; }
-    bool first = true, queue_empty = false;
+    Orbit o;
+    uint32_t it = 0, px = 0, py = 0, tile = 0;
+    bool busy = false;
+    bool first = true, queue_empty = false, tested = true;
     uint32_t pend = 0, x0 = 0, y0 = 0, cur_tile = 0;         /* warp-uniform: the tile being handed out */
-    unsigned long long iters = 0, nsamples = 0;
+    unsigned long long iters = 0, nsamples = 0, skipped = 0;
 
     for (;;) {
-        bool done[U];
-        run_lane_orbits<Orbit>(o, it, busy, done, nb, max_iter);
-        bool any_done = false;
-#pragma unroll
-        for (int j = 0; j < U; ++j) any_done |= done[j];
-        if (!__any_sync(CHAOS_FULL_MASK, any_done) && !first) continue;
+        const bool done = run_block(o, it, busy, tested, nb, max_iter);
+        tested = __any_sync(CHAOS_FULL_MASK, busy && !done && o.wants_tested());
+        if (!__any_sync(CHAOS_FULL_MASK, done) && !first) continue;
         first = false;
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            if (done[j]) {
-                uint32_t et = o[j].finish(it[j], max_iter);
-                iters += it[j];
-                nsamples += 1;
-                if (kProbe) { /* pass A: park the escape time in the record for pass B, fold the trip count into the tile's statistics */
-                    store_record(record_at(a.out, a.out_pitch, px[j], py[j]), __uint_as_float(et), __uint_as_float(it[j]), 0u, 0.f);
-                    atomicMax(&a.tile_tmax[tile[j]], it[j]);
-                    atomicMin(&a.tile_tmin[tile[j]], it[j]);
-                }
-                else          /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
-                    store_record(record_at(a.out, a.out_pitch, px[j], py[j]), __uint2float_rn(et), 1.0f, 0u, 0.f);
-                busy[j] = false;
+        if (done) {
+            uint32_t et = o.finish(it, max_iter);
+            iters += it;
+            skipped += o.skipped();
+            nsamples += 1;
+            if (kProbe) { /* pass A: park the escape time in the record for pass B, fold the trip count into the tile's statistics */
+                store_record(record_at(a.out, a.out_pitch, px, py), __uint_as_float(et), __uint_as_float(it), 0u, 0.f);
+                atomicMax(&a.tile_tmax[tile], it);
+                atomicMin(&a.tile_tmin[tile], it);
             }
+            else          /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
+                store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
+            busy = false;
         }
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            for (;;) {
-                uint32_t idle = __ballot_sync(CHAOS_FULL_MASK, !busy[j]);
-                if (!idle) break;
-                if (!pend) {
-                    if (queue_empty) break;
-                    uint32_t t = 0;
-                    if (lane == 0) t = atomicAdd(&a.counters->next_tile, 1u);
-                    t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
-                    if (t >= a.n_tiles) { queue_empty = true; break; }
-                    cur_tile = t;
-                    tile_origin(a, t, x0, y0);
-                    pend = __ballot_sync(CHAOS_FULL_MASK, (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height);
-                }
-                uint32_t rank = __popc(idle & lanemask_lt());
-                bool take = !busy[j] && rank < (uint32_t)__popc(pend);
-                uint32_t mypix = 0;
-                if (take) {
-                    mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
-                    px[j] = x0 + (mypix & 7u);
-                    py[j] = y0 + (mypix >> 3);
-                    tile[j] = cur_tile;
-                    Real cx, cy;
-                    fm.template plane_point<fused_plane_y<FractalT>::value>(px[j], py[j], dx0, dy0, cx, cy);
-                    o[j].start(cx, cy);
-                    it[j] = 0;
-                    busy[j] = true;
-                }
-                pend &= ~__reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
+        for (;;) {
+            uint32_t idle = __ballot_sync(CHAOS_FULL_MASK, !busy);
+            if (!idle) break;
+            if (!pend) {
+                if (queue_empty) break;
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(&a.counters->next_tile, 1u);
+                t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
+                if (t >= a.n_tiles) { queue_empty = true; break; }
+                cur_tile = t;
+                tile_origin(a, t, x0, y0);
+                pend = __ballot_sync(CHAOS_FULL_MASK, (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height);
             }
+            uint32_t rank = __popc(idle & lanemask_lt());
+            bool take = !busy && rank < (uint32_t)__popc(pend);
+            uint32_t mypix = 0;
+            if (take) {
+                mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
+                px = x0 + (mypix & 7u);
+                py = y0 + (mypix >> 3);
+                tile = cur_tile;
+                Real cx, cy;
+                fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx0, dy0, cx, cy);
+                o.start(cx, cy, ctx);
+                it = 0;
+                busy = true;
+                tested = true;                               /* new orbits start with a tested block */
+            }
+            pend &= ~__reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
         }
-        bool any_busy = false;
-#pragma unroll
-        for (int j = 0; j < U; ++j) any_busy |= busy[j];
-        if (!__any_sync(CHAOS_FULL_MASK, any_busy)) break;
+        tested = __any_sync(CHAOS_FULL_MASK, tested);
+        if (!__any_sync(CHAOS_FULL_MASK, busy)) break;
     }
-    flush_counters(a, iters, nsamples);
+    flush_counters(a, iters, nsamples, skipped);
 }
 
 /* ---- general case: sample rounds with tile-wide votes ----------------------------------------- */
@@ -220,12 +170,12 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
 {
     typedef typename FractalT::template Orbit<Real> Orbit;
     constexpr int K = CHAOS_REFILL_SLOTS;
-    constexpr int U = CHAOS_ILP;
     frame_map<Real> fm;
     fm.init(a);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t max_iter = a.max_iter;
     const uint32_t nb = a.block_iters;
+    const orbit_ctx ctx = {a.max_iter, a.shortcuts};
     const bool adaptive = (a.flags & CHAOS_FLAG_ADAPTIVE_SS) != 0u;
     const float scf = a.max_ss;                               /* host guarantees >= 1 (:174) */
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(scf)));
@@ -237,37 +187,41 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
     }
     __syncwarp();
 
-    Orbit o[U];
-    uint32_t it[U], slot[U], pix[U];
-    bool busy[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) { it[j] = 0; slot[j] = 0; pix[j] = 0; busy[j] = false; }
-    bool first = true, queue_empty = false;
-    unsigned long long iters = 0, nsamples = 0;
+    Orbit o;
+    uint32_t it = 0, slot = 0, pix = 0;
+    bool busy = false;
+    bool first = true, queue_empty = false, tested = true;
+    unsigned long long iters = 0, nsamples = 0, skipped = 0;
 
+#ifdef CHAOS_PROFILE
+    unsigned long long prof_blk[2] = {0, 0}, prof_busy[2] = {0, 0}, prof_sched = 0, prof_want = 0;
+#endif
     for (;;) {
-        /* (1) iterate: up to block_iters trips for every orbit this lane holds */
-        bool done[U];
-        run_lane_orbits<Orbit>(o, it, busy, done, nb, max_iter);
-        bool any_done = false;
-#pragma unroll
-        for (int j = 0; j < U; ++j) any_done |= done[j];
-        if (!__any_sync(CHAOS_FULL_MASK, any_done) && !first) continue;
+        /* (1) iterate: one block of trips for the orbit this lane holds */
+#ifdef CHAOS_PROFILE
+        prof_blk[tested ? 1 : 0] += 1;
+        prof_busy[tested ? 1 : 0] += __popc(__ballot_sync(CHAOS_FULL_MASK, busy));
+        prof_want += __popc(__ballot_sync(CHAOS_FULL_MASK, busy && o.wants_tested()));
+#endif
+        const bool done = run_block(o, it, busy, tested, nb, max_iter);
+        tested = __any_sync(CHAOS_FULL_MASK, busy && !done && o.wants_tested());
+        if (!__any_sync(CHAOS_FULL_MASK, done) && !first) continue;
         first = false;
+#ifdef CHAOS_PROFILE
+        prof_sched += 1;
+#endif
 
         /* (2) retire finished orbits into their slot (:125-127) */
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            if (done[j]) {
-                uint32_t et = o[j].finish(it[j], max_iter);
-                iters += it[j];
-                nsamples += 1;
-                uint32_t r = ws.hdr[slot[j]].rnd;
-                ws.sum[slot[j]][pix[j]] += et;
-                if (r < CHAOS_ADAPTIVE_THRESHOLD) ws.smp[slot[j]][r][pix[j]] = __uint2float_rn(et);
-                atomicSub(&ws.hdr[slot[j]].left, 1u);
-                busy[j] = false;
-            }
+        if (done) {
+            uint32_t et = o.finish(it, max_iter);
+            iters += it;
+            skipped += o.skipped();
+            nsamples += 1;
+            uint32_t r = ws.hdr[slot].rnd;
+            ws.sum[slot][pix] += et;
+            if (r < CHAOS_ADAPTIVE_THRESHOLD) ws.smp[slot][r][pix] = __uint2float_rn(et);
+            atomicSub(&ws.hdr[slot].left, 1u);
+            busy = false;
         }
         __syncwarp();
 
@@ -341,42 +295,45 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
             __syncwarp();
         }
 
-        /* (4) refill: idle orbit contexts take pending orbits, from any slot */
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            for (int k = 0; k < K; ++k) {
-                uint32_t idle = __ballot_sync(CHAOS_FULL_MASK, !busy[j]);
-                if (!idle) break;
-                const uint32_t pend = ws.hdr[k].pend;
-                if (!pend) continue;
-                uint32_t rank = __popc(idle & lanemask_lt());
-                bool take = !busy[j] && rank < (uint32_t)__popc(pend);
-                uint32_t mypix = 0;
-                if (take) {
-                    mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
-                    slot[j] = k;
-                    pix[j] = mypix;
-                    Real dx, dy, cx, cy;
-                    sample_delta<Real>(ws.hdr[k].rnd, spr, dx, dy);
-                    fm.template plane_point<fused_plane_y<FractalT>::value>(ws.hdr[k].x0 + (mypix & 7u), ws.hdr[k].y0 + (mypix >> 3), dx, dy, cx, cy);
-                    o[j].start(cx, cy);
-                    it[j] = 0;
-                    busy[j] = true;
-                }
-                uint32_t taken = __reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
-                __syncwarp();
-                if (lane == 0) ws.hdr[k].pend = pend & ~taken;
-                __syncwarp();
+        /* (4) refill: idle lanes take pending orbits, from any slot */
+        for (int k = 0; k < K; ++k) {
+            uint32_t idle = __ballot_sync(CHAOS_FULL_MASK, !busy);
+            if (!idle) break;
+            const uint32_t pend = ws.hdr[k].pend;
+            if (!pend) continue;
+            uint32_t rank = __popc(idle & lanemask_lt());
+            bool take = !busy && rank < (uint32_t)__popc(pend);
+            uint32_t mypix = 0;
+            if (take) {
+                mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
+                slot = k;
+                pix = mypix;
+                Real dx, dy, cx, cy;
+                sample_delta<Real>(ws.hdr[k].rnd, spr, dx, dy);
+                fm.template plane_point<fused_plane_y<FractalT>::value>(ws.hdr[k].x0 + (mypix & 7u), ws.hdr[k].y0 + (mypix >> 3), dx, dy, cx, cy);
+                o.start(cx, cy, ctx);
+                it = 0;
+                busy = true;
+                tested = true;                               /* new orbits start with a tested block */
             }
+            uint32_t taken = __reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
+            __syncwarp();
+            if (lane == 0) ws.hdr[k].pend = pend & ~taken;
+            __syncwarp();
         }
+        tested = __any_sync(CHAOS_FULL_MASK, tested);
 
         /* (5) nothing running after a full scheduling pass = no tile left anywhere for this warp */
-        bool any_busy = false;
-#pragma unroll
-        for (int j = 0; j < U; ++j) any_busy |= busy[j];
-        if (!__any_sync(CHAOS_FULL_MASK, any_busy)) break;
+        if (!__any_sync(CHAOS_FULL_MASK, busy)) break;
     }
-    flush_counters(a, iters, nsamples);
+#ifdef CHAOS_PROFILE
+    if (lane == 0) {
+        atomicAdd(&a.counters->prof[0], prof_blk[0]); atomicAdd(&a.counters->prof[1], prof_blk[1]);
+        atomicAdd(&a.counters->prof[2], prof_busy[0]); atomicAdd(&a.counters->prof[3], prof_busy[1]);
+        atomicAdd(&a.counters->prof[4], prof_sched); atomicAdd(&a.counters->prof[5], prof_want);
+    }
+#endif
+    flush_counters(a, iters, nsamples, skipped);
 }
 
 template <class Real, class FractalT>

@@ -101,10 +101,14 @@ typedef struct chaos_stats {
     float render_ms;                 /* iteration / reuse kernel, CUDA events on the render stream */
     float compose_ms;                /* compose kernel */
     float reuse_ms;                  /* fast frames: the reprojection pass alone (part of render_ms), else 0 */
-    uint32_t reserved;
-    uint64_t pixel_iterations;       /* sum of escape-loop trip counts over every evaluated sample */
+    float frame_ms;                  /* first render kernel's start to compose's end (what one frame costs on the device) */
+    uint64_t pixel_iterations;       /* sum of escape-loop trip counts over every evaluated sample, as the reference's
+                                      * loop counts them */
     uint64_t samples;                /* number of evaluated samples (orbits) */
     uint64_t launches_total;         /* kernels launched since the renderer was opened */
+    uint64_t skipped_iterations;     /* the part of pixel_iterations that was PROVEN instead of executed: an orbit whose
+                                      * state recurs bit for bit never escapes, so its trip count is maxIterations
+                                      * (same records as the reference; CHAOS_SHORTCUTS=0 executes every trip) */
 } chaos_stats;
 
 typedef struct chaos_provider chaos_provider;

@@ -269,3 +269,83 @@ def test_zoom_sequence_4k_matches_live_reference(cu, provider, double):
             helpers.assert_records_equal(got, want, "frame %d" % f)
             assert got["isReused"].mean() > 0.9 and (got["weightOfNewSamples"] > 0).sum() > 10000
             seg, ref_prev = new_seg, want
+
+
+# ---- count-preserving shortcuts of the escape loop (quadratic.cuh items 3 and 4): every trip executed and tested
+# ---- (CHAOS_SHORTCUTS=0) vs deferred test (1) vs deferred test + exact recurrence (3, the default) must give the same
+# ---- records, the same reference-equivalent pixel-iteration total and the same RGBA, on frames dominated by
+# ---- never-escaping orbits, odd iteration limits (tails shorter than a group), both precisions, both kernels.
+SHORTCUT_CASES = [
+    dict(name="sc_full_set_f64", fractal="mandelbrot", W=1920, H=1080, image=cases.seg(-0.5, 0.0, 2.0, 1920, 1080), maxIter=10007,
+         maxSS=8.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="sc_full_set_f32", fractal="mandelbrot", W=1920, H=1080, image=cases.seg(-0.5, 0.0, 2.0, 1920, 1080), maxIter=5003,
+         maxSS=4.0, flags=cases.A, double=False, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="sc_bulb_boundary_f64", fractal="mandelbrot", W=1280, H=720, image=cases.seg(-0.75, 0.05, 0.2, 1280, 720), maxIter=30000,
+         maxSS=1.0, flags=0, double=True, julia_c=(0.0, 0.0), amplifier=10),    # parabolic point: slow, non-closing orbits
+    dict(name="sc_tip_minus2_f64", fractal="mandelbrot", W=1280, H=720, image=cases.seg(-1.9, 0.0, 0.3, 1280, 720), maxIter=4001,
+         maxSS=3.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),    # |c|^2 crosses 3.6 inside the frame
+    dict(name="sc_julia_basilica_f64", fractal="julia", W=1920, H=1080, image=cases.seg(0.0, 0.0, 3.0, 1920, 1080), maxIter=5000,
+         maxSS=4.0, flags=cases.A, double=True, julia_c=(-1.0, 0.0), amplifier=10),   # c.im == 0: unscaled 6-operation form
+    dict(name="sc_julia_rabbit_f32", fractal="julia", W=1920, H=1080, image=cases.seg(0.0, 0.0, 3.0, 1920, 1080), maxIter=3001,
+         maxSS=2.0, flags=cases.A, double=False, julia_c=(-0.123, 0.745), amplifier=10),
+    dict(name="sc_sync_kernel_f64", fractal="mandelbrot", W=1920, H=1080, image=cases.seg(-0.5, 0.0, 2.0, 1920, 1080), maxIter=1001,
+         maxSS=6.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),    # below the refill threshold: tile-synchronous kernel
+    dict(name="sc_julia_far_c_f64", fractal="julia", W=640, H=360, image=cases.seg(0.0, 0.0, 5.0, 640, 360), maxIter=500,
+         maxSS=2.0, flags=cases.A, double=True, julia_c=(1.5, 1.5), amplifier=10),    # |c|^2 > 3.6: shortcuts must stay off
+]
+
+
+@pytest.mark.parametrize("case", SHORTCUT_CASES, ids=_ids(SHORTCUT_CASES))
+def test_shortcuts_change_nothing(cu, provider, case):
+    out = {}
+    for sc in (0, 1, 3):
+        os.environ["CHAOS_SHORTCUTS"] = str(sc)
+        try:
+            provider.getRenderer("test", False)   # drop the active renderer so the knob is re-read
+            r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+            r.renderQuality(helpers.model_for(cu, case))
+            st = r.stats()
+            out[sc] = (r.downloadRecords(), st.pixel_iterations, st.samples, r.outputRGBA(), st.skipped_iterations)
+        finally:
+            os.environ.pop("CHAOS_SHORTCUTS", None)
+    for sc in (1, 3):
+        helpers.assert_records_equal(out[sc][0], out[0][0], "%s shortcuts %d vs 0" % (case["name"], sc))
+        assert out[sc][1] == out[0][1] and out[sc][2] == out[0][2]
+        assert (out[sc][3] == out[0][3]).all()
+    assert out[0][4] == 0 and out[1][4] == 0
+    assert out[3][4] <= out[3][1]
+    if case["name"] == "sc_julia_far_c_f64":
+        assert out[3][4] == 0
+    elif case["name"] in ("sc_bulb_boundary_f64", "sc_tip_minus2_f64", "sc_sync_kernel_f64"):
+        assert out[3][4] > 0
+    else:
+        assert out[3][4] > out[3][1] // 2, "most of these frames' work is never-escaping orbits that close exactly"
+
+
+def test_shortcuts_in_fast_frames_change_nothing(cu, provider):
+    """zoom steps with resampling in the fovea: pass S runs escape loops through the tile-synchronous sampler"""
+    W, H, focus = 1920, 1080, (700, 500)
+    flags = cases.A | cases.FOV | cases.REUSE | cases.ZOOMING | cases.ZOOM_IN
+    base = dict(name="sczoom", fractal="mandelbrot", W=W, H=H, maxIter=3000, maxSS=4.0, flags=flags, double=True,
+                julia_c=(0.0, 0.0), amplifier=10, focus=focus)
+    frames = {}
+    for sc in (0, 3):
+        os.environ["CHAOS_SHORTCUTS"] = str(sc)
+        try:
+            provider.getRenderer("test", False)
+            seg = cases.seg(-0.6, 0.0, 2.0, W, H)
+            r = helpers.open_renderer(cu, provider, dict(base, image=seg), mode=cu.OUTPUT_DEVICE)
+            r.renderQuality(helpers.model_for(cu, dict(base, image=seg)))
+            got = []
+            for _ in range(3):
+                seg = cases.zoom_at(seg, W, H, focus, True)
+                r.renderFast(helpers.model_for(cu, dict(base, image=seg)))
+                st = r.stats()
+                got.append((r.downloadRecords(), st.pixel_iterations, st.samples, st.skipped_iterations))
+            frames[sc] = got
+        finally:
+            os.environ.pop("CHAOS_SHORTCUTS", None)
+    for f, (a, b) in enumerate(zip(frames[3], frames[0])):
+        helpers.assert_records_equal(a[0], b[0], "fast frame %d" % (f + 1))
+        assert a[1] == b[1] and a[2] == b[2] and b[3] == 0
+    assert frames[3][0][3] > 0
