@@ -333,6 +333,7 @@ struct chaos_renderer {
     uint32_t engine = 1;           /* 1 = lane-refill scheduler (default), 0 = tile-synchronous */
     uint32_t block_iters = 0;      /* 0 = choose from maxIterations */
     uint32_t shortcuts = CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE;   /* count-preserving shortcuts of the escape loop */
+    uint32_t sched_idle_indep = 6, sched_idle_rounds = 8;   /* see take_scheduling_pass (render_refill.cuh) */
 };
 
 static chaos_status check_renderer(const chaos_renderer *r)
@@ -517,6 +518,11 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (tp) r->two_pass = (uint32_t)atoi(tp) ? 1u : 0u;
     const char *nb = getenv("CHAOS_BLOCK_ITERS");
     if (nb) r->block_iters = ((uint32_t)atoi(nb) + 3u) & ~3u;
+    const char *si = getenv("CHAOS_SCHED_IDLE");   /* "indep,rounds" */
+    if (si) {
+        unsigned x = 0, y = 0;
+        if (sscanf(si, "%u,%u", &x, &y) == 2 && x >= 1 && y >= 1) { r->sched_idle_indep = x; r->sched_idle_rounds = y; }
+    }
     const char *sc = getenv("CHAOS_SHORTCUTS");   /* 0 = every trip executed and tested, as the reference does */
     if (sc) r->shortcuts = (uint32_t)atoi(sc) & (CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE);
     chaos_status st = load_module(r);
@@ -771,6 +777,8 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
      * orbit ended does not idle long; orbits are at most max_iter long */
     a->block_iters = r->block_iters ? r->block_iters : 128u;
     a->shortcuts = r->shortcuts;
+    a->sched_idle_lanes_indep = r->sched_idle_indep;
+    a->sched_idle_lanes_rounds = r->sched_idle_rounds;
 }
 
 static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg)
@@ -815,11 +823,6 @@ static chaos_status finish_frame(chaos_renderer *r)
     r->stats.pixel_iterations = r->counters_host->pixel_iterations;
     r->stats.samples = r->counters_host->samples;
     r->stats.skipped_iterations = r->counters_host->skipped_iterations;
-    if (getenv("CHAOS_PROFILE_PRINT")) {
-        const unsigned long long *q = r->counters_host->prof;
-        fprintf(stderr, "chaos profile: untested blocks %llu (busy lanes %.1f), tested blocks %llu (busy lanes %.1f), scheduling passes %llu, lanes waiting for a tested block %llu\n",
-                q[0], q[0] ? (double)q[2] / q[0] : 0.0, q[1], q[1] ? (double)q[3] / q[1] : 0.0, q[4], q[5]);
-    }
     return CHAOS_OK;
 }
 
@@ -878,6 +881,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
             const int small_grid = (int)std::min<uint64_t>((a.n_tiles + 255u) / 256u, (uint64_t)cap);
             CUresult em = D->p_cuMemsetD32Async(r->tile_tmax, 0u, a.n_tiles, r->stream);
             if (em == CUDA_SUCCESS) em = D->p_cuMemsetD32Async(r->tile_tmin, 0xffffffffu, a.n_tiles, r->stream);
+            if (em == CUDA_SUCCESS) em = D->p_cuMemsetD32Async(r->tile_key, 0u, a.n_tiles, r->stream);
             if (em != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed: %s", cu_err_name(em));
             a.phase = 1u;
             st = launch(r, k1, bi, 256, 0, &a);                    /* independent orbits: no slot memory */

@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 10u
+#define CHAOS_MODULE_ABI 11u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -43,7 +43,6 @@ struct chaos_counters {
     unsigned long long skipped_iterations; /* part of pixel_iterations that was proven, not executed (exact recurrence) */
     unsigned int bucket_count[CHAOS_COST_BUCKETS + 3];  /* tiles per cost class (chaosClassifyTiles) */
     unsigned int bucket_cursor[CHAOS_COST_BUCKETS + 3]; /* fill position per class (chaosOrderTiles) */
-    unsigned long long prof[8];         /* scheduler statistics of the rounds engine, filled only by -DCHAOS_PROFILE builds */
 };
 
 struct chaos_render_args {
@@ -76,6 +75,8 @@ struct chaos_render_args {
     uint32_t force_exact;   /* 1 = always the reference's 7-operation trip (differential check) */
     uint32_t block_iters;   /* engine 1: trips between two scheduling points (multiple of 4) */
     uint32_t shortcuts;     /* CHAOS_SHORTCUT_* bits an Orbit may use; 0 with force_exact */
+    uint32_t sched_idle_lanes_indep;   /* engine 1: finished or empty lanes a warp lets accumulate before a scheduling pass, */
+    uint32_t sched_idle_lanes_rounds;  /* independent orbits / sample rounds (1 = a pass after every block that ended an orbit) */
 };
 
 struct chaos_compose_args {

@@ -104,7 +104,7 @@ static __device__ __forceinline__ float dispersion(const float *s, uint32_t n, f
 
 /* per-pixel predicates of the decision block (:128-150) after sample i, for a pixel with the
  * running sum `sum` and stored samples s[0..min(i,9)] */
-struct vote_preds { bool eq, lt, le; };
+struct vote_preds { bool eq, lt, le, zero_mean; };
 static __device__ __forceinline__ vote_preds decision_preds(const float *s, uint32_t i, uint32_t sum)
 {
     vote_preds p;
@@ -122,6 +122,7 @@ static __device__ __forceinline__ vote_preds decision_preds(const float *s, uint
         var = __fmaf_rn(d, d, var);
     }
     float disp = __fdiv_rn(__fdiv_rn(var, __uint2float_rn(i - 1u)), mean);
+    p.zero_mean = mean == 0.f;      /* every dispersion of this pixel is NaN or inf as long as its mean stays 0: it vetoes both stop rules */
     p.eq = (i == 1u) && (fabsf(__fsub_rn(s[0], s[1])) < FLT_EPSILON);
     p.lt = disp < 0.01f;
     p.le = disp <= 1.0f;
@@ -241,7 +242,7 @@ static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_a
             }
         }
         if (decision_entered(adaptive, i, S)) {
-            vote_preds p = {true, true, true};
+            vote_preds p = {true, true, true, false};
             if (participate) p = decision_preds(samples, i, sum);
             bool all_eq = __all_sync(CHAOS_FULL_MASK, p.eq);
             bool all_lt = __all_sync(CHAOS_FULL_MASK, p.lt);

@@ -41,19 +41,30 @@
 #endif
 #define CHAOS_REFILL_WARPS (CHAOS_RENDER_THREADS / 32)
 
+/* Rounds 0 .. CHAOS_OVERLAP_ROUNDS-1 of a tile keep one escape time per pixel and round (the reference keeps the same
+ * ten values in samples[], :96), so several of them may be IN FLIGHT at once; their effects become visible to the
+ * decision logic strictly in round order.  Later rounds (maxSuperSampling > 10) only add to the running sum and run
+ * one at a time. */
+#define CHAOS_OVERLAP_ROUNDS CHAOS_ADAPTIVE_THRESHOLD
+
 struct refill_slot_hdr {
     uint32_t x0, y0;   /* tile origin */
     uint32_t S;        /* current sample bound (sampleCount) */
-    uint32_t rnd;      /* sample index i of the round in flight */
-    uint32_t pend;     /* pixels whose orbit of this round has not been handed to a lane yet */
-    uint32_t left;     /* orbits of this round not yet retired */
+    uint32_t dec;      /* the round whose decision is outstanding; every earlier round is complete and decided */
+    uint32_t issued;   /* rounds dec .. issued-1 are in flight */
     uint32_t inb;      /* in-bounds pixels = the voters */
     uint32_t active;
+    uint32_t rmask;    /* bit j: round slot j (= round % CHAOS_OVERLAP_ROUNDS) still has orbits no lane has taken */
+    uint32_t pend[CHAOS_OVERLAP_ROUNDS];   /* per round slot: pixels whose orbit has not been handed to a lane yet */
+    uint32_t left[CHAOS_OVERLAP_ROUNDS];   /* per round slot: orbits not yet retired */
+    /* work of the retired orbits of a round; counted into the frame's totals when the round is DECIDED, dropped if the
+     * tile stops before it (a round started ahead of its turn that turns out not to exist) */
+    unsigned long long iters[CHAOS_OVERLAP_ROUNDS], skipped[CHAOS_OVERLAP_ROUNDS];
 };
 
 struct refill_warp_store {
-    uint32_t sum[CHAOS_REFILL_SLOTS][32];
-    float smp[CHAOS_REFILL_SLOTS][CHAOS_ADAPTIVE_THRESHOLD][32];
+    uint32_t sum[CHAOS_REFILL_SLOTS][32];                            /* escape times of the decided rounds, summed */
+    uint32_t et[CHAOS_REFILL_SLOTS][CHAOS_OVERLAP_ROUNDS][32];       /* escape time per round and pixel */
     refill_slot_hdr hdr[CHAOS_REFILL_SLOTS];
 };
 
@@ -78,6 +89,21 @@ static __device__ __forceinline__ uint32_t lanemask_lt()
  * (Two orbits per lane with interleaved chains was measured in round 1 and removed: no gain once the loop is
  * pipe-bound, a loss with sample rounds.) */
 #define CHAOS_TESTED_BLOCK 40u   /* >= quadratic_orbit::kGroup + 1: the replay of a failed group ends inside one tested block */
+
+/* A scheduling pass costs the warp some hundred instructions, a lane that waits for one costs nothing but its share
+ * of the next blocks.  So a pass is not taken for every finished orbit: finished lanes wait until `idle_lanes` lanes
+ * are finished or empty, or `CHAOS_SCHED_MAX_WAIT` blocks have gone by since the first of them finished, or no lane is
+ * running any more.  (Results do not depend on when a pass is taken.) */
+#define CHAOS_SCHED_MAX_WAIT 8u
+static __device__ __forceinline__ bool take_scheduling_pass(bool fin, bool busy, uint32_t idle_lanes, uint32_t &waited)
+{
+    const uint32_t n_fin = __popc(__ballot_sync(CHAOS_FULL_MASK, fin));
+    const uint32_t n_run = __popc(__ballot_sync(CHAOS_FULL_MASK, busy && !fin));
+    if (n_run == 0u) { waited = 0u; return true; }
+    if (n_fin == 0u) { waited = 0u; return false; }
+    if (32u - n_run >= idle_lanes || ++waited >= CHAOS_SCHED_MAX_WAIT) { waited = 0u; return true; }
+    return false;
+}
 
 template <class Orbit>
 static __device__ __forceinline__ bool run_block(Orbit &o, uint32_t &it, bool busy, bool tested, uint32_t nb, uint32_t max_iter)
@@ -104,17 +130,19 @@ static __device__ void render_main_independent(const chaos_render_args &a)
 
     Orbit o;
     uint32_t it = 0, px = 0, py = 0, tile = 0;
-    bool busy = false;
+    bool busy = false, fin = false;                          /* fin: the orbit is over and waits to be retired */
     bool first = true, queue_empty = false, tested = true;
     uint32_t pend = 0, x0 = 0, y0 = 0, cur_tile = 0;         /* warp-uniform: the tile being handed out */
+    uint32_t waited = 0;
     unsigned long long iters = 0, nsamples = 0, skipped = 0;
 
     for (;;) {
-        const bool done = run_block(o, it, busy, tested, nb, max_iter);
-        tested = __any_sync(CHAOS_FULL_MASK, busy && !done && o.wants_tested());
-        if (!__any_sync(CHAOS_FULL_MASK, done) && !first) continue;
+        fin |= run_block(o, it, busy && !fin, tested, nb, max_iter);
+        tested = __any_sync(CHAOS_FULL_MASK, busy && !fin && o.wants_tested());
+        if (!take_scheduling_pass(fin, busy, a.sched_idle_lanes_indep, waited) && !first) continue;
         first = false;
-        if (done) {
+        if (fin) {
+            fin = false;
             uint32_t et = o.finish(it, max_iter);
             iters += it;
             skipped += o.skipped();
@@ -123,6 +151,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                 store_record(record_at(a.out, a.out_pitch, px, py), __uint_as_float(et), __uint_as_float(it), 0u, 0.f);
                 atomicMax(&a.tile_tmax[tile], it);
                 atomicMin(&a.tile_tmin[tile], it);
+                atomicMax(&a.tile_key[tile], it - o.skipped());   /* what the orbit COST: a proven never-ending orbit is cheap */
             }
             else          /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
                 store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
@@ -165,11 +194,32 @@ static __device__ void render_main_independent(const chaos_render_args &a)
 }
 
 /* ---- general case: sample rounds with tile-wide votes ----------------------------------------- */
+/* the first round after i at which the decision block is entered (:128); S if there is none */
+static __device__ __forceinline__ uint32_t next_decision_round(bool adaptive, uint32_t i, uint32_t S)
+{
+    if (adaptive && i + 1u < CHAOS_ADAPTIVE_THRESHOLD) return i + 1u;
+    return (S >> 1) > i ? (S >> 1) : S;
+}
+
+/*
+ * A tile's rounds are decided in order, but they need not RUN in order: the decision after round i only needs rounds
+ * 0..i complete.  After each decision the slot issues
+ *   - every round up to the next decision point (certain to run: nothing can change S before it), and
+ *   - if the tile looks set to use its whole sample budget -- some pixel's mean is 0 (its dispersion is undefined, which
+ *     vetoes both stop rules: tiles the set's boundary runs through, in modules that report 0 inside), or, from
+ *     sample 2 on, some pixel's dispersion is above 1 (not even the loosest stop rule fired) -- all remaining rounds
+ *     below CHAOS_OVERLAP_ROUNDS, ahead of their turn.
+ * A round started ahead of its turn is dropped without trace if the tile stops before it: its orbits are abandoned
+ * where they are and their trips are not counted.  So the records and the exact counters do not depend on the policy;
+ * only the tile's critical path does (one orbit instead of up to S sequential ones), and more orbits are pending per
+ * warp to keep the lanes filled.
+ */
 template <class Real, class FractalT, bool kResume>
 static __device__ void render_main_rounds(const chaos_render_args &a, refill_warp_store &ws)
 {
     typedef typename FractalT::template Orbit<Real> Orbit;
     constexpr int K = CHAOS_REFILL_SLOTS;
+    constexpr uint32_t R = CHAOS_OVERLAP_ROUNDS;
     frame_map<Real> fm;
     fm.init(a);
     const uint32_t lane = threadIdx.x & 31u;
@@ -181,88 +231,106 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(scf)));
     const float spr = sqrtf(__fadd_rn(scf, -2.0f));
 
-    if (lane < K) {
-        refill_slot_hdr z = {0, 0, 0, 0, 0, 0, 0, 0};
-        ws.hdr[lane] = z;
-    }
+    for (uint32_t w = lane; w < sizeof(ws.hdr) / 4u; w += 32u) reinterpret_cast<uint32_t *>(ws.hdr)[w] = 0u;
     __syncwarp();
 
     Orbit o;
-    uint32_t it = 0, slot = 0, pix = 0;
-    bool busy = false;
+    uint32_t it = 0, slot = 0, pix = 0, rnd = 0;
+    bool busy = false, fin = false;                          /* fin: the orbit is over and waits to be retired */
     bool first = true, queue_empty = false, tested = true;
-    unsigned long long iters = 0, nsamples = 0, skipped = 0;
+    uint32_t waited = 0;
+    unsigned long long iters = 0, nsamples = 0, skipped = 0;   /* lane 0 carries the warp's totals */
 
-#ifdef CHAOS_PROFILE
-    unsigned long long prof_blk[2] = {0, 0}, prof_busy[2] = {0, 0}, prof_sched = 0, prof_want = 0;
-#endif
     for (;;) {
         /* (1) iterate: one block of trips for the orbit this lane holds */
-#ifdef CHAOS_PROFILE
-        prof_blk[tested ? 1 : 0] += 1;
-        prof_busy[tested ? 1 : 0] += __popc(__ballot_sync(CHAOS_FULL_MASK, busy));
-        prof_want += __popc(__ballot_sync(CHAOS_FULL_MASK, busy && o.wants_tested()));
-#endif
-        const bool done = run_block(o, it, busy, tested, nb, max_iter);
-        tested = __any_sync(CHAOS_FULL_MASK, busy && !done && o.wants_tested());
-        if (!__any_sync(CHAOS_FULL_MASK, done) && !first) continue;
+        fin |= run_block(o, it, busy && !fin, tested, nb, max_iter);
+        tested = __any_sync(CHAOS_FULL_MASK, busy && !fin && o.wants_tested());
+        if (!take_scheduling_pass(fin, busy, a.sched_idle_lanes_rounds, waited) && !first) continue;
         first = false;
-#ifdef CHAOS_PROFILE
-        prof_sched += 1;
-#endif
 
         /* (2) retire finished orbits into their slot (:125-127) */
-        if (done) {
-            uint32_t et = o.finish(it, max_iter);
-            iters += it;
-            skipped += o.skipped();
-            nsamples += 1;
-            uint32_t r = ws.hdr[slot].rnd;
-            ws.sum[slot][pix] += et;
-            if (r < CHAOS_ADAPTIVE_THRESHOLD) ws.smp[slot][r][pix] = __uint2float_rn(et);
-            atomicSub(&ws.hdr[slot].left, 1u);
+        const uint32_t touched = __reduce_or_sync(CHAOS_FULL_MASK, fin ? (1u << slot) : 0u);   /* slots that got a result */
+        if (fin) {
+            fin = false;
+            const uint32_t et = o.finish(it, max_iter);
+            const uint32_t j = rnd % R;
+            if (rnd < R) ws.et[slot][rnd][pix] = et;
+            else ws.sum[slot][pix] += et;                   /* rounds >= R run one at a time, straight into the sum */
+            atomicAdd(&ws.hdr[slot].iters[j], (unsigned long long)it);
+            const uint32_t sk = o.skipped();
+            if (sk) atomicAdd(&ws.hdr[slot].skipped[j], (unsigned long long)sk);
+            atomicSub(&ws.hdr[slot].left[j], 1u);
             busy = false;
         }
         __syncwarp();
 
-        /* (3) rounds that just completed: decide (:128-150), then next round, or finish the tile and take a new one */
+        /* (3) per slot: decide every round that is complete and next in order (:128-150); issue further rounds, or
+         *     finish the tile and take a new one */
         for (int k = 0; k < K; ++k) {
-            refill_slot_hdr h = ws.hdr[k];
-            __syncwarp();                                   /* every lane has its copy before lane 0 rewrites the header */
-            if (h.active && h.left == 0u && h.pend == 0u) {
-                const uint32_t i = h.rnd;
-                uint32_t S = h.S;
-                const bool part = (h.inb >> lane) & 1u;
+            while ((touched >> k) & 1u) {                   /* only a slot that got a result can have completed a round */
+                const refill_slot_hdr &hk = ws.hdr[k];
+                const uint32_t act = hk.active, i = hk.dec, issued = hk.issued, inb = hk.inb;
+                uint32_t S = hk.S;
+                const uint32_t j = i % R;
+                const bool complete = act && i < issued && hk.left[j] == 0u && hk.pend[j] == 0u;
+                const unsigned long long r_iters = hk.iters[j], r_skipped = hk.skipped[j];
+                __syncwarp();                               /* every lane has read the header before lane 0 rewrites it */
+                if (!complete) break;
+                const bool part = (inb >> lane) & 1u;
+                if (i < R && part) ws.sum[k][lane] += ws.et[k][i][lane];
                 const uint32_t sum = ws.sum[k][lane];
+                if (lane == 0) { iters += r_iters; skipped += r_skipped; nsamples += (unsigned long long)__popc(inb); }
+                bool blocked = false;                       /* some pixel rules out even the loosest stop rule */
                 if (decision_entered(adaptive, i, S)) {
-                    vote_preds p = {true, true, true};
+                    vote_preds p = {true, true, true, false};
                     if (part) {
-                        float s[CHAOS_ADAPTIVE_THRESHOLD];
+                        float sm[CHAOS_ADAPTIVE_THRESHOLD];
 #pragma unroll
-                        for (uint32_t j = 0; j < CHAOS_ADAPTIVE_THRESHOLD; ++j) s[j] = (j <= i) ? ws.smp[k][j][lane] : 0.f;
-                        p = decision_preds(s, i, sum);
+                        for (uint32_t q = 0; q < CHAOS_ADAPTIVE_THRESHOLD; ++q) sm[q] = (q <= i) ? __uint2float_rn(ws.et[k][q][lane]) : 0.f;
+                        p = decision_preds(sm, i, sum);
                     }
-                    bool all_eq = __all_sync(CHAOS_FULL_MASK, p.eq);
-                    bool all_lt = __all_sync(CHAOS_FULL_MASK, p.lt);
-                    bool all_le = __all_sync(CHAOS_FULL_MASK, p.le);
+                    const bool all_eq = __all_sync(CHAOS_FULL_MASK, p.eq);
+                    const bool all_lt = __all_sync(CHAOS_FULL_MASK, p.lt);
+                    const bool all_le = __all_sync(CHAOS_FULL_MASK, p.le);
                     S = decision_update(i, S, all_eq, all_lt, all_le);
+                    /* after sample 1 every dispersion is a division by zero, so the vote says nothing then; a pixel whose
+                     * mean is 0 (all its samples 0: inside the set for modules that report 0 there) vetoes at every i */
+                    blocked = __any_sync(CHAOS_FULL_MASK, p.zero_mean && part) || (i >= 2u && !all_le);
                 }
                 if (i + 1u < S) {
+                    /* rounds certain to run, then rounds ahead of their turn; a round >= R only when it is the next one */
+                    uint32_t upto = min(next_decision_round(adaptive, i, S) + 1u, S);
+                    if (blocked) upto = S;
+                    upto = max(min(upto, R), i + 2u);
+                    upto = max(upto, issued);
                     if (lane == 0) {
-                        ws.hdr[k].rnd = i + 1u;
-                        ws.hdr[k].S = S;
-                        ws.hdr[k].pend = h.inb;
-                        ws.hdr[k].left = __popc(h.inb);
+                        refill_slot_hdr &h = ws.hdr[k];
+                        h.iters[j] = 0ull; h.skipped[j] = 0ull;
+                        h.dec = i + 1u;
+                        h.S = S;
+                        uint32_t rm = h.rmask;
+                        for (uint32_t r = issued; r < upto; ++r) {
+                            h.pend[r % R] = inb;
+                            h.left[r % R] = (uint32_t)__popc(inb);
+                            rm |= 1u << (r % R);
+                        }
+                        h.rmask = rm;
+                        h.issued = upto;
                     }
+                    __syncwarp();
                 } else {
                     if (part)
-                        store_record(record_at(a.out, a.out_pitch, h.x0 + (lane & 7u), h.y0 + (lane >> 3)),
+                        store_record(record_at(a.out, a.out_pitch, hk.x0 + (lane & 7u), hk.y0 + (lane >> 3)),
                                      __uint2float_rn(sum / S), __uint2float_rn(S), 0u, 0.f);
-                    if (lane == 0) ws.hdr[k].active = 0u;
-                    h.active = 0u;
+                    if (busy && slot == (uint32_t)k) busy = false;      /* rounds started ahead of their turn: abandoned */
+                    __syncwarp();
+                    if (lane < sizeof(refill_slot_hdr) / 4u) reinterpret_cast<uint32_t *>(&ws.hdr[k])[lane] = 0u;
+                    for (uint32_t w = 32u + lane; w < sizeof(refill_slot_hdr) / 4u; w += 32u) reinterpret_cast<uint32_t *>(&ws.hdr[k])[w] = 0u;
+                    __syncwarp();
+                    break;
                 }
             }
-            if (!h.active && !queue_empty) {
+            if (!ws.hdr[k].active && !queue_empty) {
                 uint32_t t = 0;
                 if (lane == 0) {
                     t = atomicAdd(kResume ? &a.counters->next_tile_b : &a.counters->next_tile, 1u);
@@ -276,63 +344,75 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                     uint32_t x0, y0;
                     tile_origin(a, t, x0, y0);
                     const bool in = (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height;
-                    uint32_t inb = __ballot_sync(CHAOS_FULL_MASK, in);
-                    uint32_t first_round = 0u;
+                    const uint32_t inb = __ballot_sync(CHAOS_FULL_MASK, in);
+                    uint32_t first_round = 0u, upto = 1u;
                     if (kResume) {           /* sample 0 was taken by pass A; its escape time sits in the record */
-                        uint32_t et0 = in ? __float_as_uint(record_at(a.out, a.out_pitch, x0 + (lane & 7u), y0 + (lane >> 3))->value) : 0u;
+                        const uint32_t et0 = in ? __float_as_uint(record_at(a.out, a.out_pitch, x0 + (lane & 7u), y0 + (lane >> 3))->value) : 0u;
                         ws.sum[k][lane] = et0;
-                        ws.smp[k][0][lane] = __uint2float_rn(et0);
+                        ws.et[k][0][lane] = et0;
                         first_round = 1u;
+                        upto = 2u;
                     } else {
                         ws.sum[k][lane] = 0u;
                     }
                     if (lane == 0) {
-                        refill_slot_hdr n = {x0, y0, S0, first_round, inb, (uint32_t)__popc(inb), inb, 1u};
-                        ws.hdr[k] = n;
+                        refill_slot_hdr &h = ws.hdr[k];
+                        h.x0 = x0; h.y0 = y0; h.S = S0; h.dec = first_round; h.issued = min(upto, max(S0, first_round + 1u)); h.inb = inb;
+                        uint32_t rm = 0u;
+                        for (uint32_t r = first_round; r < h.issued; ++r) {
+                            h.pend[r % R] = inb;
+                            h.left[r % R] = (uint32_t)__popc(inb);
+                            rm |= 1u << (r % R);
+                        }
+                        h.rmask = rm;
+                        h.active = 1u;
                     }
                 }
             }
             __syncwarp();
         }
 
-        /* (4) refill: idle lanes take pending orbits, from any slot */
+        /* (4) refill: idle lanes take pending orbits, from any slot, earliest round first */
         for (int k = 0; k < K; ++k) {
             uint32_t idle = __ballot_sync(CHAOS_FULL_MASK, !busy);
             if (!idle) break;
-            const uint32_t pend = ws.hdr[k].pend;
-            if (!pend) continue;
-            uint32_t rank = __popc(idle & lanemask_lt());
-            bool take = !busy && rank < (uint32_t)__popc(pend);
-            uint32_t mypix = 0;
-            if (take) {
-                mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
-                slot = k;
-                pix = mypix;
-                Real dx, dy, cx, cy;
-                sample_delta<Real>(ws.hdr[k].rnd, spr, dx, dy);
-                fm.template plane_point<fused_plane_y<FractalT>::value>(ws.hdr[k].x0 + (mypix & 7u), ws.hdr[k].y0 + (mypix >> 3), dx, dy, cx, cy);
-                o.start(cx, cy, ctx);
-                it = 0;
-                busy = true;
-                tested = true;                               /* new orbits start with a tested block */
+            const uint32_t dec = ws.hdr[k].dec, issued = ws.hdr[k].issued;
+            if (!ws.hdr[k].rmask) continue;
+            for (uint32_t r = dec; r < issued && idle; ++r) {
+                const uint32_t j = r % R;
+                const uint32_t pend = ws.hdr[k].pend[j];
+                if (!pend) continue;
+                const uint32_t rank = __popc(idle & lanemask_lt());
+                const bool take = !busy && rank < (uint32_t)__popc(pend);
+                uint32_t mypix = 0;
+                if (take) {
+                    mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
+                    slot = k;
+                    pix = mypix;
+                    rnd = r;
+                    Real dx, dy, cx, cy;
+                    sample_delta<Real>(r, spr, dx, dy);
+                    fm.template plane_point<fused_plane_y<FractalT>::value>(ws.hdr[k].x0 + (mypix & 7u), ws.hdr[k].y0 + (mypix >> 3), dx, dy, cx, cy);
+                    o.start(cx, cy, ctx);
+                    it = 0;
+                    busy = true;
+                    tested = true;                           /* new orbits start with a tested block */
+                }
+                const uint32_t taken = __reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
+                __syncwarp();
+                if (lane == 0) {
+                    ws.hdr[k].pend[j] = pend & ~taken;
+                    if ((pend & ~taken) == 0u) ws.hdr[k].rmask &= ~(1u << j);
+                }
+                __syncwarp();
+                idle = __ballot_sync(CHAOS_FULL_MASK, !busy);
             }
-            uint32_t taken = __reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
-            __syncwarp();
-            if (lane == 0) ws.hdr[k].pend = pend & ~taken;
-            __syncwarp();
         }
         tested = __any_sync(CHAOS_FULL_MASK, tested);
 
         /* (5) nothing running after a full scheduling pass = no tile left anywhere for this warp */
         if (!__any_sync(CHAOS_FULL_MASK, busy)) break;
     }
-#ifdef CHAOS_PROFILE
-    if (lane == 0) {
-        atomicAdd(&a.counters->prof[0], prof_blk[0]); atomicAdd(&a.counters->prof[1], prof_blk[1]);
-        atomicAdd(&a.counters->prof[2], prof_busy[0]); atomicAdd(&a.counters->prof[3], prof_busy[1]);
-        atomicAdd(&a.counters->prof[4], prof_sched); atomicAdd(&a.counters->prof[5], prof_want);
-    }
-#endif
     flush_counters(a, iters, nsamples, skipped);
 }
 
@@ -350,7 +430,9 @@ static __device__ __forceinline__ void render_main_refill(const chaos_render_arg
 
 
 /* ---- cost classes between the two passes ------------------------------------------------------ */
-/* Expected critical path of a tile's remaining rounds from pass A's trip counts (tile_tmax/tile_tmin):
+/* Expected critical path of a tile's remaining rounds from pass A's trip counts (tile_tmax/tile_tmin, and the longest
+ * executed orbit in tile_key -- with exact recurrence a never-ending orbit may have cost a few hundred trips or all of
+ * maxIterations, and only the latter kind makes a tile expensive):
  *   longest orbit x (S0 - 1) rounds if the pixels disagree (the tile will probably use its whole sample budget),
  *   x 1 if all agree (the i == 1 vote will most likely end it after one more round).
  * (Also ranking a tile by its 8 neighbours' longest orbit -- to catch boundary tiles whose own sample-0 orbits all
@@ -365,7 +447,7 @@ static __device__ void classify_tiles(const chaos_render_args &a)
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_tiles; t += gridDim.x * blockDim.x) {
         const uint32_t own_max = a.tile_tmax[t], own_min = a.tile_tmin[t];
-        const uint32_t nmax = own_max;
+        const uint32_t nmax = a.tile_key[t];          /* pass A left the longest EXECUTED orbit here; replaced by the class below */
         const bool uniform = own_max == own_min;
         const unsigned long long est = (unsigned long long)(nmax | 1u) * (uniform ? 1u : (S0 > 1u ? S0 - 1u : 1u));
         const uint32_t key = (uint32_t)__clzll((long long)est) - 27u;      /* est < 2^37: clzll in [27,63] -> key in [0,36] */
