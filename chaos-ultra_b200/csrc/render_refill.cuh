@@ -77,6 +77,26 @@ static __device__ __forceinline__ uint32_t lanemask_lt()
     return m;
 }
 
+/* position of the n-th (0-based) set bit of m; n < popc(m).  (__fns is a loop of up to 32 steps.) */
+static __device__ __forceinline__ uint32_t nth_set_bit(uint32_t m, uint32_t n)
+{
+    uint32_t pos = 0;
+#pragma unroll
+    for (uint32_t w = 16u; w; w >>= 1) {
+        const uint32_t c = __popc(m & ((1u << w) - 1u));
+        if (n >= c) { n -= c; m >>= w; pos += w; }
+    }
+    return pos;
+}
+
+/* 64-bit add in shared memory from 32-bit pieces (a 64-bit shared atomicAdd is a compare-and-swap loop) */
+static __device__ __forceinline__ void shared_add64(unsigned long long *p, uint32_t v)
+{
+    unsigned int *w = reinterpret_cast<unsigned int *>(p);
+    const unsigned int old = atomicAdd(w, v);
+    if (old + v < old) atomicAdd(w + 1, 1u);
+}
+
 /* ---- phases ------------------------------------------------------------------------------------------
  * All lanes of a warp run the escape loop together for a BLOCK of trips, then meet at a scheduling point.
  * A block is either TESTED (every trip carries its escape test; short: CHAOS_TESTED_BLOCK trips) or UNTESTED
@@ -174,7 +194,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
             bool take = !busy && rank < (uint32_t)__popc(pend);
             uint32_t mypix = 0;
             if (take) {
-                mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
+                mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : nth_set_bit(pend, rank);
                 px = x0 + (mypix & 7u);
                 py = y0 + (mypix >> 3);
                 tile = cur_tile;
@@ -256,9 +276,9 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
             const uint32_t j = rnd % R;
             if (rnd < R) ws.et[slot][rnd][pix] = et;
             else ws.sum[slot][pix] += et;                   /* rounds >= R run one at a time, straight into the sum */
-            atomicAdd(&ws.hdr[slot].iters[j], (unsigned long long)it);
+            shared_add64(&ws.hdr[slot].iters[j], it);
             const uint32_t sk = o.skipped();
-            if (sk) atomicAdd(&ws.hdr[slot].skipped[j], (unsigned long long)sk);
+            if (sk) shared_add64(&ws.hdr[slot].skipped[j], sk);
             atomicSub(&ws.hdr[slot].left[j], 1u);
             busy = false;
         }
@@ -386,7 +406,7 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                 const bool take = !busy && rank < (uint32_t)__popc(pend);
                 uint32_t mypix = 0;
                 if (take) {
-                    mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : __fns(pend, 0u, rank + 1u);
+                    mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : nth_set_bit(pend, rank);
                     slot = k;
                     pix = mypix;
                     rnd = r;
