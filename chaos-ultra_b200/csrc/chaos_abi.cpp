@@ -299,18 +299,22 @@ struct chaos_renderer {
     /* module (FractalRenderingModule) */
     CUmodule module = nullptr;
     CUfunction k_main_f = nullptr, k_main_d = nullptr, k_adv_f = nullptr, k_adv_d = nullptr;
+    CUfunction k_pass_a[2] = {nullptr, nullptr}, k_pass_b[2] = {nullptr, nullptr}, k_pass_c[2] = {nullptr, nullptr};   /* [0] float, [1] double */
+    int blocks_pass_a[2] = {0, 0}, blocks_pass_b[2] = {0, 0}, blocks_pass_c[2] = {0, 0};
     CUfunction k_main_f_sync = nullptr, k_main_d_sync = nullptr;   /* engine 0 (differential check) */
     CUfunction k_classify = nullptr, k_order = nullptr;            /* between the two passes of engine 1 */
+    CUfunction k_replay = nullptr;                                 /* pass D */
+    chaos_export exp_buf = {0, nullptr, nullptr, nullptr, nullptr, nullptr};   /* pass B -> pass C -> pass D (device memory) */
+    uint32_t export_enabled = 1;
     CUfunction k_reuse_f = nullptr, k_reuse_d = nullptr;           /* pass R of a fast frame */
     int blocks_reuse_f = 0, blocks_reuse_d = 0;
     CUdeviceptr tile_key = 0, tile_order = 0, tile_tmax = 0, tile_tmin = 0;
-    uint32_t two_pass = 1;
+    CUdeviceptr warp_trace = 0;         /* diagnostics, CHAOS_WARP_TRACE=<file>: per-warp timeline of pass B */
     uint32_t sync_below_iters = 2048;   /* see render_quality_locked */
     int blocks_main_f_sync = 0, blocks_main_d_sync = 0;
     uint32_t refill_smem = 0;
     CUfunction k_compose = nullptr, k_undersampled = nullptr, k_debug = nullptr;
     int blocks_main_f = 0, blocks_main_d = 0, blocks_adv_f = 0, blocks_adv_d = 0;
-    int blocks_indep_f = 0, blocks_indep_d = 0;   /* the same main kernels launched without slot memory (independent orbits) */
     /* renderer state (CudaFractalRenderer) */
     chaos_state state = CHAOS_STATE_NOT_INITIALIZED;
     uint32_t width = 0, height = 0;
@@ -442,10 +446,13 @@ static chaos_status load_module(chaos_renderer *r)
     /* all kernels are resolved eagerly; a missing one is an error (FractalRenderingModule.java:91-97) */
     struct { const char *name; CUfunction *fn; } fns[] = {
         {"fractalRenderMainFloat", &r->k_main_f}, {"fractalRenderMainDouble", &r->k_main_d},
+        {"chaosPassAFloat", &r->k_pass_a[0]}, {"chaosPassADouble", &r->k_pass_a[1]},
+        {"chaosPassBFloat", &r->k_pass_b[0]}, {"chaosPassBDouble", &r->k_pass_b[1]},
+        {"chaosPassCFloat", &r->k_pass_c[0]}, {"chaosPassCDouble", &r->k_pass_c[1]},
         {"fractalRenderAdvancedFloat", &r->k_adv_f}, {"fractalRenderAdvancedDouble", &r->k_adv_d},
         {"fractalRenderUnderSampled", &r->k_undersampled}, {"compose", &r->k_compose}, {"debug", &r->k_debug},
         {"fractalRenderMainFloatSync", &r->k_main_f_sync}, {"fractalRenderMainDoubleSync", &r->k_main_d_sync},
-        {"chaosClassifyTiles", &r->k_classify}, {"chaosOrderTiles", &r->k_order},
+        {"chaosClassifyTiles", &r->k_classify}, {"chaosOrderTiles", &r->k_order}, {"chaosReplayExported", &r->k_replay},
         {"chaosReusePassFloat", &r->k_reuse_f}, {"chaosReusePassDouble", &r->k_reuse_d},
     };
     for (auto &k : fns) {
@@ -468,14 +475,17 @@ static chaos_status load_module(chaos_renderer *r)
         unload_module(r);
         return fail(CHAOS_ERR_CUDA_INIT, "module %s does not export CHAOS_REFILL_SMEM", path.c_str());
     }
-    for (CUfunction fn : {r->k_main_f, r->k_main_d}) {
+    for (CUfunction fn : {r->k_pass_b[0], r->k_pass_b[1]}) {
         CUresult ea = D->p_cuFuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)r->refill_smem);
         if (ea != CUDA_SUCCESS) { unload_module(r); return fail(CHAOS_ERR_CUDA_INIT, "cannot reserve %u B of shared memory: %s", r->refill_smem, cu_err_name(ea)); }
     }
-    r->blocks_main_f = persistent_blocks(r, r->k_main_f, 256, r->refill_smem);
-    r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256, r->refill_smem);
-    r->blocks_indep_f = persistent_blocks(r, r->k_main_f, 256, 0);
-    r->blocks_indep_d = persistent_blocks(r, r->k_main_d, 256, 0);
+    r->blocks_main_f = persistent_blocks(r, r->k_main_f, 256);
+    r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256);
+    for (int p = 0; p < 2; ++p) {
+        r->blocks_pass_a[p] = persistent_blocks(r, r->k_pass_a[p], 256);
+        r->blocks_pass_b[p] = persistent_blocks(r, r->k_pass_b[p], 256, r->refill_smem);
+        r->blocks_pass_c[p] = persistent_blocks(r, r->k_pass_c[p], 256);
+    }
     r->blocks_main_f_sync = persistent_blocks(r, r->k_main_f_sync, 256);
     r->blocks_main_d_sync = persistent_blocks(r, r->k_main_d_sync, 256);
     r->blocks_reuse_f = persistent_blocks(r, r->k_reuse_f, 256);
@@ -514,8 +524,6 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (eng) r->engine = (uint32_t)atoi(eng) ? 1u : 0u;
     const char *sb = getenv("CHAOS_SYNC_BELOW");
     if (sb) r->sync_below_iters = (uint32_t)atoi(sb);
-    const char *tp = getenv("CHAOS_TWO_PASS");
-    if (tp) r->two_pass = (uint32_t)atoi(tp) ? 1u : 0u;
     const char *nb = getenv("CHAOS_BLOCK_ITERS");
     if (nb) r->block_iters = ((uint32_t)atoi(nb) + 3u) & ~3u;
     const char *si = getenv("CHAOS_SCHED_IDLE");   /* "indep,rounds" */
@@ -523,6 +531,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
         unsigned x = 0, y = 0;
         if (sscanf(si, "%u,%u", &x, &y) == 2 && x >= 1 && y >= 1) { r->sched_idle_indep = x; r->sched_idle_rounds = y; }
     }
+    const char *ex = getenv("CHAOS_EXPORT");      /* 0 = every tile keeps all its rounds in pass B */
+    if (ex) r->export_enabled = (uint32_t)atoi(ex) ? 1u : 0u;
     const char *sc = getenv("CHAOS_SHORTCUTS");   /* 0 = every trip executed and tested, as the reference does */
     if (sc) r->shortcuts = (uint32_t)atoi(sc) & (CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE);
     chaos_status st = load_module(r);
@@ -545,6 +555,39 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
 /* ------------------------------------------------------------------------------------------
  * lifecycle
  * ---------------------------------------------------------------------------------------- */
+static void free_export(chaos_renderer *r)
+{
+    chaos_export &x = r->exp_buf;
+    if (x.tile) D->p_cuMemFree((CUdeviceptr)x.tile);
+    if (x.first) D->p_cuMemFree((CUdeviceptr)x.first);
+    if (x.et) D->p_cuMemFree((CUdeviceptr)x.et);
+    if (x.iters) D->p_cuMemFree((CUdeviceptr)x.iters);
+    if (x.skipped) D->p_cuMemFree((CUdeviceptr)x.skipped);
+    x = chaos_export{0, nullptr, nullptr, nullptr, nullptr, nullptr};
+}
+
+/* arrays for the tiles pass B hands to pass C; allocated by the first multi-sample render of a frame size */
+static bool ensure_export(chaos_renderer *r, uint32_t n_tiles)
+{
+    chaos_export &x = r->exp_buf;
+    if (x.capacity >= n_tiles) return true;
+    D->p_cuStreamSynchronize(r->stream);
+    free_export(r);
+    CUdeviceptr p[5] = {0, 0, 0, 0, 0};
+    const size_t bytes[5] = {(size_t)n_tiles * 4u, (size_t)n_tiles * 4u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 32u * 4u,
+                             (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u};
+    for (int i = 0; i < 5; ++i) {
+        if (D->p_cuMemAlloc(&p[i], bytes[i]) != CUDA_SUCCESS) {
+            for (int j = 0; j < i; ++j) D->p_cuMemFree(p[j]);
+            return false;
+        }
+    }
+    x.capacity = n_tiles;
+    x.tile = (uint32_t *)p[0]; x.first = (uint32_t *)p[1]; x.et = (uint32_t *)p[2];
+    x.iters = (unsigned long long *)p[3]; x.skipped = (unsigned long long *)p[4];
+    return true;
+}
+
 static void free_frame_memory(chaos_renderer *r)
 {
     for (int i = 0; i < 2; ++i) if (r->buf[i].ptr) { D->p_cuMemFree(r->buf[i].ptr); r->buf[i].ptr = 0; r->buf[i].pitch = 0; }
@@ -553,6 +596,7 @@ static void free_frame_memory(chaos_renderer *r)
     if (r->tile_order) { D->p_cuMemFree(r->tile_order); r->tile_order = 0; }
     if (r->tile_tmax) { D->p_cuMemFree(r->tile_tmax); r->tile_tmax = 0; }
     if (r->tile_tmin) { D->p_cuMemFree(r->tile_tmin); r->tile_tmin = 0; }
+    free_export(r);
     if (r->rgba_host) { D->p_cuMemFreeHost(r->rgba_host); r->rgba_host = nullptr; r->rgba_dev = 0; }
     if (r->rgba_dev) { D->p_cuMemFree(r->rgba_dev); r->rgba_dev = 0; }
 }
@@ -864,9 +908,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
     if (a.n_tiles) {
-        CUfunction k1 = dbl ? r->k_main_d : r->k_main_f;
-        const int b1 = dbl ? r->blocks_main_d : r->blocks_main_f;
-        const int bi = dbl ? r->blocks_indep_d : r->blocks_indep_f;
+        const int p = dbl ? 1 : 0;
         const uint32_t S0 = (uint32_t)std::min(64.0f, roundf(m->max_super_sampling));
         /* Short orbits (low iteration limit) with several samples: the per-orbit scheduling work of the refill
          * engine costs more than the divergence it removes, so those frames take the tile-synchronous kernel
@@ -875,24 +917,45 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         a.force_exact = r->engine == 0 ? 1u : 0u;
         if (sync_kernel) {
             st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a);
-        } else if (S0 >= 2u && r->two_pass) {
-            /* pass A: sample 0 of every pixel; classify + order: expected-longest tiles first; pass B: the other rounds */
+        } else if (S0 <= 1u) {
+            st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, 0, &a);
+        } else {
+            /* pass A: sample 0 of every pixel; classify + order: expected-longest tiles first; pass B: the other rounds,
+             * except those of tiles set to use their whole budget -> pass C (independent orbits) + pass D (their decisions) */
             const int cap = r->provider->sm_count * 4;
             const int small_grid = (int)std::min<uint64_t>((a.n_tiles + 255u) / 256u, (uint64_t)cap);
             CUresult em = D->p_cuMemsetD32Async(r->tile_tmax, 0u, a.n_tiles, r->stream);
             if (em == CUDA_SUCCESS) em = D->p_cuMemsetD32Async(r->tile_tmin, 0xffffffffu, a.n_tiles, r->stream);
             if (em == CUDA_SUCCESS) em = D->p_cuMemsetD32Async(r->tile_key, 0u, a.n_tiles, r->stream);
             if (em != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed: %s", cu_err_name(em));
+            if (r->export_enabled && S0 >= 3u && S0 <= CHAOS_EXPORT_ROUNDS && ensure_export(r, a.n_tiles)) a.exp = r->exp_buf;
             a.phase = 1u;
-            st = launch(r, k1, bi, 256, 0, &a);                    /* independent orbits: no slot memory */
+            st = launch(r, r->k_pass_a[p], r->blocks_pass_a[p], 256, 0, &a);
             if (st == CHAOS_OK) st = launch(r, r->k_classify, small_grid, 256, 0, &a);
             if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &a);
             a.phase = 2u;
-            if (st == CHAOS_OK) st = launch(r, k1, b1, 256, r->refill_smem, &a);
-        } else if (S0 <= 1u) {
-            st = launch(r, k1, bi, 256, 0, &a);
-        } else {
-            st = launch(r, k1, b1, 256, r->refill_smem, &a);
+            const char *trace_path = getenv("CHAOS_WARP_TRACE");
+            const size_t trace_bytes = (size_t)r->blocks_pass_b[p] * 8u * 8u * sizeof(unsigned long long);
+            if (trace_path) {
+                if (!r->warp_trace && D->p_cuMemAlloc(&r->warp_trace, trace_bytes) != CUDA_SUCCESS) r->warp_trace = 0;
+                if (r->warp_trace) { D->p_cuMemsetD8Async(r->warp_trace, 0, trace_bytes, r->stream); a.warp_trace = (unsigned long long *)r->warp_trace; }
+            }
+            if (st == CHAOS_OK) st = launch(r, r->k_pass_b[p], r->blocks_pass_b[p], 256, r->refill_smem, &a);
+            if (trace_path && r->warp_trace && st == CHAOS_OK) {
+                std::vector<unsigned long long> host(trace_bytes / sizeof(unsigned long long));
+                D->p_cuStreamSynchronize(r->stream);
+                if (D->p_cuMemcpyDtoH(host.data(), r->warp_trace, trace_bytes) == CUDA_SUCCESS) {
+                    FILE *f = fopen(trace_path, "wb");
+                    if (f) { fwrite(host.data(), 1, trace_bytes, f); fclose(f); }
+                }
+            }
+            a.warp_trace = nullptr;
+            if (a.exp.capacity) {
+                a.phase = 3u;
+                if (st == CHAOS_OK) st = launch(r, r->k_pass_c[p], r->blocks_pass_c[p], 256, 0, &a);
+                const int replay_grid = (int)std::min<uint64_t>((a.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);
+                if (st == CHAOS_OK) st = launch(r, r->k_replay, replay_grid, 256, 0, &a);
+            }
         }
         if (st != CHAOS_OK) return st;
     }

@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 11u
+#define CHAOS_MODULE_ABI 14u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -37,12 +37,29 @@ struct chaos_pixel_info {
 #define CHAOS_COST_BUCKETS 37
 struct chaos_counters {
     unsigned int next_tile;             /* work-stealing cursor over vote tiles */
-    unsigned int next_tile_b;           /* second cursor (pass B of a two-pass render) */
+    unsigned int next_tile_b;           /* pass B: cursor from the expensive end of tile_order (fast frames: the sampling pass' cursor) */
+    unsigned int tail_tile_b;           /* pass B: cursor from the cheap end */
+    unsigned int claimed_b;             /* pass B: tiles claimed from either end */
+    unsigned int n_exported;            /* pass B: tiles whose remaining rounds were handed to pass C (may exceed export.capacity: clamp) */
+    unsigned int next_export_item;      /* pass C: work-stealing cursor over (exported tile, round) items */
     unsigned long long pixel_iterations;
     unsigned long long samples;
     unsigned long long skipped_iterations; /* part of pixel_iterations that was proven, not executed (exact recurrence) */
     unsigned int bucket_count[CHAOS_COST_BUCKETS + 3];  /* tiles per cost class (chaosClassifyTiles) */
     unsigned int bucket_cursor[CHAOS_COST_BUCKETS + 3]; /* fill position per class (chaosOrderTiles) */
+};
+
+/* Tiles that will (almost surely) use their whole sample budget leave pass B after a decision: their remaining rounds
+ * are run by pass C as independent orbits of one GPU-wide pool, and pass D replays the decisions over the stored
+ * escape times (render_refill.cuh).  Rounds are stored for S <= CHAOS_EXPORT_ROUNDS only. */
+#define CHAOS_EXPORT_ROUNDS 10
+struct chaos_export {
+    uint32_t capacity;                  /* tiles the arrays below can hold (0 = no export) */
+    uint32_t *tile;                     /* [capacity] which tile */
+    uint32_t *first;                    /* [capacity] first round pass C computes for it (the earlier ones came with it) */
+    uint32_t *et;                       /* [capacity][CHAOS_EXPORT_ROUNDS][32] escape time per round and pixel */
+    unsigned long long *iters;          /* [capacity][CHAOS_EXPORT_ROUNDS] trips of the round's orbits (reference count) */
+    unsigned long long *skipped;        /* [capacity][CHAOS_EXPORT_ROUNDS] of which proven, not executed */
 };
 
 struct chaos_render_args {
@@ -70,11 +87,14 @@ struct chaos_render_args {
     uint32_t *tile_tmin;    /* [n_tiles] shortest one (atomicMin) */
     uint32_t *tile_key;     /* [n_tiles] cost class of each tile after pass A */
     uint32_t *tile_order;   /* [n_tiles] tiles sorted by descending expected cost: the order pass B takes them in */
-    uint32_t phase;         /* 0 = whole render in one launch; 1 = pass A (sample 0 of every pixel); 2 = pass B (the rest) */
+    uint32_t phase;         /* 0 = whole render in one launch; 1 = pass A (sample 0 of every pixel); 2 = pass B (the rest);
+                             * 3 = pass C (the rounds pass B exported, as independent orbits) */
+    chaos_export exp;
     uint32_t engine;        /* 0 = tile-synchronous, 1 = lane-refill scheduler */
     uint32_t force_exact;   /* 1 = always the reference's 7-operation trip (differential check) */
     uint32_t block_iters;   /* engine 1: trips between two scheduling points (multiple of 4) */
     uint32_t shortcuts;     /* CHAOS_SHORTCUT_* bits an Orbit may use; 0 with force_exact */
+    unsigned long long *warp_trace;   /* NULL, or [warps][8]: per-warp timeline of the rounds engine (CHAOS_WARP_TRACE, diagnostics) */
     uint32_t sched_idle_lanes_indep;   /* engine 1: finished or empty lanes a warp lets accumulate before a scheduling pass, */
     uint32_t sched_idle_lanes_rounds;  /* independent orbits / sample rounds (1 = a pass after every block that ended an orbit) */
 };

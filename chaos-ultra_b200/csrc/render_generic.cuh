@@ -590,12 +590,26 @@ static __device__ void advanced_sample_pass(const chaos_render_args &a)
 
 extern "C" __global__ void init() {}
 
-/* engine 1 (default): lane-refill scheduler; dynamic shared memory = CHAOS_REFILL_SMEM_BYTES */
+/* engine 1 (default): lane-refill scheduler (render_refill.cuh).  One kernel per pass, each with its own register
+ * allocation.  fractalRenderMain*: one sample per pixel, the whole frame in one launch; multi-sample frames run
+ * chaosPassA* (sample 0), chaosPassB* (rounds with votes; dynamic shared memory = CHAOS_REFILL_SMEM_BYTES),
+ * chaosPassC* (exported rounds as independent orbits) and chaosReplayExported. */
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
-fractalRenderMainFloat(const __grid_constant__ chaos_render_args a) { render_main_refill<float, Fractal>(a); }
-
+fractalRenderMainFloat(const __grid_constant__ chaos_render_args a) { render_main_independent<float, Fractal, 0>(a); }
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
-fractalRenderMainDouble(const __grid_constant__ chaos_render_args a) { render_main_refill<double, Fractal>(a); }
+fractalRenderMainDouble(const __grid_constant__ chaos_render_args a) { render_main_independent<double, Fractal, 0>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosPassAFloat(const __grid_constant__ chaos_render_args a) { render_main_independent<float, Fractal, 1>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosPassADouble(const __grid_constant__ chaos_render_args a) { render_main_independent<double, Fractal, 1>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosPassBFloat(const __grid_constant__ chaos_render_args a) { render_pass_b<float, Fractal>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosPassBDouble(const __grid_constant__ chaos_render_args a) { render_pass_b<double, Fractal>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosPassCFloat(const __grid_constant__ chaos_render_args a) { render_main_independent<float, Fractal, 2>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosPassCDouble(const __grid_constant__ chaos_render_args a) { render_main_independent<double, Fractal, 2>(a); }
 
 /* engine 0: tile-synchronous, reference operation sequence; the differential check of engine 1 */
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
@@ -607,6 +621,8 @@ fractalRenderMainDoubleSync(const __grid_constant__ chaos_render_args a) { rende
 /* between pass A and pass B of a two-pass render (render_refill.cuh) */
 extern "C" __global__ void __launch_bounds__(256) chaosClassifyTiles(const __grid_constant__ chaos_render_args a) { classify_tiles(a); }
 extern "C" __global__ void __launch_bounds__(256) chaosOrderTiles(const __grid_constant__ chaos_render_args a) { order_tiles(a); }
+/* after pass C: the decisions of the tiles pass B exported */
+extern "C" __global__ void __launch_bounds__(256) chaosReplayExported(const __grid_constant__ chaos_render_args a) { replay_exported(a); }
 
 /* shared-memory need of the engine-1 kernels, read by the host at module load */
 __constant__ uint32_t CHAOS_REFILL_SMEM = (uint32_t)CHAOS_REFILL_SMEM_BYTES;

@@ -55,6 +55,7 @@ struct refill_slot_hdr {
     uint32_t inb;      /* in-bounds pixels = the voters */
     uint32_t active;
     uint32_t rmask;    /* bit j: round slot j (= round % CHAOS_OVERLAP_ROUNDS) still has orbits no lane has taken */
+    uint32_t tile;     /* the tile's index */
     uint32_t pend[CHAOS_OVERLAP_ROUNDS];   /* per round slot: pixels whose orbit has not been handed to a lane yet */
     uint32_t left[CHAOS_OVERLAP_ROUNDS];   /* per round slot: orbits not yet retired */
     /* work of the retired orbits of a round; counted into the frame's totals when the round is DECIDED, dropped if the
@@ -134,10 +135,17 @@ static __device__ __forceinline__ bool run_block(Orbit &o, uint32_t &it, bool bu
     return ended || it >= max_iter;
 }
 
-/* ---- one sample per pixel: independent orbits ------------------------------------------------ */
-template <class Real, class FractalT, bool kProbe>
+/* ---- independent orbits ---------------------------------------------------------------------- */
+/* kMode 0: one sample per pixel, the frame's only launch.  1: pass A, sample 0 of every pixel.  2: pass C, the rounds
+ * pass B exported -- a work item is (exported tile, round), handed out exactly like a tile. */
+static __device__ __forceinline__ uint32_t *export_et(const chaos_render_args &a, uint32_t e, uint32_t round)
+{
+    return a.exp.et + ((size_t)e * CHAOS_EXPORT_ROUNDS + round) * 32u;
+}
+template <class Real, class FractalT, int kMode>
 static __device__ void render_main_independent(const chaos_render_args &a)
 {
+    constexpr bool kProbe = kMode == 1, kExport = kMode == 2;
     typedef typename FractalT::template Orbit<Real> Orbit;
     frame_map<Real> fm;
     fm.init(a);
@@ -147,12 +155,17 @@ static __device__ void render_main_independent(const chaos_render_args &a)
     const orbit_ctx ctx = {a.max_iter, a.shortcuts};
     Real dx0, dy0;
     sample_delta<Real>(0u, 0.f, dx0, dy0);                  /* sample 0 sits at offset 0/3 */
+    const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
+    const float spr = sqrtf(__fadd_rn(a.max_ss, -2.0f));
+    const uint32_t rounds_per_tile = kExport ? S0 - 2u : 1u;                 /* pass C: rounds 2 .. S0-1 */
+    const uint32_t n_items = kExport ? min(a.counters->n_exported, a.exp.capacity) * rounds_per_tile : a.n_tiles;
+    unsigned int *cursor = kExport ? &a.counters->next_export_item : &a.counters->next_tile;
 
     Orbit o;
-    uint32_t it = 0, px = 0, py = 0, tile = 0;
+    uint32_t it = 0, px = 0, py = 0, tile = 0, rnd = 0;      /* pass C: tile = export index, px = pixel within the tile */
     bool busy = false, fin = false;                          /* fin: the orbit is over and waits to be retired */
     bool first = true, queue_empty = false, tested = true;
-    uint32_t pend = 0, x0 = 0, y0 = 0, cur_tile = 0;         /* warp-uniform: the tile being handed out */
+    uint32_t pend = 0, x0 = 0, y0 = 0, cur_tile = 0, cur_round = 0;   /* warp-uniform: the tile being handed out */
     uint32_t waited = 0;
     unsigned long long iters = 0, nsamples = 0, skipped = 0;
 
@@ -167,11 +180,15 @@ static __device__ void render_main_independent(const chaos_render_args &a)
             iters += it;
             skipped += o.skipped();
             nsamples += 1;
-            if (kProbe) { /* pass A: park the escape time in the record for pass B, fold the trip count into the tile's statistics */
+            if (kExport) {   /* pass C: the escape time waits for pass D; the work is counted when pass D knows the round existed */
+                export_et(a, tile, rnd)[px] = et;
+                atomicAdd(&a.exp.iters[(size_t)tile * CHAOS_EXPORT_ROUNDS + rnd], (unsigned long long)it);
+                if (o.skipped()) atomicAdd(&a.exp.skipped[(size_t)tile * CHAOS_EXPORT_ROUNDS + rnd], (unsigned long long)o.skipped());
+            } else if (kProbe) { /* pass A: park the escape time in the record for pass B, fold the trip count into the tile's statistics */
                 store_record(record_at(a.out, a.out_pitch, px, py), __uint_as_float(et), __uint_as_float(it), 0u, 0.f);
                 atomicMax(&a.tile_tmax[tile], it);
                 atomicMin(&a.tile_tmin[tile], it);
-                atomicMax(&a.tile_key[tile], it - o.skipped());   /* what the orbit COST: a proven never-ending orbit is cheap */
+                atomicAdd(&a.tile_key[tile], min(it - o.skipped(), 1u << 26));   /* what the tile's orbits COST (a proven never-ending orbit is cheap) */
             }
             else          /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
                 store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
@@ -183,11 +200,18 @@ static __device__ void render_main_independent(const chaos_render_args &a)
             if (!pend) {
                 if (queue_empty) break;
                 uint32_t t = 0;
-                if (lane == 0) t = atomicAdd(&a.counters->next_tile, 1u);
+                if (lane == 0) t = atomicAdd(cursor, 1u);
                 t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
-                if (t >= a.n_tiles) { queue_empty = true; break; }
-                cur_tile = t;
-                tile_origin(a, t, x0, y0);
+                if (t >= n_items) { queue_empty = true; break; }
+                if (kExport) {
+                    cur_tile = t / rounds_per_tile;                       /* export index */
+                    cur_round = 2u + (t - cur_tile * rounds_per_tile);
+                    if (cur_round < a.exp.first[cur_tile]) continue;      /* pass B had taken this round already */
+                    tile_origin(a, a.exp.tile[cur_tile], x0, y0);
+                } else {
+                    cur_tile = t;
+                    tile_origin(a, t, x0, y0);
+                }
                 pend = __ballot_sync(CHAOS_FULL_MASK, (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height);
             }
             uint32_t rank = __popc(idle & lanemask_lt());
@@ -195,11 +219,19 @@ static __device__ void render_main_independent(const chaos_render_args &a)
             uint32_t mypix = 0;
             if (take) {
                 mypix = (pend == CHAOS_FULL_MASK && idle == CHAOS_FULL_MASK) ? lane : nth_set_bit(pend, rank);
-                px = x0 + (mypix & 7u);
-                py = y0 + (mypix >> 3);
                 tile = cur_tile;
                 Real cx, cy;
-                fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx0, dy0, cx, cy);
+                if (kExport) {
+                    Real dx, dy;
+                    sample_delta<Real>(cur_round, spr, dx, dy);
+                    fm.template plane_point<fused_plane_y<FractalT>::value>(x0 + (mypix & 7u), y0 + (mypix >> 3), dx, dy, cx, cy);
+                    px = mypix;
+                    rnd = cur_round;
+                } else {
+                    px = x0 + (mypix & 7u);
+                    py = y0 + (mypix >> 3);
+                    fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx0, dy0, cx, cy);
+                }
                 o.start(cx, cy, ctx);
                 it = 0;
                 busy = true;
@@ -210,7 +242,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
         tested = __any_sync(CHAOS_FULL_MASK, tested);
         if (!__any_sync(CHAOS_FULL_MASK, busy)) break;
     }
-    flush_counters(a, iters, nsamples, skipped);
+    if (!kExport) flush_counters(a, iters, nsamples, skipped);
 }
 
 /* ---- general case: sample rounds with tile-wide votes ----------------------------------------- */
@@ -234,9 +266,10 @@ static __device__ __forceinline__ uint32_t next_decision_round(bool adaptive, ui
  * only the tile's critical path does (one orbit instead of up to S sequential ones), and more orbits are pending per
  * warp to keep the lanes filled.
  */
-template <class Real, class FractalT, bool kResume>
+template <class Real, class FractalT>
 static __device__ void render_main_rounds(const chaos_render_args &a, refill_warp_store &ws)
 {
+    constexpr bool kResume = true;      /* sample 0 of every pixel was taken by pass A */
     typedef typename FractalT::template Orbit<Real> Orbit;
     constexpr int K = CHAOS_REFILL_SLOTS;
     constexpr uint32_t R = CHAOS_OVERLAP_ROUNDS;
@@ -260,14 +293,19 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
     bool first = true, queue_empty = false, tested = true;
     uint32_t waited = 0;
     unsigned long long iters = 0, nsamples = 0, skipped = 0;   /* lane 0 carries the warp's totals */
+    /* diagnostics (args.warp_trace): when the warp started, saw the queue run dry, and ended; what it did */
+    unsigned long long tr_start = 0, tr_dry = 0, tr_blocks = 0, tr_passes = 0, tr_tiles = 0, tr_lane_blocks = 0;
+    if (a.warp_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
 
     for (;;) {
         /* (1) iterate: one block of trips for the orbit this lane holds */
+        if (a.warp_trace) { tr_blocks += 1; tr_lane_blocks += __popc(__ballot_sync(CHAOS_FULL_MASK, busy && !fin)); }
         fin |= run_block(o, it, busy && !fin, tested, nb, max_iter);
         tested = __any_sync(CHAOS_FULL_MASK, busy && !fin && o.wants_tested());
         if (!take_scheduling_pass(fin, busy, a.sched_idle_lanes_rounds, waited) && !first) continue;
         first = false;
 
+        if (a.warp_trace) tr_passes += 1;
         /* (2) retire finished orbits into their slot (:125-127) */
         const uint32_t touched = __reduce_or_sync(CHAOS_FULL_MASK, fin ? (1u << slot) : 0u);   /* slots that got a result */
         if (fin) {
@@ -317,6 +355,28 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                      * mean is 0 (all its samples 0: inside the set for modules that report 0 there) vetoes at every i */
                     blocked = __any_sync(CHAOS_FULL_MASK, p.zero_mean && part) || (i >= 2u && !all_le);
                 }
+                /* A tile that looks set to use its whole budget leaves here: pass C runs its remaining rounds as independent
+                 * orbits of one GPU-wide pool (a tile of 32 never-ending pixels is 7 x 32 full-length orbits -- seven waves
+                 * of this warp's lanes, the whole launch's critical path when it stays here), pass D replays the decisions. */
+                uint32_t e = 0xffffffffu;
+                if (kResume && i + 1u < S && blocked && S <= CHAOS_EXPORT_ROUNDS && issued == i + 1u && i >= 1u && a.exp.capacity) {
+                    if (lane == 0) e = atomicAdd(&a.counters->n_exported, 1u);
+                    e = __shfl_sync(CHAOS_FULL_MASK, e, 0);
+                    if (e >= a.exp.capacity) e = 0xffffffffu;
+                }
+                if (e != 0xffffffffu) {
+                    for (uint32_t q = 0; q <= i; ++q) export_et(a, e, q)[lane] = part ? ws.et[k][q][lane] : 0u;
+                    if (lane == 0) { a.exp.tile[e] = hk.tile; a.exp.first[e] = i + 1u; }
+                    if (lane >= i + 1u && lane < CHAOS_EXPORT_ROUNDS) {
+                        a.exp.iters[(size_t)e * CHAOS_EXPORT_ROUNDS + lane] = 0ull;
+                        a.exp.skipped[(size_t)e * CHAOS_EXPORT_ROUNDS + lane] = 0ull;
+                    }
+                    __syncwarp();
+                    if (lane < sizeof(refill_slot_hdr) / 4u) reinterpret_cast<uint32_t *>(&ws.hdr[k])[lane] = 0u;
+                    for (uint32_t w = 32u + lane; w < sizeof(refill_slot_hdr) / 4u; w += 32u) reinterpret_cast<uint32_t *>(&ws.hdr[k])[w] = 0u;
+                    __syncwarp();
+                    break;
+                }
                 if (i + 1u < S) {
                     /* rounds certain to run, then rounds ahead of their turn; a round >= R only when it is the next one */
                     uint32_t upto = min(next_decision_round(adaptive, i, S) + 1u, S);
@@ -353,14 +413,24 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
             if (!ws.hdr[k].active && !queue_empty) {
                 uint32_t t = 0;
                 if (lane == 0) {
-                    t = atomicAdd(kResume ? &a.counters->next_tile_b : &a.counters->next_tile, 1u);
-                    if (kResume && t < a.n_tiles) t = a.tile_order[t];      /* longest expected first */
-                    else if (kResume) t = 0xffffffffu;
+                    if (kResume) {
+                        /* tile_order runs from the most to the least expensive tile.  Slot 0 draws from the expensive end,
+                         * the other slots from the cheap end: a warp then works on ONE heavy tile at a time (up to 7 x 32
+                         * full-length orbits: seven waves of its 32 lanes) next to light ones, instead of four heavy tiles
+                         * at once while other warps run dry -- measured on c2: SM busy time 3.9 .. 8.1 Mcycles before. */
+                        if (atomicAdd(&a.counters->claimed_b, 1u) >= a.n_tiles) t = 0xffffffffu;
+                        else if (k == 0) t = a.tile_order[atomicAdd(&a.counters->next_tile_b, 1u)];
+                        else t = a.tile_order[a.n_tiles - 1u - atomicAdd(&a.counters->tail_tile_b, 1u)];
+                    } else {
+                        t = atomicAdd(&a.counters->next_tile, 1u);
+                    }
                 }
                 t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
                 if (t >= a.n_tiles) {
                     queue_empty = true;
+                    if (a.warp_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_dry));
                 } else {
+                    tr_tiles += 1;
                     uint32_t x0, y0;
                     tile_origin(a, t, x0, y0);
                     const bool in = (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height;
@@ -377,7 +447,7 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                     }
                     if (lane == 0) {
                         refill_slot_hdr &h = ws.hdr[k];
-                        h.x0 = x0; h.y0 = y0; h.S = S0; h.dec = first_round; h.issued = min(upto, max(S0, first_round + 1u)); h.inb = inb;
+                        h.tile = t; h.x0 = x0; h.y0 = y0; h.S = S0; h.dec = first_round; h.issued = min(upto, max(S0, first_round + 1u)); h.inb = inb;
                         uint32_t rm = 0u;
                         for (uint32_t r = first_round; r < h.issued; ++r) {
                             h.pend[r % R] = inb;
@@ -433,21 +503,75 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
         /* (5) nothing running after a full scheduling pass = no tile left anywhere for this warp */
         if (!__any_sync(CHAOS_FULL_MASK, busy)) break;
     }
+    if (a.warp_trace && lane == 0) {
+        unsigned long long tr_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_end));
+        unsigned long long *w = a.warp_trace + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8u;
+        w[0] = tr_start; w[1] = tr_dry; w[2] = tr_end; w[3] = tr_blocks; w[4] = tr_passes; w[5] = tr_tiles; w[6] = tr_lane_blocks; w[7] = nsamples;
+    }
     flush_counters(a, iters, nsamples, skipped);
 }
 
+/* pass B as a kernel body: one slot store per warp in dynamic shared memory */
 template <class Real, class FractalT>
-static __device__ __forceinline__ void render_main_refill(const chaos_render_args &a)
+static __device__ __forceinline__ void render_pass_b(const chaos_render_args &a)
 {
     extern __shared__ __align__(16) unsigned char chaos_dyn_smem[];
-    const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
     refill_warp_store *stores = reinterpret_cast<refill_warp_store *>(chaos_dyn_smem);
-    if (S0 <= 1u) render_main_independent<Real, FractalT, false>(a);
-    else if (a.phase == 1u) render_main_independent<Real, FractalT, true>(a);
-    else if (a.phase == 2u) render_main_rounds<Real, FractalT, true>(a, stores[threadIdx.x >> 5]);
-    else render_main_rounds<Real, FractalT, false>(a, stores[threadIdx.x >> 5]);
+    render_main_rounds<Real, FractalT>(a, stores[threadIdx.x >> 5]);
 }
 
+/* ---- pass D: the decisions of an exported tile, replayed over its stored rounds (:128-150) ----------------- */
+static __device__ void replay_exported(const chaos_render_args &a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = min(a.counters->n_exported, a.exp.capacity);
+    const bool adaptive = (a.flags & CHAOS_FLAG_ADAPTIVE_SS) != 0u;
+    const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long iters = 0, nsamples = 0, skipped = 0;   /* lane 0 carries the warp's totals */
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += warps) {
+        uint32_t x0, y0;
+        tile_origin(a, a.exp.tile[e], x0, y0);
+        const uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
+        const bool part = px < a.width && py < a.height;
+        const uint32_t n_part = __popc(__ballot_sync(CHAOS_FULL_MASK, part));
+        const uint32_t first = a.exp.first[e];
+        float sm[CHAOS_ADAPTIVE_THRESHOLD];
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < CHAOS_ADAPTIVE_THRESHOLD; ++q) {
+            const uint32_t v = (part && q < S0) ? export_et(a, e, q)[lane] : 0u;
+            sm[q] = __uint2float_rn(v);
+            if (q < first) sum += v;
+        }
+        uint32_t S = S0;
+        for (uint32_t i = first; ; ++i) {
+            sum += part ? export_et(a, e, i)[lane] : 0u;
+            if (lane == 0) {
+                iters += a.exp.iters[(size_t)e * CHAOS_EXPORT_ROUNDS + i];
+                skipped += a.exp.skipped[(size_t)e * CHAOS_EXPORT_ROUNDS + i];
+                nsamples += n_part;
+            }
+            if (decision_entered(adaptive, i, S)) {
+                vote_preds p = {true, true, true, false};
+                if (part) {
+                    float sq[CHAOS_ADAPTIVE_THRESHOLD];
+#pragma unroll
+                    for (uint32_t q = 0; q < CHAOS_ADAPTIVE_THRESHOLD; ++q) sq[q] = (q <= i) ? sm[q] : 0.f;
+                    p = decision_preds(sq, i, sum);
+                }
+                const bool all_eq = __all_sync(CHAOS_FULL_MASK, p.eq);
+                const bool all_lt = __all_sync(CHAOS_FULL_MASK, p.lt);
+                const bool all_le = __all_sync(CHAOS_FULL_MASK, p.le);
+                S = decision_update(i, S, all_eq, all_lt, all_le);
+            }
+            if (i + 1u >= S) break;
+        }
+        if (part) store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(sum / S), __uint2float_rn(S), 0u, 0.f);
+    }
+    flush_counters(a, iters, nsamples, skipped);
+}
 
 /* ---- cost classes between the two passes ------------------------------------------------------ */
 /* Expected critical path of a tile's remaining rounds from pass A's trip counts (tile_tmax/tile_tmin, and the longest
@@ -467,10 +591,10 @@ static __device__ void classify_tiles(const chaos_render_args &a)
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_tiles; t += gridDim.x * blockDim.x) {
         const uint32_t own_max = a.tile_tmax[t], own_min = a.tile_tmin[t];
-        const uint32_t nmax = a.tile_key[t];          /* pass A left the longest EXECUTED orbit here; replaced by the class below */
+        const uint32_t cost = a.tile_key[t];          /* pass A left the trips it EXECUTED in the tile here; replaced by the class below */
         const bool uniform = own_max == own_min;
-        const unsigned long long est = (unsigned long long)(nmax | 1u) * (uniform ? 1u : (S0 > 1u ? S0 - 1u : 1u));
-        const uint32_t key = (uint32_t)__clzll((long long)est) - 27u;      /* est < 2^37: clzll in [27,63] -> key in [0,36] */
+        const unsigned long long est = (unsigned long long)(cost | 1u) * (uniform ? 1u : (S0 > 1u ? S0 - 1u : 1u));
+        const uint32_t key = (uint32_t)__clzll((long long)est) - 27u;      /* est < 2^37 (cost <= 32 x 2^26): clzll in [27,63] -> key in [0,36] */
         a.tile_key[t] = key;
         atomicAdd(&hist[key], 1u);
     }

@@ -46,7 +46,7 @@ def test_main_matches_oracle(cu, provider, engine, case):
     st = r.stats()
     assert st.pixel_iterations == want.pixel_iterations
     assert st.samples == want.samples
-    assert st.kernel_launches in (2, 5)
+    assert st.kernel_launches in (2, 5, 7)   # one launch, or passes A, classify, order, B (, C, D); + compose
     # compose: palette lookup must be identical
     pal = cu.createDefaultColorPalette()
     assert (r.outputRGBA() == oracle.compose(case["fractal"], want.records, pal, case["maxSS"])).all()
