@@ -308,7 +308,7 @@ struct chaos_renderer {
     uint32_t export_enabled = 1;
     CUfunction k_reuse_f = nullptr, k_reuse_d = nullptr;           /* pass R of a fast frame */
     int blocks_reuse_f = 0, blocks_reuse_d = 0;
-    CUdeviceptr tile_key = 0, tile_order = 0, tile_tmax = 0, tile_tmin = 0;
+    CUdeviceptr tile_key = 0, tile_order = 0;
     CUdeviceptr warp_trace = 0;         /* diagnostics, CHAOS_WARP_TRACE=<file>: per-warp timeline of pass B */
     uint32_t sync_below_iters = 2048;   /* see render_quality_locked */
     int blocks_main_f_sync = 0, blocks_main_d_sync = 0;
@@ -337,7 +337,7 @@ struct chaos_renderer {
     uint32_t engine = 1;           /* 1 = lane-refill scheduler (default), 0 = tile-synchronous */
     uint32_t block_iters = 0;      /* 0 = choose from maxIterations */
     uint32_t shortcuts = CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE;   /* count-preserving shortcuts of the escape loop */
-    uint32_t sched_idle_indep = 6, sched_idle_rounds = 8;   /* see take_scheduling_pass (render_refill.cuh) */
+    uint32_t sched_idle_indep = 6, sched_idle_rounds = 16;   /* see take_scheduling_pass (render_refill.cuh) */
 };
 
 static chaos_status check_renderer(const chaos_renderer *r)
@@ -594,8 +594,6 @@ static void free_frame_memory(chaos_renderer *r)
     if (r->palette) { D->p_cuMemFree(r->palette); r->palette = 0; }
     if (r->tile_key) { D->p_cuMemFree(r->tile_key); r->tile_key = 0; }
     if (r->tile_order) { D->p_cuMemFree(r->tile_order); r->tile_order = 0; }
-    if (r->tile_tmax) { D->p_cuMemFree(r->tile_tmax); r->tile_tmax = 0; }
-    if (r->tile_tmin) { D->p_cuMemFree(r->tile_tmin); r->tile_tmin = 0; }
     free_export(r);
     if (r->rgba_host) { D->p_cuMemFreeHost(r->rgba_host); r->rgba_host = nullptr; r->rgba_dev = 0; }
     if (r->rgba_dev) { D->p_cuMemFree(r->rgba_dev); r->rgba_dev = 0; }
@@ -624,8 +622,6 @@ extern "C" chaos_status chaos_initialize(chaos_renderer *r, uint32_t width, uint
     const size_t all_tiles = (size_t)((width + 7u) / 8u) * ((height + 3u) / 4u);
     CUresult e = D->p_cuMemAlloc(&r->tile_key, all_tiles * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->tile_order, all_tiles * 4u);
-    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->tile_tmax, all_tiles * 4u);
-    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->tile_tmin, all_tiles * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->palette, (size_t)palette_len * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemcpyHtoD(r->palette, palette_rgba, (size_t)palette_len * 4u);
     size_t frame_bytes = (size_t)width * height * 4u;
@@ -812,8 +808,6 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
             owned_rows += std::min(a->band_tile_rows, a->tile_rows - b * a->band_tile_rows);
     }
     a->n_tiles = owned_rows * a->tiles_x;
-    a->tile_tmax = (uint32_t *)r->tile_tmax;
-    a->tile_tmin = (uint32_t *)r->tile_tmin;
     a->tile_key = (uint32_t *)r->tile_key;
     a->tile_order = (uint32_t *)r->tile_order;
     a->engine = r->engine;
@@ -924,14 +918,11 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
              * except those of tiles set to use their whole budget -> pass C (independent orbits) + pass D (their decisions) */
             const int cap = r->provider->sm_count * 4;
             const int small_grid = (int)std::min<uint64_t>((a.n_tiles + 255u) / 256u, (uint64_t)cap);
-            CUresult em = D->p_cuMemsetD32Async(r->tile_tmax, 0u, a.n_tiles, r->stream);
-            if (em == CUDA_SUCCESS) em = D->p_cuMemsetD32Async(r->tile_tmin, 0xffffffffu, a.n_tiles, r->stream);
-            if (em == CUDA_SUCCESS) em = D->p_cuMemsetD32Async(r->tile_key, 0u, a.n_tiles, r->stream);
-            if (em != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed: %s", cu_err_name(em));
             if (r->export_enabled && S0 >= 3u && S0 <= CHAOS_EXPORT_ROUNDS && ensure_export(r, a.n_tiles)) a.exp = r->exp_buf;
             a.phase = 1u;
             st = launch(r, r->k_pass_a[p], r->blocks_pass_a[p], 256, 0, &a);
-            if (st == CHAOS_OK) st = launch(r, r->k_classify, small_grid, 256, 0, &a);
+            const int tile_grid = (int)std::min<uint64_t>((a.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);   /* one warp per tile */
+            if (st == CHAOS_OK) st = launch(r, r->k_classify, tile_grid, 256, 0, &a);
             if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &a);
             a.phase = 2u;
             const char *trace_path = getenv("CHAOS_WARP_TRACE");

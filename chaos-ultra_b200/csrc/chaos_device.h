@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 14u
+#define CHAOS_MODULE_ABI 15u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -83,8 +83,6 @@ struct chaos_render_args {
     /* multi-GPU row-band partition: this launch covers bands b with b % part_count == part_index */
     uint32_t part_index, part_count, band_tile_rows;
     uint32_t n_tiles;       /* vote tiles owned by this launch */
-    uint32_t *tile_tmax;    /* [n_tiles] longest orbit of the tile in pass A (atomicMax by the retiring lanes) */
-    uint32_t *tile_tmin;    /* [n_tiles] shortest one (atomicMin) */
     uint32_t *tile_key;     /* [n_tiles] cost class of each tile after pass A */
     uint32_t *tile_order;   /* [n_tiles] tiles sorted by descending expected cost: the order pass B takes them in */
     uint32_t phase;         /* 0 = whole render in one launch; 1 = pass A (sample 0 of every pixel); 2 = pass B (the rest);

@@ -184,11 +184,9 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                 export_et(a, tile, rnd)[px] = et;
                 atomicAdd(&a.exp.iters[(size_t)tile * CHAOS_EXPORT_ROUNDS + rnd], (unsigned long long)it);
                 if (o.skipped()) atomicAdd(&a.exp.skipped[(size_t)tile * CHAOS_EXPORT_ROUNDS + rnd], (unsigned long long)o.skipped());
-            } else if (kProbe) { /* pass A: park the escape time in the record for pass B, fold the trip count into the tile's statistics */
-                store_record(record_at(a.out, a.out_pitch, px, py), __uint_as_float(et), __uint_as_float(it), 0u, 0.f);
-                atomicMax(&a.tile_tmax[tile], it);
-                atomicMin(&a.tile_tmin[tile], it);
-                atomicAdd(&a.tile_key[tile], min(it - o.skipped(), 1u << 26));   /* what the tile's orbits COST (a proven never-ending orbit is cheap) */
+            } else if (kProbe) { /* pass A: park the escape time in the record for pass B, with the orbit's trip count and what it
+                                  * cost (a proven never-ending orbit is cheap) for chaosClassifyTiles */
+                store_record(record_at(a.out, a.out_pitch, px, py), __uint_as_float(et), __uint_as_float(it), 0u, __uint_as_float(it - o.skipped()));
             }
             else          /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
                 store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
@@ -574,9 +572,10 @@ static __device__ void replay_exported(const chaos_render_args &a)
 }
 
 /* ---- cost classes between the two passes ------------------------------------------------------ */
-/* Expected critical path of a tile's remaining rounds from pass A's trip counts (tile_tmax/tile_tmin, and the longest
- * executed orbit in tile_key -- with exact recurrence a never-ending orbit may have cost a few hundred trips or all of
- * maxIterations, and only the latter kind makes a tile expensive):
+/* Expected cost of a tile's remaining rounds from what pass A left in its records: do the pixels' trip counts agree
+ * (then the i == 1 vote will most likely end the tile after one more round), and how many trips did pass A EXECUTE in
+ * the tile (with exact recurrence a never-ending orbit may have cost a few hundred trips or all of maxIterations, and
+ * only the latter kind makes a tile expensive):
  *   longest orbit x (S0 - 1) rounds if the pixels disagree (the tile will probably use its whole sample budget),
  *   x 1 if all agree (the i == 1 vote will most likely end it after one more round).
  * (Also ranking a tile by its 8 neighbours' longest orbit -- to catch boundary tiles whose own sample-0 orbits all
@@ -588,15 +587,29 @@ static __device__ void classify_tiles(const chaos_render_args &a)
     __shared__ uint32_t hist[CHAOS_COST_BUCKETS];
     for (uint32_t k = threadIdx.x; k < CHAOS_COST_BUCKETS; k += blockDim.x) hist[k] = 0u;
     __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_tiles; t += gridDim.x * blockDim.x) {
-        const uint32_t own_max = a.tile_tmax[t], own_min = a.tile_tmin[t];
-        const uint32_t cost = a.tile_key[t];          /* pass A left the trips it EXECUTED in the tile here; replaced by the class below */
-        const bool uniform = own_max == own_min;
-        const unsigned long long est = (unsigned long long)(cost | 1u) * (uniform ? 1u : (S0 > 1u ? S0 - 1u : 1u));
-        const uint32_t key = (uint32_t)__clzll((long long)est) - 27u;      /* est < 2^37 (cost <= 32 x 2^26): clzll in [27,63] -> key in [0,36] */
-        a.tile_key[t] = key;
-        atomicAdd(&hist[key], 1u);
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < a.n_tiles; t += warps) {   /* one warp per tile, lane = pixel */
+        uint32_t x0, y0;
+        tile_origin(a, t, x0, y0);
+        const uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
+        const bool part = px < a.width && py < a.height;
+        uint32_t trips = 0, cost = 0;
+        if (part) {
+            const float4 rec = *reinterpret_cast<const float4 *>(record_at(a.out, a.out_pitch, px, py));   /* pass A: (et, trips, -, cost) */
+            trips = __float_as_uint(rec.y);
+            cost = min(__float_as_uint(rec.w), 1u << 26);
+        }
+        const uint32_t first = __shfl_sync(CHAOS_FULL_MASK, trips, __ffs(__ballot_sync(CHAOS_FULL_MASK, part)) - 1);
+        const bool uniform = __all_sync(CHAOS_FULL_MASK, !part || trips == first);
+        const uint32_t total = __reduce_add_sync(CHAOS_FULL_MASK, cost);          /* <= 32 x 2^26 */
+        if (lane == 0) {
+            const unsigned long long est = (unsigned long long)(total | 1u) * (uniform ? 1u : (S0 > 1u ? S0 - 1u : 1u));
+            const uint32_t key = (uint32_t)__clzll((long long)est) - 27u;      /* est < 2^37: clzll in [27,63] -> key in [0,36] */
+            a.tile_key[t] = key;
+            atomicAdd(&hist[key], 1u);
+        }
     }
     __syncthreads();
     for (uint32_t k = threadIdx.x; k < CHAOS_COST_BUCKETS; k += blockDim.x)
