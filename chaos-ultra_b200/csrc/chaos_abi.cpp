@@ -304,7 +304,7 @@ struct chaos_renderer {
     CUfunction k_main_f_sync = nullptr, k_main_d_sync = nullptr;   /* engine 0 (differential check) */
     CUfunction k_classify = nullptr, k_order = nullptr;            /* between the two passes of engine 1 */
     CUfunction k_replay = nullptr;                                 /* pass D */
-    chaos_export exp_buf = {0, nullptr, nullptr, nullptr, nullptr, nullptr};   /* pass B -> pass C -> pass D (device memory) */
+    chaos_export exp_buf = {0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   /* pass B -> pass C -> pass D (device memory) */
     uint32_t export_enabled = 1;
     CUfunction k_reuse_f = nullptr, k_reuse_d = nullptr;           /* pass R of a fast frame */
     int blocks_reuse_f = 0, blocks_reuse_d = 0;
@@ -331,7 +331,10 @@ struct chaos_renderer {
     CUdeviceptr counters = 0;
     chaos_counters *counters_host = nullptr; /* pinned staging for the read-back */
     CUstream stream = nullptr;
-    CUevent ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   /* render start/end, compose start/end, pass boundary */
+    CUevent ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   /* render start/end, compose start/end, pass boundary,
+                                                                    * pass B done, early compose start/end (stream2) */
+    CUstream stream2 = nullptr;    /* the frame-wide compose of a multi-pass render runs here, next to passes C and D */
+    uint32_t overlap_compose = 1;
     uint32_t part_index = 0, part_count = 1, band_rows = 64;
     chaos_stats stats;
     uint32_t engine = 1;           /* 1 = lane-refill scheduler (default), 0 = tile-synchronous */
@@ -451,6 +454,7 @@ static chaos_status load_module(chaos_renderer *r)
         {"chaosPassCFloat", &r->k_pass_c[0]}, {"chaosPassCDouble", &r->k_pass_c[1]},
         {"fractalRenderAdvancedFloat", &r->k_adv_f}, {"fractalRenderAdvancedDouble", &r->k_adv_d},
         {"fractalRenderUnderSampled", &r->k_undersampled}, {"compose", &r->k_compose}, {"debug", &r->k_debug},
+
         {"fractalRenderMainFloatSync", &r->k_main_f_sync}, {"fractalRenderMainDoubleSync", &r->k_main_d_sync},
         {"chaosClassifyTiles", &r->k_classify}, {"chaosOrderTiles", &r->k_order}, {"chaosReplayExported", &r->k_replay},
         {"chaosReusePassFloat", &r->k_reuse_f}, {"chaosReusePassDouble", &r->k_reuse_d},
@@ -531,6 +535,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
         unsigned x = 0, y = 0;
         if (sscanf(si, "%u,%u", &x, &y) == 2 && x >= 1 && y >= 1) { r->sched_idle_indep = x; r->sched_idle_rounds = y; }
     }
+    const char *oc = getenv("CHAOS_OVERLAP_COMPOSE");   /* 0 = compose only after the last render pass */
+    if (oc) r->overlap_compose = (uint32_t)atoi(oc) ? 1u : 0u;
     const char *ex = getenv("CHAOS_EXPORT");      /* 0 = every tile keeps all its rounds in pass B */
     if (ex) r->export_enabled = (uint32_t)atoi(ex) ? 1u : 0u;
     const char *sc = getenv("CHAOS_SHORTCUTS");   /* 0 = every trip executed and tested, as the reference does */
@@ -538,7 +544,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     chaos_status st = load_module(r);
     if (st != CHAOS_OK) { delete r; return st; }
     CUresult e = D->p_cuStreamCreate(&r->stream, CU_STREAM_NON_BLOCKING);
-    for (int i = 0; i < 5 && e == CUDA_SUCCESS; ++i) e = D->p_cuEventCreate(&r->ev[i], CU_EVENT_DEFAULT);
+    if (e == CUDA_SUCCESS) e = D->p_cuStreamCreate(&r->stream2, CU_STREAM_NON_BLOCKING);
+    for (int i = 0; i < 8 && e == CUDA_SUCCESS; ++i) e = D->p_cuEventCreate(&r->ev[i], CU_EVENT_DEFAULT);
     if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->counters, sizeof(chaos_counters));
     if (e == CUDA_SUCCESS) e = D->p_cuMemHostAlloc((void **)&r->counters_host, sizeof(chaos_counters), 0);
     if (e != CUDA_SUCCESS) {
@@ -563,7 +570,8 @@ static void free_export(chaos_renderer *r)
     if (x.et) D->p_cuMemFree((CUdeviceptr)x.et);
     if (x.iters) D->p_cuMemFree((CUdeviceptr)x.iters);
     if (x.skipped) D->p_cuMemFree((CUdeviceptr)x.skipped);
-    x = chaos_export{0, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (x.bitmap) D->p_cuMemFree((CUdeviceptr)x.bitmap);
+    x = chaos_export{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 }
 
 /* arrays for the tiles pass B hands to pass C; allocated by the first multi-sample render of a frame size */
@@ -573,10 +581,12 @@ static bool ensure_export(chaos_renderer *r, uint32_t n_tiles)
     if (x.capacity >= n_tiles) return true;
     D->p_cuStreamSynchronize(r->stream);
     free_export(r);
-    CUdeviceptr p[5] = {0, 0, 0, 0, 0};
-    const size_t bytes[5] = {(size_t)n_tiles * 4u, (size_t)n_tiles * 4u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 32u * 4u,
-                             (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u};
-    for (int i = 0; i < 5; ++i) {
+    const size_t frame_tiles = (size_t)((r->width + 7u) / 8u) * ((r->height + 3u) / 4u);
+    CUdeviceptr p[6] = {0, 0, 0, 0, 0, 0};
+    const size_t bytes[6] = {(size_t)n_tiles * 4u, (size_t)n_tiles * 4u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 32u * 4u,
+                             (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u,
+                             ((frame_tiles + 31u) / 32u) * 4u};
+    for (int i = 0; i < 6; ++i) {
         if (D->p_cuMemAlloc(&p[i], bytes[i]) != CUDA_SUCCESS) {
             for (int j = 0; j < i; ++j) D->p_cuMemFree(p[j]);
             return false;
@@ -584,7 +594,7 @@ static bool ensure_export(chaos_renderer *r, uint32_t n_tiles)
     }
     x.capacity = n_tiles;
     x.tile = (uint32_t *)p[0]; x.first = (uint32_t *)p[1]; x.et = (uint32_t *)p[2];
-    x.iters = (unsigned long long *)p[3]; x.skipped = (unsigned long long *)p[4];
+    x.iters = (unsigned long long *)p[3]; x.skipped = (unsigned long long *)p[4]; x.bitmap = (uint32_t *)p[5];
     return true;
 }
 
@@ -664,7 +674,8 @@ extern "C" chaos_status chaos_close(chaos_renderer *r)
     free_frame_memory(r);
     if (r->counters) D->p_cuMemFree(r->counters);
     if (r->counters_host) D->p_cuMemFreeHost(r->counters_host);
-    for (int i = 0; i < 5; ++i) if (r->ev[i]) D->p_cuEventDestroy(r->ev[i]);
+    for (int i = 0; i < 8; ++i) if (r->ev[i]) D->p_cuEventDestroy(r->ev[i]);
+    if (r->stream2) { D->p_cuStreamSynchronize(r->stream2); D->p_cuStreamDestroy(r->stream2); }
     if (r->stream) D->p_cuStreamDestroy(r->stream);
     unload_module(r);
     if (r->provider && r->provider->active == r) r->provider->active = nullptr;
@@ -819,10 +830,10 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
     a->sched_idle_lanes_rounds = r->sched_idle_rounds;
 }
 
-static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg)
+static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg, CUstream stream = nullptr)
 {
     void *params[1] = {arg};
-    CUresult e = D->p_cuLaunchKernel(fn, (unsigned)blocks, 1, 1, (unsigned)threads, 1, 1, smem, r->stream, params, nullptr);
+    CUresult e = D->p_cuLaunchKernel(fn, (unsigned)blocks, 1, 1, (unsigned)threads, 1, 1, smem, stream ? stream : r->stream, params, nullptr);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "Error just after launching a kernel:%s", cu_err_name(e));
     r->stats.kernel_launches += 1;
     r->stats.launches_total += 1;
@@ -830,9 +841,24 @@ static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int thr
 }
 
 /* launchDrawingKernel :275-364 without the GL map/unmap and surface objects */
-static chaos_status launch_compose(chaos_renderer *r, const chaos_params *m)
+static void fill_compose_args(chaos_renderer *r, const chaos_params *m, chaos_compose_args &c);
+
+/* only_tiles: compose just the tiles flagged there (the ones pass D finished after the frame-wide compose had started) */
+static chaos_status launch_compose(chaos_renderer *r, const chaos_params *m, CUstream stream = nullptr, const uint32_t *only_tiles = nullptr)
 {
     chaos_compose_args c;
+    fill_compose_args(r, m, c);
+    c.only_tiles = only_tiles;
+    c.tiles_x = (r->width + 7u) / 8u;
+    uint64_t quads = (uint64_t)((r->width + 3u) / 4u) * r->height;
+    int max_blocks = r->provider->sm_count * 8;
+    int blocks = (int)std::min<uint64_t>((quads + 255u) / 256u, (uint64_t)max_blocks);
+    if (blocks < 1) blocks = 1;
+    return launch(r, r->k_compose, blocks, 256, r->palette_len * 4u, &c, stream);
+}
+
+static void fill_compose_args(chaos_renderer *r, const chaos_params *m, chaos_compose_args &c)
+{
     memset(&c, 0, sizeof c);
     c.in = (const chaos_pixel_info *)r->buf[0].ptr;
     c.in_pitch = r->buf[0].pitch;
@@ -842,11 +868,6 @@ static chaos_status launch_compose(chaos_renderer *r, const chaos_params *m)
     c.width = r->width; c.height = r->height;
     c.max_ss = m->max_super_sampling;
     c.part_index = r->part_index; c.part_count = r->part_count; c.band_rows = r->band_rows;
-    uint64_t quads = (uint64_t)((r->width + 3u) / 4u) * r->height;
-    int max_blocks = r->provider->sm_count * 8;
-    int blocks = (int)std::min<uint64_t>((quads + 255u) / 256u, (uint64_t)max_blocks);
-    if (blocks < 1) blocks = 1;
-    return launch(r, r->k_compose, blocks, 256, r->palette_len * 4u, &c);
 }
 
 static chaos_status finish_frame(chaos_renderer *r)
@@ -901,6 +922,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters), r->stream);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
+    bool early_compose = false;
     if (a.n_tiles) {
         const int p = dbl ? 1 : 0;
         const uint32_t S0 = (uint32_t)std::min(64.0f, roundf(m->max_super_sampling));
@@ -918,7 +940,12 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
              * except those of tiles set to use their whole budget -> pass C (independent orbits) + pass D (their decisions) */
             const int cap = r->provider->sm_count * 4;
             const int small_grid = (int)std::min<uint64_t>((a.n_tiles + 255u) / 256u, (uint64_t)cap);
-            if (r->export_enabled && S0 >= 3u && S0 <= CHAOS_EXPORT_ROUNDS && ensure_export(r, a.n_tiles)) a.exp = r->exp_buf;
+            if (r->export_enabled && S0 >= 3u && S0 <= CHAOS_EXPORT_ROUNDS && ensure_export(r, a.n_tiles)) {
+                a.exp = r->exp_buf;
+                const size_t frame_tiles = (size_t)a.tiles_x * a.tile_rows;
+                if (D->p_cuMemsetD32Async((CUdeviceptr)a.exp.bitmap, 0u, (frame_tiles + 31u) / 32u, r->stream) != CUDA_SUCCESS)
+                    return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed");
+            }
             a.phase = 1u;
             st = launch(r, r->k_pass_a[p], r->blocks_pass_a[p], 256, 0, &a);
             const int tile_grid = (int)std::min<uint64_t>((a.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);   /* one warp per tile */
@@ -941,6 +968,15 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                 }
             }
             a.warp_trace = nullptr;
+            if (a.exp.capacity && r->overlap_compose && st == CHAOS_OK) {
+                /* every tile pass B did not export is final: stream the frame out now, next to passes C and D */
+                D->p_cuEventRecord(r->ev[5], r->stream);
+                D->p_cuStreamWaitEvent(r->stream2, r->ev[5], 0);
+                D->p_cuEventRecord(r->ev[6], r->stream2);
+                st = launch_compose(r, m, r->stream2);
+                D->p_cuEventRecord(r->ev[7], r->stream2);
+                early_compose = st == CHAOS_OK;
+            }
             if (a.exp.capacity) {
                 a.phase = 3u;
                 if (st == CHAOS_OK) st = launch(r, r->k_pass_c[p], r->blocks_pass_c[p], 256, 0, &a);
@@ -951,12 +987,18 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         if (st != CHAOS_OK) return st;
     }
     D->p_cuEventRecord(r->ev[1], r->stream);
+    if (early_compose) D->p_cuStreamWaitEvent(r->stream, r->ev[7], 0);
     D->p_cuEventRecord(r->ev[2], r->stream);
-    st = launch_compose(r, m);
+    st = early_compose ? launch_compose(r, m, nullptr, a.exp.bitmap) : launch_compose(r, m);
     if (st != CHAOS_OK) return st;
     D->p_cuEventRecord(r->ev[3], r->stream);
     st = finish_frame(r);
     if (st != CHAOS_OK) return st;
+    if (early_compose) {
+        float early = 0.f;
+        D->p_cuEventElapsedTime(&early, r->ev[6], r->ev[7]);
+        r->stats.compose_ms += early;
+    }
     r->last = *m; r->have_last = true;                             /* lastRendering = model.copy() */
     r->primary_dirty = false;
     m->sample_reuse_cache_dirty = 0;

@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 15u
+#define CHAOS_MODULE_ABI 17u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -60,6 +60,7 @@ struct chaos_export {
     uint32_t *et;                       /* [capacity][CHAOS_EXPORT_ROUNDS][32] escape time per round and pixel */
     unsigned long long *iters;          /* [capacity][CHAOS_EXPORT_ROUNDS] trips of the round's orbits (reference count) */
     unsigned long long *skipped;        /* [capacity][CHAOS_EXPORT_ROUNDS] of which proven, not executed */
+    uint32_t *bitmap;                   /* one bit per vote tile of the FRAME (row-major): set for exported tiles */
 };
 
 struct chaos_render_args {
@@ -106,6 +107,10 @@ struct chaos_compose_args {
     uint32_t width, height;
     float max_ss;
     uint32_t part_index, part_count, band_rows;
+    /* NULL, or one bit per vote tile of the frame (row-major, tiles_x per row): compose only the tiles whose bit is set
+     * (the ones pass D finished after the frame-wide compose had started) */
+    const uint32_t *only_tiles;
+    uint32_t tiles_x;
 };
 
 #endif

@@ -44,6 +44,7 @@
     X(cuStreamCreate)                           \
     X(cuStreamDestroy)                          \
     X(cuStreamSynchronize)                      \
+    X(cuStreamWaitEvent)                        \
     X(cuEventCreate)                            \
     X(cuEventRecord)                            \
     X(cuEventSynchronize)                       \

@@ -142,18 +142,23 @@ static __device__ __forceinline__ bool decision_entered(bool adaptive, uint32_t 
 }
 
 /* vote tile t of this launch -> pixel origin, honouring the row-band partition */
-static __device__ __forceinline__ void tile_origin(const chaos_render_args &a, uint32_t t, uint32_t &x0, uint32_t &y0)
+static __device__ __forceinline__ void tile_origin_of(uint32_t tiles_x, uint32_t part_index, uint32_t part_count, uint32_t band_tile_rows,
+                                                      uint32_t t, uint32_t &x0, uint32_t &y0)
 {
-    uint32_t row = t / a.tiles_x;
-    uint32_t col = t - row * a.tiles_x;
-    if (a.part_count > 1u) {
+    uint32_t row = t / tiles_x;
+    uint32_t col = t - row * tiles_x;
+    if (part_count > 1u) {
         /* local tile row -> global: bands of band_tile_rows rows are dealt round-robin */
-        uint32_t band_local = row / a.band_tile_rows;
-        uint32_t in_band = row - band_local * a.band_tile_rows;
-        row = (band_local * a.part_count + a.part_index) * a.band_tile_rows + in_band;
+        uint32_t band_local = row / band_tile_rows;
+        uint32_t in_band = row - band_local * band_tile_rows;
+        row = (band_local * part_count + part_index) * band_tile_rows + in_band;
     }
     x0 = col * 8u;
     y0 = row * 4u;
+}
+static __device__ __forceinline__ void tile_origin(const chaos_render_args &a, uint32_t t, uint32_t &x0, uint32_t &y0)
+{
+    tile_origin_of(a.tiles_x, a.part_index, a.part_count, a.band_tile_rows, t, x0, y0);
 }
 
 static __device__ __forceinline__ chaos_pixel_info *record_at(chaos_pixel_info *base, uint64_t pitch, uint32_t x, uint32_t y)
@@ -674,6 +679,10 @@ compose(const __grid_constant__ chaos_compose_args a)
         uint32_t y = (uint32_t)(q / quads_x);
         uint32_t x = (uint32_t)(q - (uint64_t)y * quads_x) << 2;
         if (a.part_count > 1u && ((y / a.band_rows) % a.part_count) != a.part_index) continue;
+        if (a.only_tiles) {      /* a quad of pixels lies within one 8x4 vote tile */
+            const uint32_t gt = (y >> 2) * a.tiles_x + (x >> 3);
+            if (!((a.only_tiles[gt >> 5] >> (gt & 31u)) & 1u)) continue;
+        }
         const float4 *src = reinterpret_cast<const float4 *>((const char *)a.in + (size_t)y * a.in_pitch) + x;
         uint32_t n = min(4u, a.width - x);
         float4 rec[4];

@@ -46,7 +46,7 @@ def test_main_matches_oracle(cu, provider, engine, case):
     st = r.stats()
     assert st.pixel_iterations == want.pixel_iterations
     assert st.samples == want.samples
-    assert st.kernel_launches in (2, 5, 7)   # one launch, or passes A, classify, order, B (, C, D); + compose
+    assert st.kernel_launches in (2, 5, 8)   # one launch + compose; or passes A, classify, order, B + compose; or A, classify, order, B, compose, C, D, composeTiles
     # compose: palette lookup must be identical
     pal = cu.createDefaultColorPalette()
     assert (r.outputRGBA() == oracle.compose(case["fractal"], want.records, pal, case["maxSS"])).all()
@@ -349,3 +349,44 @@ def test_shortcuts_in_fast_frames_change_nothing(cu, provider):
         helpers.assert_records_equal(a[0], b[0], "fast frame %d" % (f + 1))
         assert a[1] == b[1] and a[2] == b[2] and b[3] == 0
     assert frames[3][0][3] > 0
+
+
+# ---- pass C/D (render_refill.cuh): tiles that leave pass B and get their remaining rounds as independent orbits must end
+# ---- up with the records, counters and colours they would have had staying in pass B (CHAOS_EXPORT=0), whatever the
+# ---- sample budget (3 = smallest that can export, 10 = largest, 11 and 64 = never exported), frame shape and module.
+EXPORT_CASES = [
+    dict(name="ex_full_set_a3_f64", fractal="mandelbrot", W=1920, H=1080, image=cases.seg(-0.5, 0.0, 2.0, 1920, 1080), maxIter=4000,
+         maxSS=3.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ex_full_set_a10_f64", fractal="mandelbrot", W=1531, H=1077, image=cases.seg(-0.5, 0.0, 2.0, 1531, 1077), maxIter=3000,
+         maxSS=10.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ex_full_set_a11_f64", fractal="mandelbrot", W=1280, H=720, image=cases.seg(-0.5, 0.0, 2.0, 1280, 720), maxIter=2500,
+         maxSS=11.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ex_noise_a8_f32", fractal="mandelbrot", W=1920, H=1080, image=cases.seg(-0.235125, 0.827215, 4.0e-4, 1920, 1080), maxIter=2500,
+         maxSS=8.0, flags=cases.A, double=False, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ex_fixed_n6_f64", fractal="mandelbrot", W=1280, H=720, image=cases.seg(-0.748, 0.1, 0.0014, 1280, 720), maxIter=2200,
+         maxSS=6.0, flags=0, double=True, julia_c=(0.0, 0.0), amplifier=10),      # not adaptive: one decision, at i == S / 2
+    dict(name="ex_julia_a8_f64", fractal="julia", W=1920, H=1080, image=cases.seg(0.0, 0.0, 3.2, 1920, 1080), maxIter=2500,
+         maxSS=8.0, flags=cases.A, double=True, julia_c=(-0.8, 0.156), amplifier=10),
+    dict(name="ex_a64_f64", fractal="mandelbrot", W=640, H=360, image=cases.seg(-0.5, 0.0, 2.0, 640, 360), maxIter=2100,
+         maxSS=64.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+]
+
+
+@pytest.mark.parametrize("case", EXPORT_CASES, ids=_ids(EXPORT_CASES))
+def test_exported_rounds_change_nothing(cu, provider, case):
+    out = {}
+    for ex in (0, 1):
+        os.environ["CHAOS_EXPORT"] = str(ex)
+        try:
+            provider.getRenderer("test", False)   # drop the active renderer so the knob is re-read
+            r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+            r.renderQuality(helpers.model_for(cu, case))
+            st = r.stats()
+            out[ex] = (r.downloadRecords(), st.pixel_iterations, st.samples, r.outputRGBA(), st.skipped_iterations, st.kernel_launches)
+        finally:
+            os.environ.pop("CHAOS_EXPORT", None)
+    helpers.assert_records_equal(out[1][0], out[0][0], case["name"] + " exported vs kept")
+    assert out[1][1] == out[0][1] and out[1][2] == out[0][2]
+    assert (out[1][3] == out[0][3]).all()
+    assert out[0][5] == 5
+    assert out[1][5] == (8 if 3 <= round(case["maxSS"]) <= 10 else 5)
