@@ -261,20 +261,24 @@ def run_ours(args, wl, rank, world, local):
         part.gather_bands(frame, rank, world, band_rows, dist)
 
     def timed_loop(mode, steps, warmup, sampler=None):
-        """W untimed + K timed steps.  Device time of a step = the library's CUDA events around its kernels (stats.frame_ms,
-        recorded on the stream the kernels are launched on) + torch CUDA events around the NCCL gather/host copy; wall time
-        between the two barriers is kept as well.  Both are reduced with MAX over ranks."""
+        """W untimed + K timed steps.  Device time: one GPU -- the library's CUDA events around each frame's kernels
+        (stats.frame_ms, recorded on the stream the kernels are launched on), summed; several GPUs -- torch CUDA events
+        bracketing the K steps on the stream that carries the exchange step (every step ends there).  The host clock
+        between the two barriers is kept as well.  All reduced with MAX over ranks."""
         if r.getState() == cu.STATE_READY_TO_RENDER:
             r.freeRenderingResources()
         r.initializeRendering(W, H, None, mode)
         r.setPartition(rank, world, band_rows)
-        frame = None
+        frame = shared = token = None
         if world > 1:
             frame = torch.as_tensor(DevBuf(r.outputRGBADevicePointer()), device="cuda") if mode == cu.OUTPUT_DEVICE else None
+            # compose straight into rank 0's frame over NVLink (CUDA IPC); falls back to the NCCL band gather
+            shared = part.share_frame(r, rank, world, dist) if (frame is not None and not args.nccl_gather) else None
+            token = torch.zeros(1, device="cuda", dtype=torch.int32)
         host_frame = torch.empty((H, W), dtype=torch.int32).pin_memory() if (world > 1 and args.e2e_host_copy) else None
         iters = launches = skipped = 0
         rms = cms = fms = 0.0
-        gather_ev = []
+        e_start = e_end = None
         for it in range(warmup + steps):
             if it == warmup:
                 barrier()
@@ -283,7 +287,9 @@ def run_ours(args, wl, rank, world, local):
                 t0 = time.perf_counter()
                 iters = launches = skipped = 0
                 rms = cms = fms = 0.0
-                gather_ev = []
+                if world > 1:
+                    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e_start.record()
             r.renderQuality(model)
             st = r.stats()
             iters += st.pixel_iterations
@@ -293,28 +299,34 @@ def run_ours(args, wl, rank, world, local):
             cms += st.compose_ms
             fms += st.frame_ms
             if world > 1 and frame is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                gather_to_rank0(frame)
-                if host_frame is not None and rank == 0:
-                    host_frame.copy_(frame, non_blocking=False)
-                e1.record()
-                gather_ev.append((e0, e1))
+                if shared is not None:
+                    dist.all_reduce(token)                  # the exchange step: every rank's bands have landed in rank 0's frame
+                else:
+                    gather_to_rank0(frame)
+                if host_frame is not None:
+                    if rank == 0:
+                        host_frame.copy_(frame, non_blocking=False)
+                    dist.all_reduce(token)                  # nobody composes the next frame into rank 0's before it is out
+        if e_end is not None:
+            e_end.record()
         barrier()
         dt = time.perf_counter() - t0
         clocks = sampler.stop() if sampler is not None else None
-        gms = sum(a.elapsed_time(b) for a, b in gather_ev)
+        dev_ms = e_start.elapsed_time(e_end) if e_end is not None else fms
         if world > 1:
-            t = torch.tensor([dt, rms, cms, fms + gms, gms], device="cuda", dtype=torch.float64)
+            t = torch.tensor([dt, rms, cms, dev_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt, rms, cms, dev_ms, gms = t.tolist()
+            dt, rms, cms, dev_ms = t.tolist()
             c = torch.tensor([iters, launches, skipped], device="cuda", dtype=torch.int64)
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
             iters, launches, skipped = c.tolist()
-        else:
-            dev_ms = fms
+        exchange = "none" if world == 1 else ("compose writes into rank 0's frame over NVLink (CUDA IPC) + completion all-reduce" if shared is not None
+                                              else "NCCL send/recv of row bands to rank 0")
+        if shared is not None:
+            torch.cuda.synchronize()
+            shared.close()
         return dict(seconds=dt, device_seconds=dev_ms * 1e-3, iters=iters, skipped=skipped, launches=launches, render_ms=rms,
-                    compose_ms=cms, gather_ms=gms, clocks=clocks)
+                    compose_ms=cms, exchange_ms=max(0.0, dev_ms - fms) if world > 1 else 0.0, clocks=clocks, exchange=exchange)
 
     sampler = ClockSampler(local) if rank == 0 else None
     dev = timed_loop(cu.OUTPUT_DEVICE, args.steps, args.warmup, sampler)
@@ -357,11 +369,11 @@ def run_ours(args, wl, rank, world, local):
             "data": "synthetic", "frames_per_s": args.steps / dev["device_seconds"],
             "wall_ms_per_step": dev["seconds"] * 1e3 / args.steps,
             "timing": "ms_per_step = CUDA events on the stream the kernels are launched on (first render kernel .. compose end"
-                      + (", + torch CUDA events around the NCCL gather" if world > 1 else "") + "), summed over the K steps, MAX over ranks; "
+                      + "), summed over the K steps" + ("" if world == 1 else "; several GPUs: torch CUDA events bracketing the K steps on the stream of the exchange step") + ", MAX over ranks; "
                       "wall_ms_per_step = host clock between the two barrier+synchronize brackets",
             "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H, "max_iterations": wl["maxIter"],
                        "max_super_sampling": wl["maxSS"], "adaptive_ss": bool(wl["flags"] & A),
-                       "parallelism": "1 GPU" if world == 1 else "row bands of %d px dealt round-robin over %d GPUs, NCCL send/recv gather to rank 0" % (band_rows, world),
+                       "parallelism": "1 GPU" if world == 1 else "row bands of %d px dealt round-robin over %d GPUs; %s" % (band_rows, world, dev["exchange"]),
                        "pixel_iterations_per_step": dev["iters"] // args.steps,
                        "executed_pixel_iterations_per_step": executed // args.steps,
                        "work_accounting": "pixel_iterations = trips of the reference's loop for this frame (inside points count maxIterations). "
@@ -377,7 +389,7 @@ def run_ours(args, wl, rank, world, local):
             "gpu_launches": dev["launches"],
             "clocks": dev["clocks"],
             "device_ms_per_step": {"render_kernel": dev["render_ms"] / args.steps, "compose_kernel": dev["compose_ms"] / args.steps,
-                                   "gather": dev["gather_ms"] / args.steps},
+                                   "exchange_and_skew": dev["exchange_ms"] / args.steps},
         }
         # roofline of the dominant kernel: the FP pipe.  peak = FMA lane-ops/s measured just now on this device.
         # achieved counts FP instructions the kernel ISSUED at the least: 5 per executed trip (the untested scaled form;
@@ -677,6 +689,7 @@ def main():
     ap.add_argument("--engine", type=int, default=None)
     ap.add_argument("--ref-kind", default="src", choices=["src", "ptx92"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="multi-GPU: gather the bands with NCCL send/recv instead of composing into rank 0's frame")
     ap.add_argument("--no-full-trips", action="store_true", help="skip the CHAOS_SHORTCUTS=0 comparison run")
     ap.add_argument("--cpu-row-stride", type=int, default=8)
     args = ap.parse_args()

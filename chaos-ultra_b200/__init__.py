@@ -154,6 +154,7 @@ _API = {
     "chaos_download_records": (C.c_int, [_VP, _VP, C.c_size_t]),
     "chaos_get_stats": (C.c_int, [_VP, C.POINTER(_Stats)]),
     "chaos_set_partition": (C.c_int, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "chaos_set_output_target": (C.c_int, [_VP, C.c_uint64]),
     "chaos_last_error": (C.c_char_p, []),
     "chaos_abi_version": (C.c_uint32, []),
 }
@@ -430,6 +431,10 @@ class CudaFractalRenderer:
 
     def outputRGBADevicePointer(self) -> int:
         return int(self._lib.chaos_output_rgba_device(self._h))
+
+    def setOutputTarget(self, device_ptr: int) -> None:
+        """DEVICE mode: compose writes into ``device_ptr`` (e.g. rank 0's frame mapped with CUDA IPC) instead of the own frame; 0 resets."""
+        _check(self._lib, self._lib.chaos_set_output_target(self._h, int(device_ptr)))
 
     def downloadRecords(self) -> np.ndarray:
         """The primary pixel_info_t buffer as an (H, W) structured array."""

@@ -304,7 +304,8 @@ struct chaos_renderer {
     CUfunction k_main_f_sync = nullptr, k_main_d_sync = nullptr;   /* engine 0 (differential check) */
     CUfunction k_classify = nullptr, k_order = nullptr;            /* between the two passes of engine 1 */
     CUfunction k_replay = nullptr;                                 /* pass D */
-    chaos_export exp_buf = {0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   /* pass B -> pass C -> pass D (device memory) */
+    chaos_export exp_buf = {0, nullptr, nullptr, nullptr, nullptr, nullptr};
+    CUdeviceptr late_tiles = 0;    /* one bit per vote tile of the frame, see chaos_render_args::late_tiles */   /* pass B -> pass C -> pass D (device memory) */
     uint32_t export_enabled = 1;
     CUfunction k_reuse_f = nullptr, k_reuse_d = nullptr;           /* pass R of a fast frame */
     int blocks_reuse_f = 0, blocks_reuse_d = 0;
@@ -327,6 +328,7 @@ struct chaos_renderer {
     CUdeviceptr palette = 0;
     uint32_t palette_len = 0;
     CUdeviceptr rgba_dev = 0;      /* DEVICE mode frame, or device alias of rgba_host */
+    CUdeviceptr rgba_target = 0;   /* chaos_set_output_target: where compose writes instead (0 = rgba_dev) */
     uint32_t *rgba_host = nullptr; /* HOST mode: pinned + mapped */
     CUdeviceptr counters = 0;
     chaos_counters *counters_host = nullptr; /* pinned staging for the read-back */
@@ -570,8 +572,7 @@ static void free_export(chaos_renderer *r)
     if (x.et) D->p_cuMemFree((CUdeviceptr)x.et);
     if (x.iters) D->p_cuMemFree((CUdeviceptr)x.iters);
     if (x.skipped) D->p_cuMemFree((CUdeviceptr)x.skipped);
-    if (x.bitmap) D->p_cuMemFree((CUdeviceptr)x.bitmap);
-    x = chaos_export{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    x = chaos_export{0, nullptr, nullptr, nullptr, nullptr, nullptr};
 }
 
 /* arrays for the tiles pass B hands to pass C; allocated by the first multi-sample render of a frame size */
@@ -581,12 +582,10 @@ static bool ensure_export(chaos_renderer *r, uint32_t n_tiles)
     if (x.capacity >= n_tiles) return true;
     D->p_cuStreamSynchronize(r->stream);
     free_export(r);
-    const size_t frame_tiles = (size_t)((r->width + 7u) / 8u) * ((r->height + 3u) / 4u);
-    CUdeviceptr p[6] = {0, 0, 0, 0, 0, 0};
-    const size_t bytes[6] = {(size_t)n_tiles * 4u, (size_t)n_tiles * 4u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 32u * 4u,
-                             (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u,
-                             ((frame_tiles + 31u) / 32u) * 4u};
-    for (int i = 0; i < 6; ++i) {
+    CUdeviceptr p[5] = {0, 0, 0, 0, 0};
+    const size_t bytes[5] = {(size_t)n_tiles * 4u, (size_t)n_tiles * 4u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 32u * 4u,
+                             (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u, (size_t)n_tiles * CHAOS_EXPORT_ROUNDS * 8u};
+    for (int i = 0; i < 5; ++i) {
         if (D->p_cuMemAlloc(&p[i], bytes[i]) != CUDA_SUCCESS) {
             for (int j = 0; j < i; ++j) D->p_cuMemFree(p[j]);
             return false;
@@ -594,7 +593,7 @@ static bool ensure_export(chaos_renderer *r, uint32_t n_tiles)
     }
     x.capacity = n_tiles;
     x.tile = (uint32_t *)p[0]; x.first = (uint32_t *)p[1]; x.et = (uint32_t *)p[2];
-    x.iters = (unsigned long long *)p[3]; x.skipped = (unsigned long long *)p[4]; x.bitmap = (uint32_t *)p[5];
+    x.iters = (unsigned long long *)p[3]; x.skipped = (unsigned long long *)p[4];
     return true;
 }
 
@@ -605,6 +604,9 @@ static void free_frame_memory(chaos_renderer *r)
     if (r->tile_key) { D->p_cuMemFree(r->tile_key); r->tile_key = 0; }
     if (r->tile_order) { D->p_cuMemFree(r->tile_order); r->tile_order = 0; }
     free_export(r);
+    if (r->late_tiles) { D->p_cuMemFree(r->late_tiles); r->late_tiles = 0; }
+    if (r->late_tiles) { D->p_cuMemFree(r->late_tiles); r->late_tiles = 0; }
+    r->rgba_target = 0;
     if (r->rgba_host) { D->p_cuMemFreeHost(r->rgba_host); r->rgba_host = nullptr; r->rgba_dev = 0; }
     if (r->rgba_dev) { D->p_cuMemFree(r->rgba_dev); r->rgba_dev = 0; }
 }
@@ -632,6 +634,7 @@ extern "C" chaos_status chaos_initialize(chaos_renderer *r, uint32_t width, uint
     const size_t all_tiles = (size_t)((width + 7u) / 8u) * ((height + 3u) / 4u);
     CUresult e = D->p_cuMemAlloc(&r->tile_key, all_tiles * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->tile_order, all_tiles * 4u);
+    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->late_tiles, ((all_tiles + 31u) / 32u) * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->palette, (size_t)palette_len * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemcpyHtoD(r->palette, palette_rgba, (size_t)palette_len * 4u);
     size_t frame_bytes = (size_t)width * height * 4u;
@@ -688,6 +691,17 @@ extern "C" uint32_t chaos_get_width(const chaos_renderer *r) { return r ? r->wid
 extern "C" uint32_t chaos_get_height(const chaos_renderer *r) { return r ? r->height : 0; }
 extern "C" const char *chaos_fractal_name(const chaos_renderer *r) { return r ? r->desc->fractal_name : ""; }
 extern "C" const uint32_t *chaos_output_rgba(const chaos_renderer *r) { return r ? r->rgba_host : nullptr; }
+extern "C" chaos_status chaos_set_output_target(chaos_renderer *r, uint64_t device_ptr)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (r->state != CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Renderer has to be initialized first");
+    if (r->mode != CHAOS_OUTPUT_DEVICE) return fail(CHAOS_ERR_ILLEGAL_STATE, "an output target needs CHAOS_OUTPUT_DEVICE mode");
+    if (device_ptr & 15u) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "the output target must be 16-byte aligned");
+    r->rgba_target = (CUdeviceptr)device_ptr;
+    return CHAOS_OK;
+}
+
 extern "C" uint64_t chaos_output_rgba_device(const chaos_renderer *r) { return (r && r->mode == CHAOS_OUTPUT_DEVICE) ? (uint64_t)r->rgba_dev : 0; }
 
 /* ------------------------------------------------------------------------------------------
@@ -862,7 +876,7 @@ static void fill_compose_args(chaos_renderer *r, const chaos_params *m, chaos_co
     memset(&c, 0, sizeof c);
     c.in = (const chaos_pixel_info *)r->buf[0].ptr;
     c.in_pitch = r->buf[0].pitch;
-    c.out_rgba = (uint32_t *)r->rgba_dev;
+    c.out_rgba = (uint32_t *)(r->rgba_target ? r->rgba_target : r->rgba_dev);
     c.palette = (const uint32_t *)r->palette;
     c.palette_len = r->palette_len;
     c.width = r->width; c.height = r->height;
@@ -942,9 +956,12 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
             const int small_grid = (int)std::min<uint64_t>((a.n_tiles + 255u) / 256u, (uint64_t)cap);
             if (r->export_enabled && S0 >= 3u && S0 <= CHAOS_EXPORT_ROUNDS && ensure_export(r, a.n_tiles)) {
                 a.exp = r->exp_buf;
-                const size_t frame_tiles = (size_t)a.tiles_x * a.tile_rows;
-                if (D->p_cuMemsetD32Async((CUdeviceptr)a.exp.bitmap, 0u, (frame_tiles + 31u) / 32u, r->stream) != CUDA_SUCCESS)
-                    return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed");
+                if (r->overlap_compose) {
+                    a.late_tiles = (uint32_t *)r->late_tiles;
+                    const size_t frame_tiles = (size_t)a.tiles_x * a.tile_rows;
+                    if (D->p_cuMemsetD32Async(r->late_tiles, 0u, (frame_tiles + 31u) / 32u, r->stream) != CUDA_SUCCESS)
+                        return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed");
+                }
             }
             a.phase = 1u;
             st = launch(r, r->k_pass_a[p], r->blocks_pass_a[p], 256, 0, &a);
@@ -968,7 +985,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                 }
             }
             a.warp_trace = nullptr;
-            if (a.exp.capacity && r->overlap_compose && st == CHAOS_OK) {
+            if (a.late_tiles && st == CHAOS_OK) {
                 /* every tile pass B did not export is final: stream the frame out now, next to passes C and D */
                 D->p_cuEventRecord(r->ev[5], r->stream);
                 D->p_cuStreamWaitEvent(r->stream2, r->ev[5], 0);
@@ -989,7 +1006,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     D->p_cuEventRecord(r->ev[1], r->stream);
     if (early_compose) D->p_cuStreamWaitEvent(r->stream, r->ev[7], 0);
     D->p_cuEventRecord(r->ev[2], r->stream);
-    st = early_compose ? launch_compose(r, m, nullptr, a.exp.bitmap) : launch_compose(r, m);
+    st = early_compose ? launch_compose(r, m, nullptr, a.late_tiles) : launch_compose(r, m);
     if (st != CHAOS_OK) return st;
     D->p_cuEventRecord(r->ev[3], r->stream);
     st = finish_frame(r);
@@ -1055,6 +1072,8 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
     D->p_cuEventRecord(r->ev[1], r->stream);
     std::swap(r->buf[0], r->buf[1]);                               /* switch2DBuffers :180 */
     r->buffers_switched = !r->buffers_switched;
+    /* (Starting the frame-wide compose right after the reuse pass, next to the sampling pass, was measured: no gain --
+     * with host output a fast frame is the 33 MB PCIe write, 0.63 ms of 0.84, and the sampling pass is 0.1 ms.) */
     D->p_cuEventRecord(r->ev[2], r->stream);
     st = launch_compose(r, m);
     if (st != CHAOS_OK) return st;

@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 17u
+#define CHAOS_MODULE_ABI 18u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -60,7 +60,6 @@ struct chaos_export {
     uint32_t *et;                       /* [capacity][CHAOS_EXPORT_ROUNDS][32] escape time per round and pixel */
     unsigned long long *iters;          /* [capacity][CHAOS_EXPORT_ROUNDS] trips of the round's orbits (reference count) */
     unsigned long long *skipped;        /* [capacity][CHAOS_EXPORT_ROUNDS] of which proven, not executed */
-    uint32_t *bitmap;                   /* one bit per vote tile of the FRAME (row-major): set for exported tiles */
 };
 
 struct chaos_render_args {
@@ -89,6 +88,8 @@ struct chaos_render_args {
     uint32_t phase;         /* 0 = whole render in one launch; 1 = pass A (sample 0 of every pixel); 2 = pass B (the rest);
                              * 3 = pass C (the rounds pass B exported, as independent orbits) */
     chaos_export exp;
+    uint32_t *late_tiles;   /* NULL, or one bit per vote tile of the FRAME (row-major): set by pass B for the tiles it exports -- the
+                             * tiles that are not final when the frame-wide compose starts */
     uint32_t engine;        /* 0 = tile-synchronous, 1 = lane-refill scheduler */
     uint32_t force_exact;   /* 1 = always the reference's 7-operation trip (differential check) */
     uint32_t block_iters;   /* engine 1: trips between two scheduling points (multiple of 4) */

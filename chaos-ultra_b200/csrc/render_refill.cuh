@@ -366,8 +366,10 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                     for (uint32_t q = 0; q <= i; ++q) export_et(a, e, q)[lane] = part ? ws.et[k][q][lane] : 0u;
                     if (lane == 0) {
                         a.exp.tile[e] = hk.tile; a.exp.first[e] = i + 1u;
-                        const uint32_t gt = (hk.y0 >> 2) * a.tiles_x + (hk.x0 >> 3);
-                        atomicOr(&a.exp.bitmap[gt >> 5], 1u << (gt & 31u));
+                        if (a.late_tiles) {
+                            const uint32_t gt = (hk.y0 >> 2) * a.tiles_x + (hk.x0 >> 3);
+                            atomicOr(&a.late_tiles[gt >> 5], 1u << (gt & 31u));
+                        }
                     }
                     if (lane >= i + 1u && lane < CHAOS_EXPORT_ROUNDS) {
                         a.exp.iters[(size_t)e * CHAOS_EXPORT_ROUNDS + lane] = 0ull;

@@ -4,9 +4,13 @@ New functionality (the reference is hard-wired to device 0, cudarenderer/CudaHel
 quality frame is independent and a vote tile is 8x4 pixels, so the frame is cut into bands of ``band_rows`` pixel
 rows (a multiple of 4: vote tiles never straddle two GPUs), band ``b`` belongs to rank ``b % world``.  Each rank
 renders and composes only its bands (``chaos_set_partition``); the one exchange step of the path is the gather of
-the composed RGBA bands into rank 0's frame -- a band is a contiguous ``rows x width x 4`` byte range, so it is one
-send/recv pair per band, batched.  The same plan runs over NCCL (device tensors, NVLink) in bench.py and over gloo
-(CPU tensors) in the tests.
+the composed RGBA bands into rank 0's frame.  Two ways:
+
+* ``share_frame`` (default on GPUs): rank 0's device frame is mapped into every other rank's process with CUDA IPC and
+  set as their compose target (``chaos_set_output_target``), so the bands cross NVLink as the compose kernel's own
+  128-bit stores -- compose and gather are one kernel -- and the exchange step shrinks to a completion barrier;
+* ``gather_bands``: a band is a contiguous ``rows x width x 4`` byte range, so it is one send/recv pair per band,
+  batched.  Runs over NCCL (device tensors) or gloo (CPU tensors, the tests).
 """
 from __future__ import annotations
 
@@ -68,3 +72,56 @@ def gather_bands(frame, rank: int, world: int, band_rows: int, dist) -> int:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return nbytes
+
+
+def share_frame(renderer, rank: int, world: int, dist):
+    """Map rank 0's device frame into the other ranks (CUDA IPC) and make it their compose target.
+    Returns an object that must stay alive while the target is in use (close() unmaps), or None if this cannot be
+    done here (no cuda.bindings, IPC refused) -- callers then fall back to gather_bands.  Collective: every rank calls it."""
+    if world == 1:
+        return None
+    try:
+        from cuda.bindings import driver as cu
+    except Exception:
+        cu = None
+    payload = [None]
+    if rank == 0 and cu is not None:
+        res, handle = cu.cuIpcGetMemHandle(renderer.outputRGBADevicePointer())
+        if res == cu.CUresult.CUDA_SUCCESS:
+            payload = [bytes(handle.reserved)]
+    dist.broadcast_object_list(payload, src=0)
+    ok, mapped = 1, None
+    if rank != 0:
+        ok = 0
+        if cu is not None and payload[0] is not None:
+            handle = cu.CUipcMemHandle()
+            handle.reserved = payload[0]
+            res, ptr = cu.cuIpcOpenMemHandle(handle, cu.CUipcMem_flags.CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS)
+            if res == cu.CUresult.CUDA_SUCCESS:
+                mapped, ok = int(ptr), 1
+    elif payload[0] is None:
+        ok = 0
+    import torch
+    flag = torch.tensor([ok], dtype=torch.int32, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:                     # somebody could not map it: nobody uses it
+        if mapped is not None:
+            cu.cuIpcCloseMemHandle(mapped)
+        return None
+    if mapped is not None:
+        renderer.setOutputTarget(mapped)
+    return _SharedFrame(renderer, mapped, cu)
+
+
+class _SharedFrame:
+    def __init__(self, renderer, mapped, cu):
+        self.renderer, self.mapped, self.cu = renderer, mapped, cu
+
+    def close(self):
+        if self.mapped is not None:
+            try:
+                self.renderer.setOutputTarget(0)
+            except Exception:
+                pass
+            self.cu.cuIpcCloseMemHandle(self.mapped)
+            self.mapped = None

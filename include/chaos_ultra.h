@@ -161,6 +161,12 @@ CHAOS_API chaos_status chaos_get_stats(const chaos_renderer *r, chaos_stats *out
  * part_index, bands being band_rows pixel rows high (a multiple of 4).  part_count 1 = whole frame. */
 CHAOS_API chaos_status chaos_set_partition(chaos_renderer *r, uint32_t part_index, uint32_t part_count, uint32_t band_rows);
 
+/* Multi-GPU, DEVICE mode: compose writes its bands into `device_ptr` instead of the renderer's own frame -- e.g. rank 0's
+ * frame mapped into this process with CUDA IPC, so that the composed bands cross NVLink as the compose kernel's own
+ * stores and no separate gather step is needed.  width*height*4 bytes must be writable there.  0 = the own frame again.
+ * chaos_free_resources resets it. */
+CHAOS_API chaos_status chaos_set_output_target(chaos_renderer *r, uint64_t device_ptr);
+
 CHAOS_API const char *chaos_last_error(void);
 CHAOS_API uint32_t chaos_abi_version(void);
 

@@ -232,6 +232,33 @@ def test_partitioned_rendering_equals_whole_frame(cu, provider, world, band):
         r.setPartition(2, 2, 8)
 
 
+def test_partitions_compose_into_one_shared_target(cu, provider):
+    """chaos_set_output_target: every part composes its bands straight into ONE frame (what the ranks do with rank 0's
+    frame mapped over CUDA IPC); after the last part that frame is the whole picture, no gather step"""
+    import torch
+    case = cases.EXTRA_MAIN_CASES[0] if hasattr(cases, "EXTRA_MAIN_CASES") and cases.EXTRA_MAIN_CASES else cases.MAIN_CASES[2]
+    case = dict(case, maxSS=8.0, flags=cases.A)            # several samples: passes A..D and both compose launches
+    r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+    r.renderQuality(helpers.model_for(cu, case))
+    whole = r.outputRGBA()
+    target = torch.zeros((case["H"], case["W"]), dtype=torch.int32, device="cuda")
+    world, band = 3, 8
+    for rank in range(world):
+        r.freeRenderingResources()
+        r.initializeRendering(case["W"], case["H"], None, cu.OUTPUT_DEVICE)
+        r.setPartition(rank, world, band)
+        r.setOutputTarget(target.data_ptr())
+        r.renderQuality(helpers.model_for(cu, case))
+    torch.cuda.synchronize()
+    assert (target.cpu().numpy().view(np.uint32) == whole).all()
+    r.setOutputTarget(0)
+    r.setPartition(0, 1, 32)
+    r.freeRenderingResources()
+    r.initializeRendering(case["W"], case["H"], None, cu.OUTPUT_HOST)
+    with pytest.raises(cu.IllegalStateException, match="DEVICE"):
+        r.setOutputTarget(target.data_ptr())
+
+
 def test_partitioned_fast_frame_equals_whole_frame(cu, provider):
     case = cases.ADV_CASES[2]
     img0, img1 = cases.adv_segments(case)
