@@ -402,7 +402,7 @@ def run_ours(args, wl, rank, world, local):
             achieved = executed / world * min_ops / kernel_s
             out["roofline"] = {"bound": "fp64" if wl["double"] else "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9,
                                "unit": "G FP-lane-ops/s", "frac": achieved / peak, "traffic": None,
-                               "kernel": "fractalRenderMain" + ("Double" if wl["double"] else "Float"),
+                               "kernel": ("fractalRenderMain%s" if round(wl["maxSS"]) <= 1 else "chaosPassA%s + chaosPassB%s + chaosPassC%s (the iteration kernels of a multi-sample frame)").replace("%s", "Double" if wl["double"] else "Float"),
                                "peak_source": "measured in this run: bench_kernels/peak.cubin, independent FMA chains, best of 5 (not in MEASURED_PEAKS.json)",
                                "achieved_definition": "%d FP instructions x %d executed pixel-iterations per launch sequence / render-kernel time (lower bound of issued instructions)"
                                                       % (min_ops, executed // args.steps // world),
@@ -691,7 +691,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-gather", action="store_true", help="multi-GPU: gather the bands with NCCL send/recv instead of composing into rank 0's frame")
     ap.add_argument("--no-full-trips", action="store_true", help="skip the CHAOS_SHORTCUTS=0 comparison run")
-    ap.add_argument("--cpu-row-stride", type=int, default=8)
+    ap.add_argument("--cpu-row-stride", type=int, default=2, help="host baseline: every n-th vote-tile row of the frame (bounds the CPU time)")
     args = ap.parse_args()
     args.e2e_host_copy = False
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

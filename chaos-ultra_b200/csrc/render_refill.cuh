@@ -1,37 +1,32 @@
 /*
- * render_refill.cuh -- engine 1 of the main render kernel: persistent warps, work-stealing over vote
- * tiles, finished lanes refilled with pending orbits.  Included by render_generic.cuh.
+ * render_refill.cuh -- engine 1 of the main render kernels: persistent warps, work stealing over vote tiles,
+ * finished lanes refilled with pending orbits.  Included by render_generic.cuh.
  *
- * Why: the escape loop runs 1 ... maxIterations trips per sample and neighbouring pixels differ by
- * orders of magnitude near the set's boundary, so "one warp = one 8x4 tile, all lanes wait for the
- * slowest" (the reference's mapping, fractalRendererGeneric.cu:36-53) leaves most FP64 lanes idle there.
- * Here an ORBIT (one sample of one pixel) is the unit of work:
+ * Why: the escape loop runs 1 ... maxIterations trips per sample and neighbouring pixels differ by orders of
+ * magnitude near the set's boundary, so "one warp = one 8x4 tile, all lanes wait for the slowest" (the reference's
+ * mapping, fractalRendererGeneric.cu:36-53) leaves most FP64 lanes idle there.  Here an ORBIT (one sample of one
+ * pixel) is the unit of work: tiles come from a global cursor, lanes iterate in blocks of trips, and at a
+ * scheduling pass the lanes whose orbit ended retire their result and take the next pending orbit (rank among idle
+ * lanes -> n-th pending pixel).
  *
- *   - every warp owns CHAOS_REFILL_SLOTS tile slots in shared memory (per pixel: running sum of escape
- *     times + the first 10 samples, exactly the state sampleTheFractal keeps in registers, :96-127);
- *   - tiles come from one global cursor (atomicAdd) -- whichever warp is free takes the next tile;
- *   - lanes iterate in blocks of `block_iters` trips; at the end of a block the lanes whose orbit ended
- *     are found with a ballot, retire their result into the slot, and take the next pending orbit of ANY
- *     of the warp's slots (rank among idle lanes -> n-th set bit of the slot's pending mask);
- *   - a slot's sample round i+1 may only start when all 32 orbits of round i have retired, because
- *     the reference's early-termination decision (:128-150) is an ALL-vote over the tile.  When the last
- *     orbit of a round retires the warp evaluates that decision cooperatively, lane p speaking for
- *     pixel p, with the same predicates and the same votes as engine 0 -- so sample counts, sums and
- *     therefore every stored record are identical to the reference's.
+ * One sample per pixel (round(maxSuperSampling) == 1: configs c1, c4): one launch of independent orbits
+ * (render_main_independent, kMode 0).
  *
- * With one sample per pixel (round(maxSuperSampling) == 1: configs c1, c4) no vote can change anything,
- * orbits are independent, and a simpler variant without slots is used (render_main_independent).
- *
- * Two-pass order (the default when more than one sample is allowed).  A tile's rounds are sequential, so a
- * tile with one never-escaping pixel and 8 rounds has a critical path of 8 x maxIterations dependent trips no
- * matter how many lanes are free; if such a tile is started late the whole GPU waits for it.  Sample 0 of
- * every pixel needs no vote (the decision block is not entered at i = 0 when S >= 2), so:
- *   pass A  = sample 0 of every pixel as independent orbits (render_main_independent, kProbe): perfect refill,
- *             leaves (escape time, trip count) in the pixel's output record;
- *   classify/order = every tile gets a cost class from pass A's trip counts (never-escaping mixed tiles first,
- *             then all-inside tiles, then by log2 of the longest orbit) and a counting sort builds the order;
- *   pass B  = rounds 1.. of every tile, slots pre-loaded from the records, tiles taken longest-expected-first.
- * Nothing is computed twice and no result depends on the order, only the tail of the launch does.
+ * Several samples: the reference's early-termination decision (:128-150) is an ALL-vote over the tile after each
+ * sample, so sample i+1 of a tile needs sample i of all its pixels.  The frame runs in passes:
+ *   pass A   sample 0 of every pixel needs no vote (the decision block is not entered at i = 0 when S >= 2):
+ *            independent orbits (kMode 1); escape time, trip count and executed trips wait in the pixel's record;
+ *   classify/order   a cost class per tile from those records, counting sort: tile_order, most expensive first;
+ *   pass B   rounds 1.. with the votes (render_main_rounds).  Every warp owns CHAOS_REFILL_SLOTS tile slots in shared
+ *            memory (per pixel: sum of the decided rounds' escape times + one escape time per round for the first
+ *            ten rounds, the state sampleTheFractal keeps in registers, :96-127); lanes take pending orbits of any
+ *            slot and any round in flight; when the round that is next in order is complete the warp evaluates the
+ *            decision cooperatively, lane p speaking for pixel p, with the reference's predicates and votes -- so
+ *            sample counts, sums and therefore every stored record are the reference's;
+ *   pass C   the remaining rounds of the tiles pass B EXPORTED (tiles set to use their whole sample budget), as
+ *            independent orbits of one GPU-wide pool (kMode 2);
+ *   pass D   the decisions of those tiles, replayed over the stored rounds (replay_exported).
+ * No result depends on the order in which anything runs; only the launches' tails do.
  */
 #ifndef CHAOS_RENDER_REFILL_CUH
 #define CHAOS_RENDER_REFILL_CUH
