@@ -288,6 +288,9 @@ struct ctx_guard {
     ~ctx_guard() { if (pushed) { CUcontext c; D->p_cuCtxPopCurrent(&c); } }
 };
 
+#define CHAOS_MAX_STRANDS 8
+#define CHAOS_DEFAULT_STRANDS 2
+
 struct record_buffer {
     CUdeviceptr ptr = 0;
     size_t pitch = 0;
@@ -336,6 +339,16 @@ struct chaos_renderer {
     CUevent ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   /* render start/end, compose start/end, pass boundary,
                                                                     * pass B done, early compose start/end (stream2) */
     CUstream stream2 = nullptr;    /* the frame-wide compose of a multi-pass render runs here, next to passes C and D */
+    /* Strands: a multi-pass frame is cut into `strands` interleaved sets of row bands (the multi-GPU partition, one level
+     * down), each with its own stream, counters, tile order and export arrays.  Their pass chains A -> B -> C -> D are
+     * independent, so the CTAs of one strand's next pass fill the SMs that the other strand's draining pass leaves idle:
+     * the tail of every pass but the last is hidden.  Strand 0 runs on `stream`. */
+    uint32_t strands = CHAOS_DEFAULT_STRANDS;
+    /* threads per CTA of the persistent pass kernels (warps are independent there): a CTA gives its SM share back only
+     * when its last warp is done, so smaller CTAs let the next pass in sooner */
+    uint32_t pass_threads = 256;
+    CUstream strand_stream[CHAOS_MAX_STRANDS] = {};
+    CUevent strand_ev_b[CHAOS_MAX_STRANDS] = {}, strand_ev_done[CHAOS_MAX_STRANDS] = {};
     uint32_t overlap_compose = 1;
     uint32_t part_index = 0, part_count = 1, band_rows = 64;
     chaos_stats stats;
@@ -487,10 +500,12 @@ static chaos_status load_module(chaos_renderer *r)
     }
     r->blocks_main_f = persistent_blocks(r, r->k_main_f, 256);
     r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256);
+    const int T = (int)r->pass_threads;
+    r->refill_smem = r->refill_smem / 8u * (r->pass_threads / 32u);   /* the module states it for 8 warps */
     for (int p = 0; p < 2; ++p) {
-        r->blocks_pass_a[p] = persistent_blocks(r, r->k_pass_a[p], 256);
-        r->blocks_pass_b[p] = persistent_blocks(r, r->k_pass_b[p], 256, r->refill_smem);
-        r->blocks_pass_c[p] = persistent_blocks(r, r->k_pass_c[p], 256);
+        r->blocks_pass_a[p] = persistent_blocks(r, r->k_pass_a[p], T);
+        r->blocks_pass_b[p] = persistent_blocks(r, r->k_pass_b[p], T, r->refill_smem);
+        r->blocks_pass_c[p] = persistent_blocks(r, r->k_pass_c[p], T);
     }
     r->blocks_main_f_sync = persistent_blocks(r, r->k_main_f_sync, 256);
     r->blocks_main_d_sync = persistent_blocks(r, r->k_main_d_sync, 256);
@@ -541,6 +556,10 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (oc) r->overlap_compose = (uint32_t)atoi(oc) ? 1u : 0u;
     const char *ex = getenv("CHAOS_EXPORT");      /* 0 = every tile keeps all its rounds in pass B */
     if (ex) r->export_enabled = (uint32_t)atoi(ex) ? 1u : 0u;
+    const char *sn = getenv("CHAOS_STRANDS");     /* 1 = the passes of a multi-sample frame run one after the other */
+    if (sn) r->strands = (uint32_t)std::min(std::max(atoi(sn), 1), CHAOS_MAX_STRANDS);
+    const char *pt = getenv("CHAOS_PASS_THREADS");
+    if (pt && (atoi(pt) == 32 || atoi(pt) == 64 || atoi(pt) == 128 || atoi(pt) == 256)) r->pass_threads = (uint32_t)atoi(pt);
     const char *sc = getenv("CHAOS_SHORTCUTS");   /* 0 = every trip executed and tested, as the reference does */
     if (sc) r->shortcuts = (uint32_t)atoi(sc) & (CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE);
     chaos_status st = load_module(r);
@@ -548,8 +567,14 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     CUresult e = D->p_cuStreamCreate(&r->stream, CU_STREAM_NON_BLOCKING);
     if (e == CUDA_SUCCESS) e = D->p_cuStreamCreate(&r->stream2, CU_STREAM_NON_BLOCKING);
     for (int i = 0; i < 8 && e == CUDA_SUCCESS; ++i) e = D->p_cuEventCreate(&r->ev[i], CU_EVENT_DEFAULT);
-    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->counters, sizeof(chaos_counters));
-    if (e == CUDA_SUCCESS) e = D->p_cuMemHostAlloc((void **)&r->counters_host, sizeof(chaos_counters), 0);
+    r->strand_stream[0] = r->stream;
+    for (uint32_t i = 0; i < CHAOS_MAX_STRANDS && e == CUDA_SUCCESS; ++i) {
+        if (i) e = D->p_cuStreamCreate(&r->strand_stream[i], CU_STREAM_NON_BLOCKING);
+        if (e == CUDA_SUCCESS) e = D->p_cuEventCreate(&r->strand_ev_b[i], CU_EVENT_DISABLE_TIMING);
+        if (e == CUDA_SUCCESS) e = D->p_cuEventCreate(&r->strand_ev_done[i], CU_EVENT_DISABLE_TIMING);
+    }
+    if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->counters, sizeof(chaos_counters) * CHAOS_MAX_STRANDS);
+    if (e == CUDA_SUCCESS) e = D->p_cuMemHostAlloc((void **)&r->counters_host, sizeof(chaos_counters) * CHAOS_MAX_STRANDS, 0);
     if (e != CUDA_SUCCESS) {
         st = fail(CHAOS_ERR_CUDA_INIT, "cannot create stream/events/counters: %s", cu_err_name(e));
         p->active = r;
@@ -679,6 +704,11 @@ extern "C" chaos_status chaos_close(chaos_renderer *r)
     if (r->counters_host) D->p_cuMemFreeHost(r->counters_host);
     for (int i = 0; i < 8; ++i) if (r->ev[i]) D->p_cuEventDestroy(r->ev[i]);
     if (r->stream2) { D->p_cuStreamSynchronize(r->stream2); D->p_cuStreamDestroy(r->stream2); }
+    for (uint32_t i = 0; i < CHAOS_MAX_STRANDS; ++i) {
+        if (i && r->strand_stream[i]) { D->p_cuStreamSynchronize(r->strand_stream[i]); D->p_cuStreamDestroy(r->strand_stream[i]); }
+        if (r->strand_ev_b[i]) D->p_cuEventDestroy(r->strand_ev_b[i]);
+        if (r->strand_ev_done[i]) D->p_cuEventDestroy(r->strand_ev_done[i]);
+    }
     if (r->stream) D->p_cuStreamDestroy(r->stream);
     unload_module(r);
     if (r->provider && r->provider->active == r) r->provider->active = nullptr;
@@ -803,6 +833,17 @@ static chaos_status validate_model(const chaos_renderer *r, const chaos_params *
     return CHAOS_OK;
 }
 
+/* tile rows of the bands b with b % part_count == part_index */
+static uint32_t owned_tile_rows(uint32_t tile_rows, uint32_t band_tile_rows, uint32_t part_index, uint32_t part_count)
+{
+    if (part_count <= 1u) return tile_rows;
+    uint32_t owned = 0;
+    const uint32_t bands = (tile_rows + band_tile_rows - 1u) / band_tile_rows;
+    for (uint32_t b = part_index; b < bands; b += part_count)
+        owned += std::min(band_tile_rows, tile_rows - b * band_tile_rows);
+    return owned;
+}
+
 static void fill_render_args(const chaos_renderer *r, const chaos_params *m, chaos_render_args *a)
 {
     memset(a, 0, sizeof *a);
@@ -825,14 +866,7 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
     a->tiles_x = (r->width + 7u) / 8u;
     a->tile_rows = (r->height + 3u) / 4u;
     a->part_index = r->part_index; a->part_count = r->part_count; a->band_tile_rows = r->band_rows / 4u;
-    uint32_t owned_rows = a->tile_rows;
-    if (r->part_count > 1u) {
-        owned_rows = 0;
-        uint32_t bands = (a->tile_rows + a->band_tile_rows - 1u) / a->band_tile_rows;
-        for (uint32_t b = r->part_index; b < bands; b += r->part_count)
-            owned_rows += std::min(a->band_tile_rows, a->tile_rows - b * a->band_tile_rows);
-    }
-    a->n_tiles = owned_rows * a->tiles_x;
+    a->n_tiles = owned_tile_rows(a->tile_rows, a->band_tile_rows, r->part_index, r->part_count) * a->tiles_x;
     a->tile_key = (uint32_t *)r->tile_key;
     a->tile_order = (uint32_t *)r->tile_order;
     a->engine = r->engine;
@@ -886,16 +920,19 @@ static void fill_compose_args(chaos_renderer *r, const chaos_params *m, chaos_co
 
 static chaos_status finish_frame(chaos_renderer *r)
 {
-    CUresult e = D->p_cuMemcpyDtoHAsync(r->counters_host, r->counters, sizeof(chaos_counters), r->stream);
+    CUresult e = D->p_cuMemcpyDtoHAsync(r->counters_host, r->counters, sizeof(chaos_counters) * CHAOS_MAX_STRANDS, r->stream);
     if (e == CUDA_SUCCESS) e = D->p_cuStreamSynchronize(r->stream);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "Error just after launching a kernel:%s", cu_err_name(e));
     D->p_cuEventElapsedTime(&r->stats.render_ms, r->ev[0], r->ev[1]);
     D->p_cuEventElapsedTime(&r->stats.compose_ms, r->ev[2], r->ev[3]);
     D->p_cuEventElapsedTime(&r->stats.frame_ms, r->ev[0], r->ev[3]);
     r->stats.reuse_ms = 0.f;
-    r->stats.pixel_iterations = r->counters_host->pixel_iterations;
-    r->stats.samples = r->counters_host->samples;
-    r->stats.skipped_iterations = r->counters_host->skipped_iterations;
+    r->stats.pixel_iterations = r->stats.samples = r->stats.skipped_iterations = 0;
+    for (uint32_t s = 0; s < CHAOS_MAX_STRANDS; ++s) {      /* every strand of the frame counts into its own block */
+        r->stats.pixel_iterations += r->counters_host[s].pixel_iterations;
+        r->stats.samples += r->counters_host[s].samples;
+        r->stats.skipped_iterations += r->counters_host[s].skipped_iterations;
+    }
     return CHAOS_OK;
 }
 
@@ -933,7 +970,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     fill_render_args(r, m, &a);
     a.out = (chaos_pixel_info *)r->buf[0].ptr; a.out_pitch = r->buf[0].pitch;
     r->stats.kernel_launches = 0;
-    CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters), r->stream);
+    CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters) * CHAOS_MAX_STRANDS, r->stream);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
     bool early_compose = false;
@@ -951,55 +988,85 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
             st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, 0, &a);
         } else {
             /* pass A: sample 0 of every pixel; classify + order: expected-longest tiles first; pass B: the other rounds,
-             * except those of tiles set to use their whole budget -> pass C (independent orbits) + pass D (their decisions) */
-            const int cap = r->provider->sm_count * 4;
-            const int small_grid = (int)std::min<uint64_t>((a.n_tiles + 255u) / 256u, (uint64_t)cap);
-            if (r->export_enabled && S0 >= 3u && S0 <= CHAOS_EXPORT_ROUNDS && ensure_export(r, a.n_tiles)) {
-                a.exp = r->exp_buf;
-                if (r->overlap_compose) {
-                    a.late_tiles = (uint32_t *)r->late_tiles;
-                    const size_t frame_tiles = (size_t)a.tiles_x * a.tile_rows;
-                    if (D->p_cuMemsetD32Async(r->late_tiles, 0u, (frame_tiles + 31u) / 32u, r->stream) != CUDA_SUCCESS)
-                        return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed");
-                }
-            }
-            a.phase = 1u;
-            st = launch(r, r->k_pass_a[p], r->blocks_pass_a[p], 256, 0, &a);
-            const int tile_grid = (int)std::min<uint64_t>((a.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);   /* one warp per tile */
-            if (st == CHAOS_OK) st = launch(r, r->k_classify, tile_grid, 256, 0, &a);
-            if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &a);
-            a.phase = 2u;
+             * except those of tiles set to use their whole budget -> pass C (independent orbits) + pass D (their decisions).
+             * The frame runs as G strands (see chaos_renderer::strands): the same chain over interleaved sets of row bands,
+             * one stream each, so one strand's next pass fills the SMs another strand's draining pass leaves idle. */
             const char *trace_path = getenv("CHAOS_WARP_TRACE");
-            const size_t trace_bytes = (size_t)r->blocks_pass_b[p] * 8u * 8u * sizeof(unsigned long long);
-            if (trace_path) {
-                if (!r->warp_trace && D->p_cuMemAlloc(&r->warp_trace, trace_bytes) != CUDA_SUCCESS) r->warp_trace = 0;
-                if (r->warp_trace) { D->p_cuMemsetD8Async(r->warp_trace, 0, trace_bytes, r->stream); a.warp_trace = (unsigned long long *)r->warp_trace; }
+            const uint32_t bands = (a.tile_rows + a.band_tile_rows - 1u) / a.band_tile_rows;
+            uint32_t G = trace_path ? 1u : r->strands;
+            while (G > 1u && (uint64_t)bands < (uint64_t)r->part_count * G * 2u) --G;   /* at least two bands per strand */
+            const bool exporting = r->export_enabled && S0 >= 3u && S0 <= CHAOS_EXPORT_ROUNDS && ensure_export(r, a.n_tiles);
+            if (exporting && r->overlap_compose) {
+                a.late_tiles = (uint32_t *)r->late_tiles;
+                const size_t frame_tiles = (size_t)a.tiles_x * a.tile_rows;
+                if (D->p_cuMemsetD32Async(r->late_tiles, 0u, (frame_tiles + 31u) / 32u, r->stream) != CUDA_SUCCESS)
+                    return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed");
             }
-            if (st == CHAOS_OK) st = launch(r, r->k_pass_b[p], r->blocks_pass_b[p], 256, r->refill_smem, &a);
-            if (trace_path && r->warp_trace && st == CHAOS_OK) {
-                std::vector<unsigned long long> host(trace_bytes / sizeof(unsigned long long));
-                D->p_cuStreamSynchronize(r->stream);
-                if (D->p_cuMemcpyDtoH(host.data(), r->warp_trace, trace_bytes) == CUDA_SUCCESS) {
-                    FILE *f = fopen(trace_path, "wb");
-                    if (f) { fwrite(host.data(), 1, trace_bytes, f); fclose(f); }
+            if (G > 1u) D->p_cuEventRecord(r->ev[4], r->stream);     /* counters and bitmap are clear */
+            uint32_t tile_base = 0;
+            for (uint32_t s = 0; s < G && st == CHAOS_OK; ++s) {
+                CUstream q = r->strand_stream[s];
+                chaos_render_args b = a;
+                if (G > 1u) {
+                    b.part_index = r->part_index + r->part_count * s;
+                    b.part_count = r->part_count * G;
+                    b.n_tiles = owned_tile_rows(a.tile_rows, a.band_tile_rows, b.part_index, b.part_count) * a.tiles_x;
+                    b.counters = (chaos_counters *)r->counters + s;
+                    b.tile_key = (uint32_t *)r->tile_key + tile_base;
+                    b.tile_order = (uint32_t *)r->tile_order + tile_base;
+                    if (s) D->p_cuStreamWaitEvent(q, r->ev[4], 0);
                 }
+                if (exporting) {
+                    b.exp = r->exp_buf;
+                    b.exp.capacity = b.n_tiles;
+                    b.exp.tile += tile_base; b.exp.first += tile_base;
+                    b.exp.et += (size_t)tile_base * CHAOS_EXPORT_ROUNDS * 32u;
+                    b.exp.iters += (size_t)tile_base * CHAOS_EXPORT_ROUNDS; b.exp.skipped += (size_t)tile_base * CHAOS_EXPORT_ROUNDS;
+                }
+                tile_base += b.n_tiles;
+                if (b.n_tiles) {
+                    const int small_grid = (int)std::min<uint64_t>((b.n_tiles + 255u) / 256u, (uint64_t)r->provider->sm_count * 4u);
+                    const int tile_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);   /* one warp per tile */
+                    b.phase = 1u;
+                    st = launch(r, r->k_pass_a[p], r->blocks_pass_a[p], (int)r->pass_threads, 0, &b, q);
+                    if (st == CHAOS_OK) st = launch(r, r->k_classify, tile_grid, 256, 0, &b, q);
+                    if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &b, q);
+                    b.phase = 2u;
+                    const size_t trace_bytes = (size_t)r->blocks_pass_b[p] * (r->pass_threads / 32u) * 8u * sizeof(unsigned long long);
+                    if (trace_path) {
+                        if (!r->warp_trace && D->p_cuMemAlloc(&r->warp_trace, trace_bytes) != CUDA_SUCCESS) r->warp_trace = 0;
+                        if (r->warp_trace) { D->p_cuMemsetD8Async(r->warp_trace, 0, trace_bytes, q); b.warp_trace = (unsigned long long *)r->warp_trace; }
+                    }
+                    if (st == CHAOS_OK) st = launch(r, r->k_pass_b[p], r->blocks_pass_b[p], (int)r->pass_threads, r->refill_smem, &b, q);
+                    if (trace_path && r->warp_trace && st == CHAOS_OK) {
+                        std::vector<unsigned long long> host(trace_bytes / sizeof(unsigned long long));
+                        D->p_cuStreamSynchronize(q);
+                        if (D->p_cuMemcpyDtoH(host.data(), r->warp_trace, trace_bytes) == CUDA_SUCCESS) {
+                            FILE *f = fopen(trace_path, "wb");
+                            if (f) { fwrite(host.data(), 1, trace_bytes, f); fclose(f); }
+                        }
+                    }
+                    b.warp_trace = nullptr;
+                }
+                D->p_cuEventRecord(r->strand_ev_b[s], q);
+                if (exporting && b.n_tiles && st == CHAOS_OK) {
+                    b.phase = 3u;
+                    st = launch(r, r->k_pass_c[p], r->blocks_pass_c[p], (int)r->pass_threads, 0, &b, q);
+                    const int replay_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);
+                    if (st == CHAOS_OK) st = launch(r, r->k_replay, replay_grid, 256, 0, &b, q);
+                }
+                if (s) D->p_cuEventRecord(r->strand_ev_done[s], q);
             }
-            a.warp_trace = nullptr;
             if (a.late_tiles && st == CHAOS_OK) {
-                /* every tile pass B did not export is final: stream the frame out now, next to passes C and D */
-                D->p_cuEventRecord(r->ev[5], r->stream);
-                D->p_cuStreamWaitEvent(r->stream2, r->ev[5], 0);
+                /* every tile pass B did not export is final: stream the frame out once every strand's pass B is over,
+                 * next to passes C and D */
+                for (uint32_t s = 0; s < G; ++s) D->p_cuStreamWaitEvent(r->stream2, r->strand_ev_b[s], 0);
                 D->p_cuEventRecord(r->ev[6], r->stream2);
                 st = launch_compose(r, m, r->stream2);
                 D->p_cuEventRecord(r->ev[7], r->stream2);
                 early_compose = st == CHAOS_OK;
             }
-            if (a.exp.capacity) {
-                a.phase = 3u;
-                if (st == CHAOS_OK) st = launch(r, r->k_pass_c[p], r->blocks_pass_c[p], 256, 0, &a);
-                const int replay_grid = (int)std::min<uint64_t>((a.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);
-                if (st == CHAOS_OK) st = launch(r, r->k_replay, replay_grid, 256, 0, &a);
-            }
+            for (uint32_t s = 1; s < G; ++s) D->p_cuStreamWaitEvent(r->stream, r->strand_ev_done[s], 0);   /* join */
         }
         if (st != CHAOS_OK) return st;
     }
@@ -1053,7 +1120,7 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
     a.in = (const chaos_pixel_info *)r->buf[0].ptr; a.in_pitch = r->buf[0].pitch;   /* input = primary */
     a.out = (chaos_pixel_info *)r->buf[1].ptr; a.out_pitch = r->buf[1].pitch;       /* output = secondary */
     r->stats.kernel_launches = 0;
-    CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters), r->stream);
+    CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters) * CHAOS_MAX_STRANDS, r->stream);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
     if (a.n_tiles) {

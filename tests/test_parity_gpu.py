@@ -377,6 +377,7 @@ def test_exported_rounds_change_nothing(cu, provider, case):
     out = {}
     for ex in (0, 1):
         os.environ["CHAOS_EXPORT"] = str(ex)
+        os.environ["CHAOS_STRANDS"] = "1"         # one pass chain: the launch counts below are per chain
         try:
             provider.getRenderer("test", False)   # drop the active renderer so the knob is re-read
             r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
@@ -385,8 +386,40 @@ def test_exported_rounds_change_nothing(cu, provider, case):
             out[ex] = (r.downloadRecords(), st.pixel_iterations, st.samples, r.outputRGBA(), st.skipped_iterations, st.kernel_launches)
         finally:
             os.environ.pop("CHAOS_EXPORT", None)
+            os.environ.pop("CHAOS_STRANDS", None)
     helpers.assert_records_equal(out[1][0], out[0][0], case["name"] + " exported vs kept")
     assert out[1][1] == out[0][1] and out[1][2] == out[0][2]
     assert (out[1][3] == out[0][3]).all()
     assert out[0][5] == 5
     assert out[1][5] == (8 if 3 <= round(case["maxSS"]) <= 10 else 5)
+
+
+# ---- strands (chaos_abi.cpp): a multi-pass frame cut into interleaved sets of row bands whose pass chains run next to
+# ---- each other on their own streams must give the records, counters and colours of the single chain, for every strand
+# ---- count, CTA size of the pass kernels, frame shape (ragged last band, fewer bands than strands) and module.
+STRAND_CASES = [EXPORT_CASES[0], EXPORT_CASES[1], EXPORT_CASES[3], EXPORT_CASES[5], EXPORT_CASES[6],
+                dict(name="st_small_a4_f64", fractal="mandelbrot", W=333, H=130, image=cases.seg(-0.5, 0.0, 2.0, 333, 130), maxIter=2100,
+                     maxSS=4.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10)]
+
+
+@pytest.mark.parametrize("case", STRAND_CASES, ids=_ids(STRAND_CASES))
+def test_strands_change_nothing(cu, provider, case):
+    out = {}
+    for key, (strands, threads) in {"one": (1, 256), "two": (2, 256), "three": (3, 128), "eight": (8, 64)}.items():
+        os.environ["CHAOS_STRANDS"] = str(strands)
+        os.environ["CHAOS_PASS_THREADS"] = str(threads)
+        try:
+            provider.getRenderer("test", False)   # drop the active renderer so the knobs are re-read
+            r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+            r.renderQuality(helpers.model_for(cu, case))
+            st = r.stats()
+            out[key] = (r.downloadRecords(), st.pixel_iterations, st.samples, r.outputRGBA(), st.kernel_launches)
+        finally:
+            os.environ.pop("CHAOS_STRANDS", None)
+            os.environ.pop("CHAOS_PASS_THREADS", None)
+    for key in ("two", "three", "eight"):
+        helpers.assert_records_equal(out[key][0], out["one"][0], case["name"] + " strands " + key)
+        assert out[key][1] == out["one"][1] and out[key][2] == out["one"][2]
+        assert (out[key][3] == out["one"][3]).all()
+    if case["H"] >= 1000:
+        assert out["two"][4] > out["one"][4]      # the frame really ran as several chains
