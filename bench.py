@@ -236,7 +236,7 @@ def run_ours(args, wl, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.engine is not None:
         os.environ["CHAOS_ENGINE"] = str(args.engine)
-    prov = cu.CudaFractalRendererProvider(device=local)
+    prov = cu.CudaFractalRendererProvider(kernels_dir=os.environ.get("CHAOS_KERNELS_DIR"), device=local)   # (diagnostic builds)
     r = prov.getRenderer(wl["fractal"], False)
     if wl["fractal"] == "julia":
         r.setFractalCustomParams("%r;%r" % tuple(wl["julia_c"]))

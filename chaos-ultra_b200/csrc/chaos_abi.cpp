@@ -347,6 +347,11 @@ struct chaos_renderer {
     /* threads per CTA of the persistent pass kernels (warps are independent there): a CTA gives its SM share back only
      * when its last warp is done, so smaller CTAs let the next pass in sooner */
     uint32_t pass_threads = 256;
+    /* orbit pool of the independent-orbit passes (chaos_render_args::pool): one per strand, allocated by the first frame */
+    CUdeviceptr pool[CHAOS_MAX_STRANDS] = {};
+    uint32_t pool_capacity = 0;
+    uint32_t pool_min_lanes = 20;
+    uint32_t pool_epoch = 0;
     CUstream strand_stream[CHAOS_MAX_STRANDS] = {};
     CUevent strand_ev_b[CHAOS_MAX_STRANDS] = {}, strand_ev_done[CHAOS_MAX_STRANDS] = {};
     uint32_t overlap_compose = 1;
@@ -558,6 +563,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (ex) r->export_enabled = (uint32_t)atoi(ex) ? 1u : 0u;
     const char *sn = getenv("CHAOS_STRANDS");     /* 1 = the passes of a multi-sample frame run one after the other */
     if (sn) r->strands = (uint32_t)std::min(std::max(atoi(sn), 1), CHAOS_MAX_STRANDS);
+    const char *pm = getenv("CHAOS_POOL_MIN");    /* 0 = orbits never change warps */
+    if (pm) r->pool_min_lanes = (uint32_t)std::min(std::max(atoi(pm), 0), 32);
     const char *pt = getenv("CHAOS_PASS_THREADS");
     if (pt && (atoi(pt) == 32 || atoi(pt) == 64 || atoi(pt) == 128 || atoi(pt) == 256)) r->pass_threads = (uint32_t)atoi(pt);
     const char *sc = getenv("CHAOS_SHORTCUTS");   /* 0 = every trip executed and tested, as the reference does */
@@ -620,6 +627,24 @@ static bool ensure_export(chaos_renderer *r, uint32_t n_tiles)
     x.tile = (uint32_t *)p[0]; x.first = (uint32_t *)p[1]; x.et = (uint32_t *)p[2];
     x.iters = (unsigned long long *)p[3]; x.skipped = (unsigned long long *)p[4];
     return true;
+}
+
+/* the pool of strand s; 0 if it cannot be had (the passes then run without) */
+static CUdeviceptr ensure_pool(chaos_renderer *r, uint32_t s)
+{
+    if (!r->pool_min_lanes) return 0;
+    if (!r->pool_capacity) {
+        int most = std::max(r->blocks_main_f, r->blocks_main_d) * 256;
+        for (int p = 0; p < 2; ++p) most = std::max(most, std::max(r->blocks_pass_a[p], r->blocks_pass_c[p]) * (int)r->pass_threads);
+        const uint32_t warps = (uint32_t)most / 32u;   /* of the largest launch */
+        r->pool_capacity = CHAOS_POOL_SHARDS * 32u * ((warps + CHAOS_POOL_SHARDS - 1u) / CHAOS_POOL_SHARDS);
+    }
+    if (!r->pool[s]) {
+        const size_t bytes = (size_t)r->pool_capacity * CHAOS_POOL_STRIDE;
+        if (D->p_cuMemAlloc(&r->pool[s], bytes) != CUDA_SUCCESS) r->pool[s] = 0;
+        else if (D->p_cuMemsetD8Async(r->pool[s], 0, bytes, r->stream) != CUDA_SUCCESS) { D->p_cuMemFree(r->pool[s]); r->pool[s] = 0; }   /* no tag matches */
+    }
+    return r->pool[s];
 }
 
 static void free_frame_memory(chaos_renderer *r)
@@ -700,6 +725,7 @@ extern "C" chaos_status chaos_close(chaos_renderer *r)
     ctx_guard g(r->provider);
     if (r->stream) D->p_cuStreamSynchronize(r->stream);
     free_frame_memory(r);
+    for (uint32_t i = 0; i < CHAOS_MAX_STRANDS; ++i) if (r->pool[i]) D->p_cuMemFree(r->pool[i]);
     if (r->counters) D->p_cuMemFree(r->counters);
     if (r->counters_host) D->p_cuMemFreeHost(r->counters_host);
     for (int i = 0; i < 8; ++i) if (r->ev[i]) D->p_cuEventDestroy(r->ev[i]);
@@ -933,6 +959,20 @@ static chaos_status finish_frame(chaos_renderer *r)
         r->stats.samples += r->counters_host[s].samples;
         r->stats.skipped_iterations += r->counters_host[s].skipped_iterations;
     }
+    if (getenv("CHAOS_LANE_STATS")) {   /* diagnostics of modules built with -DCHAOS_LANE_STATS */
+        static const char *pass[4] = {"A", "B", "C", "main"}, *kind[2] = {"tested", "untested"};
+        for (int p = 0; p < 4; ++p) for (int t = 0; t < 2; ++t) {
+            unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (uint32_t s = 0; s < CHAOS_MAX_STRANDS; ++s) for (int k = 0; k < 8; ++k) v[k] += r->counters_host[s].lane_stats[p][t][k];
+            if (!v[CHAOS_LS_CAPACITY]) continue;
+            const double c = (double)v[CHAOS_LS_CAPACITY];   /* every lane added the block's length */
+            fprintf(stderr, "lane_stats pass %-4s %-8s lane-trips %.4g useful %.3f replay_wait %.3f fin_wait %.3f idle_queue %.3f idle_dry %.3f (mid-block ends %.3f) blocks %llu passes %llu\n",
+                    pass[p], kind[t], c, v[CHAOS_LS_USEFUL] / c, v[CHAOS_LS_REPLAY_WAIT] / c, v[CHAOS_LS_FIN_WAIT] / c,
+                    v[CHAOS_LS_IDLE_QUEUE] / c, v[CHAOS_LS_IDLE_DRY] / c,
+                    1.0 - (double)(v[CHAOS_LS_USEFUL] + v[CHAOS_LS_REPLAY_WAIT] + v[CHAOS_LS_FIN_WAIT] + v[CHAOS_LS_IDLE_QUEUE] + v[CHAOS_LS_IDLE_DRY]) / c,
+                    v[CHAOS_LS_BLOCKS], v[CHAOS_LS_PASSES]);
+        }
+    }
     return CHAOS_OK;
 }
 
@@ -985,6 +1025,8 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         if (sync_kernel) {
             st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a);
         } else if (S0 <= 1u) {
+            a.pool = (unsigned char *)ensure_pool(r, 0);
+            a.pool_capacity = r->pool_capacity; a.pool_min_lanes = r->pool_min_lanes; a.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
             st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, 0, &a);
         } else {
             /* pass A: sample 0 of every pixel; classify + order: expected-longest tiles first; pass B: the other rounds,
@@ -1002,11 +1044,15 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                 if (D->p_cuMemsetD32Async(r->late_tiles, 0u, (frame_tiles + 31u) / 32u, r->stream) != CUDA_SUCCESS)
                     return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed");
             }
-            if (G > 1u) D->p_cuEventRecord(r->ev[4], r->stream);     /* counters and bitmap are clear */
+            for (uint32_t s = 0; s < G; ++s) ensure_pool(r, s);      /* (a new pool is cleared on r->stream) */
+            if (G > 1u) D->p_cuEventRecord(r->ev[4], r->stream);     /* counters, bitmap and pools are clear */
             uint32_t tile_base = 0;
+            a.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
             for (uint32_t s = 0; s < G && st == CHAOS_OK; ++s) {
                 CUstream q = r->strand_stream[s];
                 chaos_render_args b = a;
+                b.pool = (unsigned char *)ensure_pool(r, s);
+                b.pool_capacity = r->pool_capacity; b.pool_min_lanes = r->pool_min_lanes;
                 if (G > 1u) {
                     b.part_index = r->part_index + r->part_count * s;
                     b.part_count = r->part_count * G;
@@ -1197,6 +1243,21 @@ extern "C" chaos_status chaos_download_records(chaos_renderer *r, void *dst, siz
     CUresult e = D->p_cuMemcpy2D(&c);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemcpy2D failed: %s", cu_err_name(e));
     return CHAOS_OK;
+}
+
+/* diagnostics (not in the public header): the device counters as they are right now, also while a frame is running --
+ * callable from another thread; tools/pool_watch.py uses it to look at a frame that does not end */
+extern "C" int chaos_debug_peek_counters(chaos_renderer *r, void *dst, size_t bytes)
+{
+    if (!r || !r->counters || !dst) return -1;
+    ctx_guard g(r->provider);
+    CUstream q = nullptr;
+    if (D->p_cuStreamCreate(&q, CU_STREAM_NON_BLOCKING) != CUDA_SUCCESS) return -2;
+    const size_t n = std::min(bytes, sizeof(chaos_counters) * CHAOS_MAX_STRANDS);
+    CUresult e = D->p_cuMemcpyDtoHAsync(dst, r->counters, n, q);
+    if (e == CUDA_SUCCESS) e = D->p_cuStreamSynchronize(q);
+    D->p_cuStreamDestroy(q);
+    return e == CUDA_SUCCESS ? (int)sizeof(chaos_counters) : -3;
 }
 
 extern "C" chaos_status chaos_get_stats(const chaos_renderer *r, chaos_stats *out)

@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 18u
+#define CHAOS_MODULE_ABI 20u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -35,6 +35,7 @@ struct chaos_pixel_info {
 
 /* device counters, one block per renderer (zeroed by the host before each render call) */
 #define CHAOS_COST_BUCKETS 37
+#define CHAOS_POOL_SHARDS 128   /* the orbit pool is this many independent rings (warp w uses ring w % shards) */
 struct chaos_counters {
     unsigned int next_tile;             /* work-stealing cursor over vote tiles */
     unsigned int next_tile_b;           /* pass B: cursor from the expensive end of tile_order (fast frames: the sampling pass' cursor) */
@@ -47,7 +48,20 @@ struct chaos_counters {
     unsigned long long skipped_iterations; /* part of pixel_iterations that was proven, not executed (exact recurrence) */
     unsigned int bucket_count[CHAOS_COST_BUCKETS + 3];  /* tiles per cost class (chaosClassifyTiles) */
     unsigned int bucket_cursor[CHAOS_COST_BUCKETS + 3]; /* fill position per class (chaosOrderTiles) */
+    /* orbit pool of the independent-orbit passes ([0] pass A or the single launch, [1] pass C), see chaos_render_args::pool */
+    struct { unsigned int live, reserved, head, pad; } pool[2][CHAOS_POOL_SHARDS];
+    /* diagnostics, modules built with -DCHAOS_LANE_STATS only (host: CHAOS_LANE_STATS=1 prints them): lane-trips of the
+     * escape loop by what the lane was doing, [pass A/B/C/main][tested, untested][CHAOS_LS_*] */
+    unsigned long long lane_stats[4][2][8];
 };
+#define CHAOS_LS_CAPACITY 0   /* 32 x trips the warp spent in the block */
+#define CHAOS_LS_USEFUL 1     /* trips the lanes advanced */
+#define CHAOS_LS_REPLAY_WAIT 2 /* lanes waiting for a tested block */
+#define CHAOS_LS_FIN_WAIT 3   /* lanes with a finished orbit waiting for a scheduling pass */
+#define CHAOS_LS_IDLE_QUEUE 4 /* empty lanes while the queue still had work */
+#define CHAOS_LS_IDLE_DRY 5   /* empty lanes after the queue ran dry */
+#define CHAOS_LS_BLOCKS 6     /* blocks */
+#define CHAOS_LS_PASSES 7     /* scheduling passes */
 
 /* Tiles that will (almost surely) use their whole sample budget leave pass B after a decision: their remaining rounds
  * are run by pass C as independent orbits of one GPU-wide pool, and pass D replays the decisions over the stored
@@ -97,7 +111,16 @@ struct chaos_render_args {
     unsigned long long *warp_trace;   /* NULL, or [warps][8]: per-warp timeline of the rounds engine (CHAOS_WARP_TRACE, diagnostics) */
     uint32_t sched_idle_lanes_indep;   /* engine 1: finished or empty lanes a warp lets accumulate before a scheduling pass, */
     uint32_t sched_idle_lanes_rounds;  /* independent orbits / sample rounds (1 = a pass after every block that ended an orbit) */
+    /* Orbit pool (independent-orbit passes).  Once the tile queue is dry a warp's lanes empty one by one while its
+     * instructions still take whole FP-pipe slots.  A warp left with fewer than pool_min_lanes running orbits parks them
+     * here (state and all) and ends; warps with empty lanes take parked orbits over.  So the drain of a pass runs in few,
+     * full warps, and SM share goes back to the next pass early.  NULL / 0 = off. */
+    unsigned char *pool;               /* [pool_capacity][CHAOS_POOL_STRIDE] */
+    uint32_t pool_capacity;            /* entries of all CHAOS_POOL_SHARDS rings together; a ring holds >= 32 x its warps */
+    uint32_t pool_min_lanes;
+    uint32_t pool_epoch;               /* distinguishes this launch's entries from older ones (host: += 2 per frame; pass C uses epoch + 1) */
 };
+#define CHAOS_POOL_STRIDE 128u
 
 struct chaos_compose_args {
     const chaos_pixel_info *in;

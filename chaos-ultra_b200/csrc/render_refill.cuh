@@ -121,6 +121,45 @@ static __device__ __forceinline__ bool take_scheduling_pass(bool fin, bool busy,
     return false;
 }
 
+#ifdef CHAOS_LANE_STATS
+struct lane_stats {
+    unsigned long long v[2][8];
+    uint32_t it0;
+    bool run0, tested0;
+    __device__ void init() { for (int i = 0; i < 2; ++i) for (int k = 0; k < 8; ++k) v[i][k] = 0ull; }
+    /* before a block: what every lane is about to do */
+    __device__ void before(bool busy, bool fin, bool wants_tested, bool tested, bool queue_empty, uint32_t it)
+    {
+        it0 = it; tested0 = tested;
+        run0 = busy && !fin && (tested || !wants_tested);
+        cls = run0 ? 0 : (busy && !fin) ? CHAOS_LS_REPLAY_WAIT : (busy && fin) ? CHAOS_LS_FIN_WAIT : queue_empty ? CHAOS_LS_IDLE_DRY : CHAOS_LS_IDLE_QUEUE;
+    }
+    int cls;
+    /* after it: `adv` = trips this lane advanced (a proven orbit: up to the proof) */
+    __device__ void after(uint32_t adv)
+    {
+        const uint32_t a = run0 ? adv : 0u;
+        const uint32_t L = __reduce_max_sync(CHAOS_FULL_MASK, a);
+        const int t = tested0 ? 0 : 1;
+        v[t][CHAOS_LS_CAPACITY] += L; v[t][CHAOS_LS_USEFUL] += a;
+        if (cls) v[t][cls] += L;
+        if ((threadIdx.x & 31u) == 0) v[t][CHAOS_LS_BLOCKS] += 1;
+    }
+    __device__ void pass() { if ((threadIdx.x & 31u) == 0) v[0][CHAOS_LS_PASSES] += 1; }
+    __device__ void flush(const chaos_render_args &a, int which)
+    {
+        for (int i = 0; i < 2; ++i) for (int k = 0; k < 8; ++k) {
+            unsigned long long x = v[i][k];
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(CHAOS_FULL_MASK, x, o);
+            if ((threadIdx.x & 31u) == 0 && x) atomicAdd(&a.counters->lane_stats[which][i][k], x);
+        }
+    }
+};
+#define CHAOS_LS(x) x
+#else
+#define CHAOS_LS(x)
+#endif
+
 template <class Orbit>
 static __device__ __forceinline__ bool run_block(Orbit &o, uint32_t &it, bool busy, bool tested, uint32_t nb, uint32_t max_iter)
 {
@@ -128,6 +167,54 @@ static __device__ __forceinline__ bool run_block(Orbit &o, uint32_t &it, bool bu
     const uint32_t lim = Orbit::kResumable ? min(it + (tested ? CHAOS_TESTED_BLOCK : nb), max_iter) : max_iter;
     const bool ended = o.run(it, lim, tested);
     return ended || it >= max_iter;
+}
+
+/* ---- orbit pool (chaos_render_args::pool) ------------------------------------------------------ */
+/* A bounded multi-producer multi-consumer ring per shard of warps.  Producers reserve a range of indices (never more than
+ * a ring's length ahead of the consumers' cursor) and consumers claim reserved indices, both with one compare-and-swap
+ * on a cursor; the hand-over of an entry goes through the entry's own state word (its last word):
+ *     free for lap g  ->  [producer writes the orbit]  ->  full, lap g  ->  [consumer reads it]  ->  free for lap g + 1
+ * so a producer never writes over an entry of the previous lap that its consumer has claimed but not read yet, and a
+ * consumer never reads an entry its producer has reserved but not written yet.  (Both waits are short and on a word of
+ * their own.  Publishing through one common counter in reservation order made thousands of warps spin on one word, and
+ * a single ring made them retry their compare-and-swap against each other -- O(warps^2) atomics, frames 10x slower.
+ * Tags without the "free" state let a producer lap a slow consumer when the SM's store path was backed up behind the
+ * compose kernel's PCIe writes: frames that never ended.)  The word carries the launch's epoch, so a ring is never
+ * reset: whatever an older launch left there reads as "free for lap 0".  A ring holds 32 x its warps entries -- every
+ * orbit its warps can hold at once.
+ * `live` counts the warps of the shard that have not ended.  A warp ends by decrementing it; the one that brings it to
+ * zero looks at the ring once more and stays if something is parked, so a parked orbit is always picked up. */
+#define CHAOS_PARK_COOLDOWN 8u   /* scheduling passes a warp that parked waits before it parks again */
+template <class Orbit> struct parked_orbit {
+    Orbit o;
+    uint32_t it, px, py, tile, rnd;
+};
+#define CHAOS_POOL_TAG_OFFSET (CHAOS_POOL_STRIDE - 4u)   /* the tag is the entry's last word */
+struct pool_ctl_ref {
+    unsigned int *live, *reserved, *head;
+};
+/* state word of entry `index`: full = false: free for this index' lap; true: holds this index' orbit */
+static __device__ __forceinline__ uint32_t pool_state(uint32_t epoch, uint32_t index, uint32_t ring_size, bool full)
+{
+    return (epoch << 8) | ((2u * (index / ring_size) + (full ? 1u : 0u)) & 0xffu);
+}
+static __device__ __forceinline__ unsigned int ld_volatile(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+#ifdef CHAOS_POOL_DEBUG   /* diagnostics: name the loop that does not end */
+#define CHAOS_SPIN_GUARD(n, what, ...) if (++(n) >= 20000000u) { printf("pool spin: " what "\n", __VA_ARGS__); break; }
+#else
+#define CHAOS_SPIN_GUARD(n, what, ...)
+#endif
+/* lane 0: claim up to `want` reserved entries; returns how many, first index in `base` */
+static __device__ __forceinline__ uint32_t pool_claim(const pool_ctl_ref &c, uint32_t want, uint32_t &base)
+{
+    uint32_t spins = 0; (void)spins;
+    for (;;) {
+        const unsigned int h = ld_volatile(c.head), p = ld_volatile(c.reserved);
+        if (p <= h) return 0u;
+        const uint32_t take = min(want, p - h);
+        if (atomicCAS(c.head, h, h + take) == h) { base = h; return take; }
+        CHAOS_SPIN_GUARD(spins, "claim head %u reserved %u", h, p);
+    }
 }
 
 /* ---- independent orbits ---------------------------------------------------------------------- */
@@ -163,12 +250,44 @@ static __device__ void render_main_independent(const chaos_render_args &a)
     uint32_t pend = 0, x0 = 0, y0 = 0, cur_tile = 0, cur_round = 0;   /* warp-uniform: the tile being handed out */
     uint32_t waited = 0;
     unsigned long long iters = 0, nsamples = 0, skipped = 0;
+    /* orbit pool: only orbits that can be suspended can change warps */
+    typedef parked_orbit<Orbit> parked_t;
+    static_assert(sizeof(parked_t) <= CHAOS_POOL_TAG_OFFSET, "parked orbit does not fit a pool entry");
+    const bool pooling = Orbit::kResumable && a.pool != nullptr && a.pool_min_lanes > 0u;
+    /* One ring per shard of warps: with a single ring thousands of warps that park and claim at the same moment (the
+     * queue runs dry for all of them at once) retry their compare-and-swap on one word -- O(warps^2) atomics, frames 10x
+     * slower.  The last warp alive of a shard keeps what is left of it. */
+    const uint32_t shard = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) % CHAOS_POOL_SHARDS;
+    const uint32_t ring_size = a.pool_capacity / CHAOS_POOL_SHARDS;
+    unsigned char *const ring = a.pool + (size_t)shard * ring_size * CHAOS_POOL_STRIDE;
+    const pool_ctl_ref pc = {&a.counters->pool[kExport ? 1 : 0][shard].live, &a.counters->pool[kExport ? 1 : 0][shard].reserved,
+                             &a.counters->pool[kExport ? 1 : 0][shard].head};
+    const uint32_t pool_epoch = a.pool_epoch + (kExport ? 1u : 0u);
+    bool keep_all = false;                                   /* this warp is the launch's last one: it parks nothing (any more) */
+    uint32_t park_cooldown = 0;
+    uint32_t stay_spins = 0; (void)stay_spins;
+    if (pooling && lane == 0) atomicAdd(pc.live, 1u);
 
+    CHAOS_LS(lane_stats ls; ls.init();)
+    uint32_t loop_spins = 0; (void)loop_spins;
     for (;;) {
+#ifdef CHAOS_POOL_DEBUG
+        if (++loop_spins >= 3000000u) {
+            if (lane == 0) printf("main loop: warp %u shard %u busy %x fin %x queue_empty %d keep_all %d head %u reserved %u live %u it %u tested %d wants %x\n",
+                                  (blockIdx.x * blockDim.x + threadIdx.x) >> 5, shard, __ballot_sync(1u, 1), 0u, (int)queue_empty, (int)keep_all,
+                                  ld_volatile(pc.head), ld_volatile(pc.reserved), ld_volatile(pc.live), it, (int)tested, 0u);
+            break;
+        }
+#endif
+        CHAOS_LS(ls.before(busy, fin, o.wants_tested(), tested, queue_empty, it);)
         fin |= run_block(o, it, busy && !fin, tested, nb, max_iter);
+        CHAOS_LS(ls.after((fin ? it - o.skipped() : it) - ls.it0);)
         tested = __any_sync(CHAOS_FULL_MASK, busy && !fin && o.wants_tested());
-        if (!take_scheduling_pass(fin, busy, a.sched_idle_lanes_indep, waited) && !first) continue;
+        /* queue dry: a pass after every block while lanes are empty (it is cheap then: a look at the pool) */
+        const bool drain_pass = pooling && queue_empty && __any_sync(CHAOS_FULL_MASK, !busy || fin);
+        if (!take_scheduling_pass(fin, busy, a.sched_idle_lanes_indep, waited) && !first && !drain_pass) continue;
         first = false;
+        CHAOS_LS(ls.pass();)
         if (fin) {
             fin = false;
             uint32_t et = o.finish(it, max_iter);
@@ -232,10 +351,97 @@ static __device__ void render_main_independent(const chaos_render_args &a)
             }
             pend &= ~__reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
         }
+        if (pooling && queue_empty) {
+            if (park_cooldown) --park_cooldown;
+            for (int again = 0; again < 2; ++again) {
+                /* empty lanes take parked orbits over */
+                const uint32_t idle = __ballot_sync(CHAOS_FULL_MASK, !busy);
+                if (idle) {
+                    uint32_t base = 0, take = 0;
+                    if (lane == 0) take = pool_claim(pc, (uint32_t)__popc(idle), base);
+                    take = __shfl_sync(CHAOS_FULL_MASK, take, 0);
+                    base = __shfl_sync(CHAOS_FULL_MASK, base, 0);
+                    const uint32_t rank = __popc(idle & lanemask_lt());
+                    if (!busy && rank < take) {
+                        union { parked_t rec; uint4 w[(sizeof(parked_t) + 15u) / 16u]; } u;
+                        const unsigned char *entry = ring + (size_t)((base + rank) % ring_size) * CHAOS_POOL_STRIDE;
+                        const uint32_t want = pool_state(pool_epoch, base + rank, ring_size, true);
+                        uint32_t spins = 0; (void)spins;
+                        while (ld_volatile(reinterpret_cast<const unsigned int *>(entry + CHAOS_POOL_TAG_OFFSET)) != want) {
+                            CHAOS_SPIN_GUARD(spins, "tag shard %u index %u want %x have %x head %u reserved %u", shard, base + rank, want,
+                                             ld_volatile(reinterpret_cast<const unsigned int *>(entry + CHAOS_POOL_TAG_OFFSET)), ld_volatile(pc.head), ld_volatile(pc.reserved));
+                        }
+                        __threadfence();
+                        const uint4 *src = reinterpret_cast<const uint4 *>(entry);
+#pragma unroll
+                        for (uint32_t k = 0; k < (sizeof(parked_t) + 15u) / 16u; ++k) u.w[k] = __ldcg(src + k);
+                        o = u.rec.o; it = u.rec.it; px = u.rec.px; py = u.rec.py; tile = u.rec.tile; rnd = u.rec.rnd;
+                        __threadfence();            /* read before the entry is handed back */
+                        *reinterpret_cast<volatile unsigned int *>(const_cast<unsigned char *>(entry) + CHAOS_POOL_TAG_OFFSET) =
+                            pool_state(pool_epoch, base + rank + ring_size, ring_size, false);
+                        busy = true;
+                        tested = tested || o.wants_tested();
+                    }
+                }
+                /* Too few orbits left for a whole warp's pipe slots: park them all, then claim a warpful -- warps that park
+                 * at about the same time repack their orbits into full warps, and the ones that come away empty end.  (No
+                 * orbit waits in the pool for long: whoever parks claims right afterwards.)  A warp that stays thin all the
+                 * same leaves it at that for a while. */
+                const uint32_t running = __ballot_sync(CHAOS_FULL_MASK, busy);
+                const uint32_t n_run = (uint32_t)__popc(running);
+                if (again || !n_run || n_run >= a.pool_min_lanes || keep_all || park_cooldown) break;
+                park_cooldown = CHAOS_PARK_COOLDOWN;
+                uint32_t start = 0xffffffffu;
+                if (lane == 0) {             /* reserve a range of the ring (a full ring just stops taking orbits) */
+                    for (;;) {
+                        const unsigned int r = ld_volatile(pc.reserved);
+                        if (r + n_run - ld_volatile(pc.head) > ring_size) break;
+                        if (atomicCAS(pc.reserved, r, r + n_run) == r) { start = r; break; }
+                    }
+                }
+                start = __shfl_sync(CHAOS_FULL_MASK, start, 0);
+                if (start == 0xffffffffu) break;
+                if (busy) {
+                    const uint32_t index = start + __popc(running & lanemask_lt());
+                    unsigned char *entry = ring + (size_t)(index % ring_size) * CHAOS_POOL_STRIDE;
+                    /* the entry is free once the consumer of the previous lap has read it; anything from an older launch is free */
+                    if (index >= ring_size) {
+                        const uint32_t free_now = pool_state(pool_epoch, index, ring_size, false);
+                        uint32_t spins = 0; (void)spins;
+                        while (ld_volatile(reinterpret_cast<const unsigned int *>(entry + CHAOS_POOL_TAG_OFFSET)) != free_now) {
+                            CHAOS_SPIN_GUARD(spins, "free shard %u index %u want %x have %x", shard, index, free_now,
+                                             ld_volatile(reinterpret_cast<const unsigned int *>(entry + CHAOS_POOL_TAG_OFFSET)));
+                        }
+                        __threadfence();
+                    }
+                    parked_t rec;
+                    rec.o = o; rec.it = it; rec.px = px; rec.py = py; rec.tile = tile; rec.rnd = rnd;
+                    *reinterpret_cast<parked_t *>(entry) = rec;
+                    __threadfence();
+                    *reinterpret_cast<volatile unsigned int *>(entry + CHAOS_POOL_TAG_OFFSET) = pool_state(pool_epoch, index, ring_size, true);
+                    busy = false;
+                }
+                __syncwarp();
+            }
+        }
         tested = __any_sync(CHAOS_FULL_MASK, tested);
-        if (!__any_sync(CHAOS_FULL_MASK, busy)) break;
+        if (!__any_sync(CHAOS_FULL_MASK, busy)) {
+            if (!pooling) break;
+            /* end of this warp -- unless it is the last one alive and something is still parked */
+            uint32_t stay = 0u;
+            if (lane == 0) {
+                if (atomicSub(pc.live, 1u) == 1u) {
+                    __threadfence();
+                    if (ld_volatile(pc.head) != ld_volatile(pc.reserved)) { atomicAdd(pc.live, 1u); stay = 1u; }
+                }
+            }
+            if (!__shfl_sync(CHAOS_FULL_MASK, stay, 0)) break;
+            keep_all = true;
+            CHAOS_SPIN_GUARD(stay_spins, "stay shard %u head %u reserved %u live %u", shard, ld_volatile(pc.head), ld_volatile(pc.reserved), ld_volatile(pc.live));
+        }
     }
     if (!kExport) flush_counters(a, iters, nsamples, skipped);
+    CHAOS_LS(ls.flush(a, kMode == 1 ? 0 : kMode == 2 ? 2 : 3);)
 }
 
 /* ---- general case: sample rounds with tile-wide votes ----------------------------------------- */
@@ -289,14 +495,18 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
     /* diagnostics (args.warp_trace): when the warp started, saw the queue run dry, and ended; what it did */
     unsigned long long tr_start = 0, tr_dry = 0, tr_blocks = 0, tr_passes = 0, tr_tiles = 0, tr_lane_blocks = 0;
     if (a.warp_trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_start));
+    CHAOS_LS(lane_stats ls; ls.init();)
 
     for (;;) {
         /* (1) iterate: one block of trips for the orbit this lane holds */
         if (a.warp_trace) { tr_blocks += 1; tr_lane_blocks += __popc(__ballot_sync(CHAOS_FULL_MASK, busy && !fin)); }
+        CHAOS_LS(ls.before(busy, fin, o.wants_tested(), tested, queue_empty, it);)
         fin |= run_block(o, it, busy && !fin, tested, nb, max_iter);
+        CHAOS_LS(ls.after((fin ? it - o.skipped() : it) - ls.it0);)
         tested = __any_sync(CHAOS_FULL_MASK, busy && !fin && o.wants_tested());
         if (!take_scheduling_pass(fin, busy, a.sched_idle_lanes_rounds, waited) && !first) continue;
         first = false;
+        CHAOS_LS(ls.pass();)
 
         if (a.warp_trace) tr_passes += 1;
         /* (2) retire finished orbits into their slot (:125-127) */
@@ -509,6 +719,7 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
         w[0] = tr_start; w[1] = tr_dry; w[2] = tr_end; w[3] = tr_blocks; w[4] = tr_passes; w[5] = tr_tiles; w[6] = tr_lane_blocks; w[7] = nsamples;
     }
     flush_counters(a, iters, nsamples, skipped);
+    CHAOS_LS(ls.flush(a, 1);)
 }
 
 /* pass B as a kernel body: one slot store per warp in dynamic shared memory */

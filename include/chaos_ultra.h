@@ -156,6 +156,10 @@ CHAOS_API chaos_status chaos_download_rgba(chaos_renderer *r, uint32_t *dst, siz
  * the debugging counterpart of copy2DFromDevToHost (CudaFractalRenderer.java:119-134) */
 CHAOS_API chaos_status chaos_download_records(chaos_renderer *r, void *dst, size_t dst_bytes);
 CHAOS_API chaos_status chaos_get_stats(const chaos_renderer *r, chaos_stats *out);
+/* Diagnostics (no counterpart in the reference): copy the renderer's device-side scheduler counters as they are right
+ * now into dst -- callable from a second thread while a render call is running (tools/pool_watch.py looks at a frame
+ * that does not end with it).  Returns the size of one counter block (there is one per strand), negative on error. */
+CHAOS_API int chaos_debug_peek_counters(chaos_renderer *r, void *dst, size_t bytes);
 
 /* Multi-GPU: this renderer renders and composes only the row bands b with b % part_count ==
  * part_index, bands being band_rows pixel rows high (a multiple of 4).  part_count 1 = whole frame. */
