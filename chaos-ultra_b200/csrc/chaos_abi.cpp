@@ -310,6 +310,7 @@ struct chaos_renderer {
     chaos_export exp_buf = {0, nullptr, nullptr, nullptr, nullptr, nullptr};
     CUdeviceptr late_tiles = 0;    /* one bit per vote tile of the frame, see chaos_render_args::late_tiles */   /* pass B -> pass C -> pass D (device memory) */
     uint32_t export_enabled = 1;
+    int export_all_below = -1;     /* see chaos_render_args::export_all_below; -1 = two tiles per slot of the pass B launch */
     CUfunction k_reuse_f = nullptr, k_reuse_d = nullptr;           /* pass R of a fast frame */
     int blocks_reuse_f = 0, blocks_reuse_d = 0;
     CUdeviceptr tile_key = 0, tile_order = 0;
@@ -559,6 +560,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     }
     const char *oc = getenv("CHAOS_OVERLAP_COMPOSE");   /* 0 = compose only after the last render pass */
     if (oc) r->overlap_compose = (uint32_t)atoi(oc) ? 1u : 0u;
+    const char *ea = getenv("CHAOS_EXPORT_ALL_BELOW");
+    if (ea) r->export_all_below = atoi(ea);
     const char *ex = getenv("CHAOS_EXPORT");      /* 0 = every tile keeps all its rounds in pass B */
     if (ex) r->export_enabled = (uint32_t)atoi(ex) ? 1u : 0u;
     const char *sn = getenv("CHAOS_STRANDS");     /* 1 = the passes of a multi-sample frame run one after the other */
@@ -902,6 +905,7 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
     a->shortcuts = r->shortcuts;
     a->sched_idle_lanes_indep = r->sched_idle_indep;
     a->sched_idle_lanes_rounds = r->sched_idle_rounds;
+
 }
 
 static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg, CUstream stream = nullptr)
@@ -960,6 +964,10 @@ static chaos_status finish_frame(chaos_renderer *r)
         r->stats.skipped_iterations += r->counters_host[s].skipped_iterations;
     }
     if (getenv("CHAOS_LANE_STATS")) {   /* diagnostics of modules built with -DCHAOS_LANE_STATS */
+        for (uint32_t s = 0; s < CHAOS_MAX_STRANDS; ++s)
+            if (r->counters_host[s].next_tile)
+                fprintf(stderr, "strand %u: tiles after sample 1: to pass B %u, exported (by the classifier or pass B) %u\n", s,
+                        r->counters_host[s].n_continuing, r->counters_host[s].n_exported);
         static const char *pass[4] = {"A", "B", "C", "main"}, *kind[2] = {"tested", "untested"};
         for (int p = 0; p < 4; ++p) for (int t = 0; t < 2; ++t) {
             unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1078,6 +1086,8 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     if (st == CHAOS_OK) st = launch(r, r->k_classify, tile_grid, 256, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &b, q);
                     b.phase = 2u;
+                    b.export_all_below = r->export_all_below >= 0 ? (uint32_t)r->export_all_below
+                                                                  : (uint32_t)r->blocks_pass_b[p] * (r->pass_threads / 32u) * 4u * 2u;
                     const size_t trace_bytes = (size_t)r->blocks_pass_b[p] * (r->pass_threads / 32u) * 8u * sizeof(unsigned long long);
                     if (trace_path) {
                         if (!r->warp_trace && D->p_cuMemAlloc(&r->warp_trace, trace_bytes) != CUDA_SUCCESS) r->warp_trace = 0;

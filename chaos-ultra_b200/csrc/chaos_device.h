@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 20u
+#define CHAOS_MODULE_ABI 23u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -43,6 +43,8 @@ struct chaos_counters {
     unsigned int claimed_b;             /* pass B: tiles claimed from either end */
     unsigned int n_exported;            /* pass B: tiles whose remaining rounds were handed to pass C (may exceed export.capacity: clamp) */
     unsigned int next_export_item;      /* pass C: work-stealing cursor over (exported tile, round) items */
+    unsigned int n_continuing;          /* chaosOrderTiles: tiles whose decision after sample 1 did not end them = pass B's tiles */
+    unsigned int pad0;
     unsigned long long pixel_iterations;
     unsigned long long samples;
     unsigned long long skipped_iterations; /* part of pixel_iterations that was proven, not executed (exact recurrence) */
@@ -118,6 +120,7 @@ struct chaos_render_args {
     unsigned char *pool;               /* [pool_capacity][CHAOS_POOL_STRIDE] */
     uint32_t pool_capacity;            /* entries of all CHAOS_POOL_SHARDS rings together; a ring holds >= 32 x its warps */
     uint32_t pool_min_lanes;
+    uint32_t export_all_below;         /* pass B exports every tile it gets when chaosClassifyTiles left it at most this many */
     uint32_t pool_epoch;               /* distinguishes this launch's entries from older ones (host: += 2 per frame; pass C uses epoch + 1) */
 };
 #define CHAOS_POOL_STRIDE 128u

@@ -31,6 +31,7 @@
 #ifndef CHAOS_RENDER_REFILL_CUH
 #define CHAOS_RENDER_REFILL_CUH
 
+#define CHAOS_TILE_DONE 0xffffffffu   /* tile_key of a tile chaosClassifyTiles finished (its decision after sample 1 ended it) */
 #ifndef CHAOS_REFILL_SLOTS
 #define CHAOS_REFILL_SLOTS 4
 #endif
@@ -239,8 +240,10 @@ static __device__ void render_main_independent(const chaos_render_args &a)
     sample_delta<Real>(0u, 0.f, dx0, dy0);                  /* sample 0 sits at offset 0/3 */
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
     const float spr = sqrtf(__fadd_rn(a.max_ss, -2.0f));
-    const uint32_t rounds_per_tile = kExport ? S0 - 2u : 1u;                 /* pass C: rounds 2 .. S0-1 */
-    const uint32_t n_items = kExport ? min(a.counters->n_exported, a.exp.capacity) * rounds_per_tile : a.n_tiles;
+    /* work items per tile: pass C rounds 2 .. S0-1; pass A rounds 0 and 1 (both exist whenever S0 >= 2: the first
+     * decision comes after sample 1, :128); one sample per pixel otherwise */
+    const uint32_t rounds_per_tile = kExport ? S0 - 2u : kProbe ? 2u : 1u;
+    const uint32_t n_items = kExport ? min(a.counters->n_exported, a.exp.capacity) * rounds_per_tile : a.n_tiles * rounds_per_tile;
     unsigned int *cursor = kExport ? &a.counters->next_export_item : &a.counters->next_tile;
 
     Orbit o;
@@ -298,9 +301,16 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                 export_et(a, tile, rnd)[px] = et;
                 atomicAdd(&a.exp.iters[(size_t)tile * CHAOS_EXPORT_ROUNDS + rnd], (unsigned long long)it);
                 if (o.skipped()) atomicAdd(&a.exp.skipped[(size_t)tile * CHAOS_EXPORT_ROUNDS + rnd], (unsigned long long)o.skipped());
-            } else if (kProbe) { /* pass A: park the escape time in the record for pass B, with the orbit's trip count and what it
-                                  * cost (a proven never-ending orbit is cheap) for chaosClassifyTiles */
-                store_record(record_at(a.out, a.out_pitch, px, py), __uint_as_float(et), __uint_as_float(it), 0u, __uint_as_float(it - o.skipped()));
+            } else if (kProbe) { /* pass A: park the escape times in the record for chaosClassifyTiles and pass B -- sample 0 in
+                                  * `value`, with the orbit's trip count and what it cost (a proven never-ending orbit is
+                                  * cheap); sample 1 in the `isReused` word */
+                chaos_pixel_info *rec = record_at(a.out, a.out_pitch, px, py);
+                if (rnd == 0u) {
+                    *reinterpret_cast<float2 *>(&rec->value) = make_float2(__uint_as_float(et), __uint_as_float(it));
+                    rec->weight_of_new_samples = __uint_as_float(it - o.skipped());
+                } else {
+                    rec->is_reused = et;
+                }
             }
             else          /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
                 store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
@@ -320,6 +330,10 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                     cur_round = 2u + (t - cur_tile * rounds_per_tile);
                     if (cur_round < a.exp.first[cur_tile]) continue;      /* pass B had taken this round already */
                     tile_origin(a, a.exp.tile[cur_tile], x0, y0);
+                } else if (kProbe) {
+                    cur_tile = t >> 1;
+                    cur_round = t & 1u;
+                    tile_origin(a, cur_tile, x0, y0);
                 } else {
                     cur_tile = t;
                     tile_origin(a, t, x0, y0);
@@ -342,7 +356,9 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                 } else {
                     px = x0 + (mypix & 7u);
                     py = y0 + (mypix >> 3);
-                    fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx0, dy0, cx, cy);
+                    Real dx = dx0, dy = dy0;
+                    if (kProbe) { sample_delta<Real>(cur_round, spr, dx, dy); rnd = cur_round; }
+                    fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx, dy, cx, cy);
                 }
                 o.start(cx, cy, ctx);
                 it = 0;
@@ -482,6 +498,12 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
     const float scf = a.max_ss;                               /* host guarantees >= 1 (:174) */
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(scf)));
     const float spr = sqrtf(__fadd_rn(scf, -2.0f));
+    const uint32_t n_cont = kResume ? a.counters->n_continuing : a.n_tiles;   /* tiles chaosClassifyTiles left for this pass */
+    /* Few tiles left (a frame whose tiles mostly ended after sample 1): this pass would be all latency -- a tile's rounds
+     * run one after the other here, each as long as its longest orbit, with most lanes of the GPU empty (c2: 0.4 ms at
+     * 6 % of the lanes).  Then every tile is exported as it arrives: its rounds run side by side in pass C.  Rounds that
+     * turn out not to exist are wasted work, which is why a frame with many such tiles (c2ex2) does not do it. */
+    const bool export_everything = n_cont <= a.export_all_below;
 
     for (uint32_t w = lane; w < sizeof(ws.hdr) / 4u; w += 32u) reinterpret_cast<uint32_t *>(ws.hdr)[w] = 0u;
     __syncwarp();
@@ -510,7 +532,7 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
 
         if (a.warp_trace) tr_passes += 1;
         /* (2) retire finished orbits into their slot (:125-127) */
-        const uint32_t touched = __reduce_or_sync(CHAOS_FULL_MASK, fin ? (1u << slot) : 0u);   /* slots that got a result */
+        uint32_t touched = __reduce_or_sync(CHAOS_FULL_MASK, fin ? (1u << slot) : 0u);   /* slots that got a result (or a new tile) */
         if (fin) {
             fin = false;
             const uint32_t et = o.finish(it, max_iter);
@@ -528,6 +550,7 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
         /* (3) per slot: decide every round that is complete and next in order (:128-150); issue further rounds, or
          *     finish the tile and take a new one */
         for (int k = 0; k < K; ++k) {
+          for (;;) {
             while ((touched >> k) & 1u) {                   /* only a slot that got a result can have completed a round */
                 const refill_slot_hdr &hk = ws.hdr[k];
                 const uint32_t act = hk.active, i = hk.dec, issued = hk.issued, inb = hk.inb;
@@ -540,7 +563,8 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                 const bool part = (inb >> lane) & 1u;
                 if (i < R && part) ws.sum[k][lane] += ws.et[k][i][lane];
                 const uint32_t sum = ws.sum[k][lane];
-                if (lane == 0) { iters += r_iters; skipped += r_skipped; nsamples += (unsigned long long)__popc(inb); }
+                /* (round 1 came with the tile: pass A ran and counted it) */
+                if (lane == 0 && !(kResume && i == 1u)) { iters += r_iters; skipped += r_skipped; nsamples += (unsigned long long)__popc(inb); }
                 bool blocked = false;                       /* some pixel rules out even the loosest stop rule */
                 if (decision_entered(adaptive, i, S)) {
                     vote_preds p = {true, true, true, false};
@@ -562,7 +586,7 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                  * orbits of one GPU-wide pool (a tile of 32 never-ending pixels is 7 x 32 full-length orbits -- seven waves
                  * of this warp's lanes, the whole launch's critical path when it stays here), pass D replays the decisions. */
                 uint32_t e = 0xffffffffu;
-                if (kResume && i + 1u < S && blocked && S <= CHAOS_EXPORT_ROUNDS && issued == i + 1u && i >= 1u && a.exp.capacity) {
+                if (kResume && i + 1u < S && (blocked || export_everything) && S <= CHAOS_EXPORT_ROUNDS && issued == i + 1u && i >= 1u && a.exp.capacity) {
                     if (lane == 0) e = atomicAdd(&a.counters->n_exported, 1u);
                     e = __shfl_sync(CHAOS_FULL_MASK, e, 0);
                     if (e >= a.exp.capacity) e = 0xffffffffu;
@@ -619,6 +643,7 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                     break;
                 }
             }
+            bool loaded = false;
             if (!ws.hdr[k].active && !queue_empty) {
                 uint32_t t = 0;
                 if (lane == 0) {
@@ -627,9 +652,9 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                          * the other slots from the cheap end: a warp then works on ONE heavy tile at a time (up to 7 x 32
                          * full-length orbits: seven waves of its 32 lanes) next to light ones, instead of four heavy tiles
                          * at once while other warps run dry -- measured on c2: SM busy time 3.9 .. 8.1 Mcycles before. */
-                        if (atomicAdd(&a.counters->claimed_b, 1u) >= a.n_tiles) t = 0xffffffffu;
+                        if (atomicAdd(&a.counters->claimed_b, 1u) >= n_cont) t = 0xffffffffu;
                         else if (k == 0) t = a.tile_order[atomicAdd(&a.counters->next_tile_b, 1u)];
-                        else t = a.tile_order[a.n_tiles - 1u - atomicAdd(&a.counters->tail_tile_b, 1u)];
+                        else t = a.tile_order[n_cont - 1u - atomicAdd(&a.counters->tail_tile_b, 1u)];
                     } else {
                         t = atomicAdd(&a.counters->next_tile, 1u);
                     }
@@ -645,12 +670,18 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                     const bool in = (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height;
                     const uint32_t inb = __ballot_sync(CHAOS_FULL_MASK, in);
                     uint32_t first_round = 0u, upto = 1u;
-                    if (kResume) {           /* sample 0 was taken by pass A; its escape time sits in the record */
-                        const uint32_t et0 = in ? __float_as_uint(record_at(a.out, a.out_pitch, x0 + (lane & 7u), y0 + (lane >> 3))->value) : 0u;
-                        ws.sum[k][lane] = et0;
+                    if (kResume) {           /* samples 0 and 1 were taken by pass A; their escape times sit in the record */
+                        uint32_t et0 = 0u, et1 = 0u;
+                        if (in) {
+                            const float4 rec = *reinterpret_cast<const float4 *>(record_at(a.out, a.out_pitch, x0 + (lane & 7u), y0 + (lane >> 3)));
+                            et0 = __float_as_uint(rec.x); et1 = __float_as_uint(rec.z);
+                        }
+                        ws.sum[k][lane] = et0;             /* round 1 is added when it is decided, below */
                         ws.et[k][0][lane] = et0;
+                        ws.et[k][1][lane] = et1;
                         first_round = 1u;
                         upto = 2u;
+                        loaded = true;
                     } else {
                         ws.sum[k][lane] = 0u;
                     }
@@ -658,7 +689,7 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                         refill_slot_hdr &h = ws.hdr[k];
                         h.tile = t; h.x0 = x0; h.y0 = y0; h.S = S0; h.dec = first_round; h.issued = min(upto, max(S0, first_round + 1u)); h.inb = inb;
                         uint32_t rm = 0u;
-                        for (uint32_t r = first_round; r < h.issued; ++r) {
+                        for (uint32_t r = first_round; r < h.issued && !kResume; ++r) {   /* (kResume: round 1 is complete already) */
                             h.pend[r % R] = inb;
                             h.left[r % R] = (uint32_t)__popc(inb);
                             rm |= 1u << (r % R);
@@ -669,6 +700,9 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                 }
             }
             __syncwarp();
+            if (!loaded) break;
+            touched |= 1u << k;                            /* round 1 came with the tile: decide it right away */
+          }
         }
 
         /* (4) refill: idle lanes take pending orbits, from any slot, earliest round first */
@@ -801,23 +835,74 @@ static __device__ void classify_tiles(const chaos_render_args &a)
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
+    const bool adaptive = (a.flags & CHAOS_FLAG_ADAPTIVE_SS) != 0u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < a.n_tiles; t += warps) {   /* one warp per tile, lane = pixel */
         uint32_t x0, y0;
         tile_origin(a, t, x0, y0);
         const uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
         const bool part = px < a.width && py < a.height;
-        uint32_t trips = 0, cost = 0;
+        uint32_t trips = 0, cost = 0, et0 = 0, et1 = 0;
         if (part) {
-            const float4 rec = *reinterpret_cast<const float4 *>(record_at(a.out, a.out_pitch, px, py));   /* pass A: (et, trips, -, cost) */
+            const float4 rec = *reinterpret_cast<const float4 *>(record_at(a.out, a.out_pitch, px, py));   /* pass A: (et0, trips0, et1, cost0) */
+            et0 = __float_as_uint(rec.x);
             trips = __float_as_uint(rec.y);
+            et1 = __float_as_uint(rec.z);
             cost = min(__float_as_uint(rec.w), 1u << 26);
+        }
+        /* the decision after sample 1 (:128-150), exactly as pass B takes it: most tiles of a frame end here, and those get
+         * their final record now; only the others go to pass B */
+        uint32_t S = S0;
+        bool blocked = false;        /* some pixel's mean is 0: the tile looks set to use its whole budget (see render_main_rounds) */
+        if (decision_entered(adaptive, 1u, S)) {
+            vote_preds p = {true, true, true, false};
+            if (part) {
+                float sm[CHAOS_ADAPTIVE_THRESHOLD];
+#pragma unroll
+                for (uint32_t q = 0; q < CHAOS_ADAPTIVE_THRESHOLD; ++q) sm[q] = 0.f;
+                sm[0] = __uint2float_rn(et0); sm[1] = __uint2float_rn(et1);
+                p = decision_preds(sm, 1u, et0 + et1);
+            }
+            const bool all_eq = __all_sync(CHAOS_FULL_MASK, p.eq);
+            const bool all_lt = __all_sync(CHAOS_FULL_MASK, p.lt);
+            const bool all_le = __all_sync(CHAOS_FULL_MASK, p.le);
+            S = decision_update(1u, S, all_eq, all_lt, all_le);
+            blocked = __any_sync(CHAOS_FULL_MASK, p.zero_mean && part);
+        }
+        if (2u >= S) {
+            if (part) store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn((et0 + et1) / S), __uint2float_rn(S), 0u, 0.f);
+            if (lane == 0) a.tile_key[t] = CHAOS_TILE_DONE;
+            continue;
+        }
+        /* a tile that goes on (S is still S0 then) and is set to use its whole budget skips pass B: its remaining rounds go
+         * to pass C as independent orbits, its decisions to pass D */
+        if (blocked && S <= CHAOS_EXPORT_ROUNDS && a.exp.capacity) {
+            uint32_t e = 0u;
+            if (lane == 0) e = atomicAdd(&a.counters->n_exported, 1u);
+            e = __shfl_sync(CHAOS_FULL_MASK, e, 0);
+            if (e < a.exp.capacity) {
+                export_et(a, e, 0u)[lane] = part ? et0 : 0u;
+                export_et(a, e, 1u)[lane] = part ? et1 : 0u;
+                if (lane == 0) {
+                    a.exp.tile[e] = t; a.exp.first[e] = 2u;
+                    a.tile_key[t] = CHAOS_TILE_DONE;
+                    if (a.late_tiles) {
+                        const uint32_t gt = (y0 >> 2) * a.tiles_x + (x0 >> 3);
+                        atomicOr(&a.late_tiles[gt >> 5], 1u << (gt & 31u));
+                    }
+                }
+                if (lane >= 2u && lane < CHAOS_EXPORT_ROUNDS) {
+                    a.exp.iters[(size_t)e * CHAOS_EXPORT_ROUNDS + lane] = 0ull;
+                    a.exp.skipped[(size_t)e * CHAOS_EXPORT_ROUNDS + lane] = 0ull;
+                }
+                continue;
+            }
         }
         const uint32_t first = __shfl_sync(CHAOS_FULL_MASK, trips, __ffs(__ballot_sync(CHAOS_FULL_MASK, part)) - 1);
         const bool uniform = __all_sync(CHAOS_FULL_MASK, !part || trips == first);
         const uint32_t total = __reduce_add_sync(CHAOS_FULL_MASK, cost);          /* <= 32 x 2^26 */
         if (lane == 0) {
-            const unsigned long long est = (unsigned long long)(total | 1u) * (uniform ? 1u : (S0 > 1u ? S0 - 1u : 1u));
+            const unsigned long long est = (unsigned long long)(total | 1u) * (uniform ? 1u : S - 1u);
             const uint32_t key = (uint32_t)__clzll((long long)est) - 27u;      /* est < 2^37: clzll in [27,63] -> key in [0,36] */
             a.tile_key[t] = key;
             atomicAdd(&hist[key], 1u);
@@ -835,12 +920,14 @@ static __device__ void order_tiles(const chaos_render_args &a)
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
         for (uint32_t j = 0; j < CHAOS_COST_BUCKETS; ++j) { base[j] = acc; acc += a.counters->bucket_count[j]; }
+        if (blockIdx.x == 0) a.counters->n_continuing = acc;
     }
     __syncthreads();
     /* a block owns a contiguous chunk of tiles */
     const uint32_t per_block = (a.n_tiles + gridDim.x - 1u) / gridDim.x;
     const uint32_t t0 = blockIdx.x * per_block, t1 = min(a.n_tiles, t0 + per_block);
-    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) atomicAdd(&cnt[a.tile_key[t]], 1u);
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x)
+        if (a.tile_key[t] != CHAOS_TILE_DONE) atomicAdd(&cnt[a.tile_key[t]], 1u);
     __syncthreads();
     for (uint32_t k = threadIdx.x; k < CHAOS_COST_BUCKETS; k += blockDim.x) {
         off[k] = cnt[k] ? base[k] + atomicAdd(&a.counters->bucket_cursor[k], cnt[k]) : 0u;
@@ -849,7 +936,7 @@ static __device__ void order_tiles(const chaos_render_args &a)
     __syncthreads();
     for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
         const uint32_t key = a.tile_key[t];
-        a.tile_order[off[key] + atomicAdd(&cnt[key], 1u)] = t;
+        if (key != CHAOS_TILE_DONE) a.tile_order[off[key] + atomicAdd(&cnt[key], 1u)] = t;
     }
 }
 

@@ -36,7 +36,7 @@ while not state["done"]:
             blk = buf[s * n:(s + 1) * n]
             head = blk[:24].view(np.uint32)
             print(" strand %d: next_tile %d next_b %d tail_b %d claimed_b %d n_exported %d next_export_item %d" % ((s,) + tuple(int(x) for x in head)))
-            off = 24 + 24 + 4 * 2 * 40     # cursors, 3 x u64, two bucket arrays
+            off = 32 + 24 + 4 * 2 * 40     # cursors, 3 x u64, two bucket arrays
             pool = blk[off:off + 2 * 128 * 16].view(np.uint32).reshape(2, 128, 4)
             for p in range(2):
                 bad = [(k, int(pool[p, k, 0]), int(pool[p, k, 1]), int(pool[p, k, 2])) for k in range(128) if pool[p, k, 0] or pool[p, k, 1] != pool[p, k, 2]]
