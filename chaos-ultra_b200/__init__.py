@@ -153,6 +153,7 @@ _API = {
     "chaos_download_rgba": (C.c_int, [_VP, _VP, C.c_size_t]),
     "chaos_download_records": (C.c_int, [_VP, _VP, C.c_size_t]),
     "chaos_get_stats": (C.c_int, [_VP, C.POINTER(_Stats)]),
+    "chaos_debug_peek_counters": (C.c_int, [_VP, _VP, C.c_size_t]),
     "chaos_set_partition": (C.c_int, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "chaos_set_output_target": (C.c_int, [_VP, C.c_uint64]),
     "chaos_last_error": (C.c_char_p, []),

@@ -29,7 +29,6 @@ while not state["done"]:
     elif time.time() - since > 8:
         lib = r._lib
         buf = np.zeros(1 << 20, dtype=np.uint8)
-        lib.chaos_debug_peek_counters.restype = C.c_int
         n = lib.chaos_debug_peek_counters(r._h, buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size))
         print("frame %d does not end; counters block = %d bytes" % (last, n))
         for s in range(2):
