@@ -185,7 +185,7 @@ static __device__ __forceinline__ bool run_block(Orbit &o, uint32_t &it, bool bu
  * orbit its warps can hold at once.
  * `live` counts the warps of the shard that have not ended.  A warp ends by decrementing it; the one that brings it to
  * zero looks at the ring once more and stays if something is parked, so a parked orbit is always picked up. */
-#define CHAOS_PARK_COOLDOWN 8u   /* scheduling passes a warp that parked waits before it parks again */
+#define CHAOS_PARK_COOLDOWN 4u   /* looks at the pool a warp that parked lets go by before it parks again */
 template <class Orbit> struct parked_orbit {
     Orbit o;
     uint32_t it, px, py, tile, rnd;
@@ -267,7 +267,8 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                              &a.counters->pool[kExport ? 1 : 0][shard].head};
     const uint32_t pool_epoch = a.pool_epoch + (kExport ? 1u : 0u);
     bool keep_all = false;                                   /* this warp is the launch's last one: it parks nothing (any more) */
-    uint32_t park_cooldown = 0;
+    uint32_t park_cooldown = 0, drain_wait = 0;
+    const uint32_t drain_interval = min(max(max_iter / (nb * 64u), 2u), 16u);   /* blocks */
     uint32_t stay_spins = 0; (void)stay_spins;
     if (pooling && lane == 0) atomicAdd(pc.live, 1u);
 
@@ -286,8 +287,12 @@ static __device__ void render_main_independent(const chaos_render_args &a)
         fin |= run_block(o, it, busy && !fin, tested, nb, max_iter);
         CHAOS_LS(ls.after((fin ? it - o.skipped() : it) - ls.it0);)
         tested = __any_sync(CHAOS_FULL_MASK, busy && !fin && o.wants_tested());
-        /* queue dry: a pass after every block while lanes are empty (it is cheap then: a look at the pool) */
-        const bool drain_pass = pooling && queue_empty && __any_sync(CHAOS_FULL_MASK, !busy || fin);
+        /* Queue dry: a look at the pool every few blocks while lanes are empty.  Not after every block: the orbits still
+         * running are the launch's critical path, and a pass (a few hundred instructions and a round trip to L2 for the
+         * ring's cursors) between any two blocks of a warp that runs alone nearly doubles the time its orbits take
+         * (c4 on 2 GPUs: 19 -> 23 ms).  The interval grows with the iteration limit: long orbits, long drain. */
+        bool drain_pass = false;
+        if (pooling && queue_empty && __any_sync(CHAOS_FULL_MASK, !busy || fin) && ++drain_wait >= drain_interval) { drain_pass = true; drain_wait = 0u; }
         if (!take_scheduling_pass(fin, busy, a.sched_idle_lanes_indep, waited) && !first && !drain_pass) continue;
         first = false;
         CHAOS_LS(ls.pass();)
