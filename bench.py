@@ -36,6 +36,14 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 A, FOV, REUSE, ZOOMING, ZOOM_IN = 1, 4, 8, 16, 32
 
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel(s), per frame, from one
+# `ncu --set full` capture of the same command (never measured in a bench run); workload -> (bytes, capture)
+NCU_TRAFFIC = {
+    "c2": (int((7.51 + 93.64 + 12.94 + 0.004 + 10.55 + 0.86) * 1e6), "profiles/r01f_passes_c2.txt: chaosPassA + chaosPassB + chaosPassC Double"),
+    "c3": (int((127.08 + 85.31 + 132.73 + 9.60) * 1e6), "profiles/r01b_fast_frame_c3.txt: chaosReusePassFloat + compose "
+           "(part of the 133 MB of records written and of the 33 MB frame stays in the 126 MB L2)"),
+}
+
 
 def seg(cx, cy, zoom, W, H):
     relW = 1.0 / float(H) * W
@@ -401,7 +409,9 @@ def run_ours(args, wl, rank, world, local):
             min_ops = 5 if wl["double"] else 6
             achieved = executed / world * min_ops / kernel_s
             out["roofline"] = {"bound": "fp64" if wl["double"] else "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9,
-                               "unit": "G FP-lane-ops/s", "frac": achieved / peak, "traffic": None,
+                               "unit": "G FP-lane-ops/s", "frac": achieved / peak,
+                               "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0] if world == 1 else None,
+                               "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1] if world == 1 else None,
                                "kernel": ("fractalRenderMain%s" if round(wl["maxSS"]) <= 1 else "chaosPassA%s + chaosPassB%s + chaosPassC%s (the iteration kernels of a multi-sample frame)").replace("%s", "Double" if wl["double"] else "Float"),
                                "peak_source": "measured in this run: bench_kernels/peak.cubin, independent FMA chains, best of 5 (not in MEASURED_PEAKS.json)",
                                "achieved_definition": "%d FP instructions x %d executed pixel-iterations per launch sequence / render-kernel time (lower bound of issued instructions)"
@@ -632,7 +642,8 @@ def run_zoom_ours(args, wl, rank, world, local):
             "gpu_launches": dev["launches"], "clocks": dev["clocks"],
             "device_ms_per_step": {"reuse_pass": dev["reuse_ms"] / args.steps, "sample_pass": (dev["render_ms"] - dev["reuse_ms"]) / args.steps,
                                    "compose_kernel": dev["compose_ms"] / args.steps},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
                          "kernel": "chaosReusePass* + compose (the two memory passes of a fast frame)", "peak_source": peak_src,
                          "algorithmic_bytes": "%d B/pixel x %d pixels per frame (reuse 16 R + 16 W, compose 16 R + 4 W)" % (HBM_BYTES_PER_PIXEL_FAST_FRAME, px),
                          "note": "the foveal disc and the pixels without history are resampled by a separate compute-bound launch (sample_pass), not part of this figure"},
