@@ -67,6 +67,12 @@
 
 #include "fractal.cuh"
 
+#ifndef CHAOS_SAVE_SHIFT
+#define CHAOS_SAVE_SHIFT 2   /* the kept state of the recurrence check is replaced at trip counts growing by 1 + 2^-shift.
+                              * Executed trips of c2 by shift: 0: 5.98 G, 1: 5.62 G, 2: 5.63 G, 3: 5.97 G, 4: 6.88 G, 5: 8.39 G
+                              * (a short distance to the kept state cannot span the longer periods) */
+#endif
+
 template <class Real> struct quad_bits;
 template <> struct quad_bits<float> {
     static constexpr bool kCanScale = false;
@@ -210,7 +216,7 @@ template <class Real> struct quadratic_orbit {
                 }
                 if (i >= next_save) {
                     sx = x; sy = y;
-                    next_save = i + max(kGroup, (i >> 2) & ~(kGroup - 1u));
+                    next_save = i + max(kGroup, (i >> CHAOS_SAVE_SHIFT) & ~(kGroup - 1u));
                 }
             }
         }
