@@ -237,7 +237,15 @@ static __device__ void render_main_independent(const chaos_render_args &a)
     const uint32_t nb = a.block_iters;
     const orbit_ctx ctx = {a.max_iter, a.shortcuts};
     Real dx0, dy0;
-    sample_delta<Real>(0u, 0.f, dx0, dy0);                  /* sample 0 sits at offset 0/3 */
+    sample_delta<Real>(0u, 0.f, dx0, dy0);                  /* sample 0 sits at offset 0/3, */
+    Real dx1, dy1;
+    sample_delta<Real>(1u, 0.f, dx1, dy1);                  /* sample 1 at 1/3 (a division: once per launch, not per orbit) */
+    /* pass C: the offsets of rounds 2 .. 9 (integer and float divisions each) once per CTA */
+    __shared__ Real s_dx[kExport ? CHAOS_EXPORT_ROUNDS : 1], s_dy[kExport ? CHAOS_EXPORT_ROUNDS : 1];
+    if (kExport) {
+        if (threadIdx.x < CHAOS_EXPORT_ROUNDS) sample_delta<Real>(threadIdx.x, sqrtf(__fadd_rn(a.max_ss, -2.0f)), s_dx[threadIdx.x], s_dy[threadIdx.x]);
+        __syncthreads();
+    }
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
     const float spr = sqrtf(__fadd_rn(a.max_ss, -2.0f));
     /* work items per tile: pass C rounds 2 .. S0-1; pass A rounds 0 and 1 (both exist whenever S0 >= 2: the first
@@ -355,8 +363,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                 tile = cur_tile;
                 Real cx, cy;
                 if (kExport) {
-                    Real dx, dy;
-                    sample_delta<Real>(cur_round, spr, dx, dy);
+                    const Real dx = s_dx[cur_round], dy = s_dy[cur_round];
                     fm.template plane_point<fused_plane_y<FractalT>::value>(x0 + (mypix & 7u), y0 + (mypix >> 3), dx, dy, cx, cy);
                     px = mypix;
                     rnd = cur_round;
@@ -364,7 +371,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                     px = x0 + (mypix & 7u);
                     py = y0 + (mypix >> 3);
                     Real dx = dx0, dy = dy0;
-                    if (kProbe) { sample_delta<Real>(cur_round, spr, dx, dy); rnd = cur_round; }
+                    if (kProbe) { if (cur_round) { dx = dx1; dy = dy1; } rnd = cur_round; }
                     fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx, dy, cx, cy);
                 }
                 o.start(cx, cy, ctx);
