@@ -67,6 +67,10 @@
 
 #include "fractal.cuh"
 
+#ifndef CHAOS_GROUP_UNROLL
+#define CHAOS_GROUP_UNROLL 4   /* how far the eight-trip body of an untested group is unrolled further: 1, 2 or 4 (= the whole
+                               * group: 160 FP instructions without a branch; c2 3.72 / 3.68 / 3.61 ms, c4 35.7 / 35.4 / 35.1 ms) */
+#endif
 #ifndef CHAOS_SAVE_SHIFT
 #define CHAOS_SAVE_SHIFT 2   /* the kept state of the recurrence check is replaced at trip counts growing by 1 + 2^-shift.
                               * Executed trips of c2 by shift: 0: 5.98 G, 1: 5.62 G, 2: 5.63 G, 3: 5.97 G, 4: 6.88 G, 5: 8.39 G
@@ -102,6 +106,7 @@ template <class Real> struct quadratic_orbit {
     static constexpr bool kResumable = true;
     static constexpr uint32_t kScaled = 1u, kDeferTest = 2u, kDetectCycle = 4u, kPeriodic = 8u, kReplay = 16u;
     static constexpr uint32_t kGroup = 32u;        /* untested trips per group (power of two) */
+    static constexpr int kGroupUnroll = CHAOS_GROUP_UNROLL;
 
     Real x, y, cx, cy;      /* kScaled: 2x, 2y, 2cx, 2cy */
     Real sx, sy;            /* the earlier state the orbit is compared with (kDetectCycle) */
@@ -196,7 +201,7 @@ template <class Real> struct quadratic_orbit {
         Real xx = op::mul(x, x), yy = op::mul(y, y);
         while (i + kGroup <= limit) {
             const Real bx = x, by = y;
-#pragma unroll 1
+#pragma unroll kGroupUnroll
             for (uint32_t r = 0; r < kGroup / 8u; ++r) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) advance<kS>(xx, yy);

@@ -512,6 +512,10 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
     const float scf = a.max_ss;                               /* host guarantees >= 1 (:174) */
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(scf)));
     const float spr = sqrtf(__fadd_rn(scf, -2.0f));
+    /* the sample offsets of all rounds (integer and float divisions each) once per CTA */
+    __shared__ Real s_dx[64], s_dy[64];
+    if (threadIdx.x < 64u) sample_delta<Real>(threadIdx.x, spr, s_dx[threadIdx.x], s_dy[threadIdx.x]);
+    __syncthreads();
     const uint32_t n_cont = kResume ? a.counters->n_continuing : a.n_tiles;   /* tiles chaosClassifyTiles left for this pass */
     /* Few tiles left (a frame whose tiles mostly ended after sample 1): this pass would be all latency -- a tile's rounds
      * run one after the other here, each as long as its longest orbit, with most lanes of the GPU empty (c2: 0.4 ms at
@@ -737,8 +741,8 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
                     slot = k;
                     pix = mypix;
                     rnd = r;
-                    Real dx, dy, cx, cy;
-                    sample_delta<Real>(r, spr, dx, dy);
+                    Real cx, cy;
+                    const Real dx = s_dx[r], dy = s_dy[r];
                     fm.template plane_point<fused_plane_y<FractalT>::value>(ws.hdr[k].x0 + (mypix & 7u), ws.hdr[k].y0 + (mypix >> 3), dx, dy, cx, cy);
                     o.start(cx, cy, ctx);
                     it = 0;
