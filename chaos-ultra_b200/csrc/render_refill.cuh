@@ -886,6 +886,12 @@ static __device__ void classify_tiles(const chaos_render_args &a)
             const bool all_le = __all_sync(CHAOS_FULL_MASK, p.le);
             S = decision_update(1u, S, all_eq, all_lt, all_le);
             blocked = __any_sync(CHAOS_FULL_MASK, p.zero_mean && part);
+            /* Also set to go on: a pixel whose first two samples lie so far apart that its dispersion after sample 2 is above 1
+             * whatever sample 2 is (variance >= d^2 / 2 for d = et0 - et1, mean <= (et0 + et1 + maxIterations) / 3).  Pass B
+             * would export such a tile after one more round; it may as well go now.  (A scheduling hint: pass D replays
+             * the reference's decisions whatever was guessed here.) */
+            const float d = __uint2float_rn(et0 > et1 ? et0 - et1 : et1 - et0);
+            blocked = blocked || __any_sync(CHAOS_FULL_MASK, part && 3.0f * d * d > 2.0f * (__uint2float_rn(et0 + et1) + __uint2float_rn(a.max_iter)));
         }
         if (2u >= S) {
             if (part) store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn((et0 + et1) / S), __uint2float_rn(S), 0u, 0.f);
