@@ -356,6 +356,7 @@ struct chaos_renderer {
     CUstream strand_stream[CHAOS_MAX_STRANDS] = {};
     CUevent strand_ev_b[CHAOS_MAX_STRANDS] = {}, strand_ev_done[CHAOS_MAX_STRANDS] = {};
     uint32_t overlap_compose = 1;
+    int host_compose_blocks = 0;   /* CTAs of that compose: 0 = one per SM, -1 = the usual grid (CHAOS_HOST_COMPOSE_BLOCKS) */
     uint32_t part_index = 0, part_count = 1, band_rows = 64;
     chaos_stats stats;
     uint32_t engine = 1;           /* 1 = lane-refill scheduler (default), 0 = tile-synchronous */
@@ -558,6 +559,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
         unsigned x = 0, y = 0;
         if (sscanf(si, "%u,%u", &x, &y) == 2 && x >= 1 && y >= 1) { r->sched_idle_indep = x; r->sched_idle_rounds = y; }
     }
+    const char *hb = getenv("CHAOS_HOST_COMPOSE_BLOCKS");
+    if (hb) r->host_compose_blocks = atoi(hb);
     const char *oc = getenv("CHAOS_OVERLAP_COMPOSE");   /* 0 = compose only after the last render pass */
     if (oc) r->overlap_compose = (uint32_t)atoi(oc) ? 1u : 0u;
     const char *ea = getenv("CHAOS_EXPORT_ALL_BELOW");
@@ -930,6 +933,11 @@ static chaos_status launch_compose(chaos_renderer *r, const chaos_params *m, CUs
     c.tiles_x = (r->width + 7u) / 8u;
     uint64_t quads = (uint64_t)((r->width + 3u) / 4u) * r->height;
     int max_blocks = r->provider->sm_count * 8;
+    /* The frame-wide compose that runs next to passes C and D into pinned host memory moves at PCIe speed (33 MB: 0.6 ms)
+     * whatever its grid; a small grid leaves the SMs (and their register files: a pass C CTA needs a quarter of one) to
+     * the passes it runs next to. */
+    if (stream == r->stream2 && stream && r->mode == CHAOS_OUTPUT_HOST && !r->rgba_target && r->host_compose_blocks >= 0)
+        max_blocks = r->host_compose_blocks ? r->host_compose_blocks : r->provider->sm_count;   /* measured: 16 / 37 / 148 / 1184 CTAs -> c2 4.13 / 3.99 / 3.91 / 3.93 ms, c2ex2 7.63 / 7.61 / 7.70 / 7.91 ms end to end */
     int blocks = (int)std::min<uint64_t>((quads + 255u) / 256u, (uint64_t)max_blocks);
     if (blocks < 1) blocks = 1;
     return launch(r, r->k_compose, blocks, 256, r->palette_len * 4u, &c, stream);
