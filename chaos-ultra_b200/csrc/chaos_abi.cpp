@@ -362,7 +362,7 @@ struct chaos_renderer {
     uint32_t engine = 1;           /* 1 = lane-refill scheduler (default), 0 = tile-synchronous */
     uint32_t block_iters = 0;      /* 0 = choose from maxIterations */
     uint32_t shortcuts = CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE;   /* count-preserving shortcuts of the escape loop */
-    uint32_t sched_idle_indep = 6, sched_idle_rounds = 16;   /* see take_scheduling_pass (render_refill.cuh) */
+    uint32_t sched_idle_indep = 10, sched_idle_rounds = 16;   /* see take_scheduling_pass (render_refill.cuh) */
 };
 
 static chaos_status check_renderer(const chaos_renderer *r)
