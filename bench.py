@@ -39,7 +39,7 @@ A, FOV, REUSE, ZOOMING, ZOOM_IN = 1, 4, 8, 16, 32
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel(s), per frame, from one
 # `ncu --set full` capture of the same command (never measured in a bench run); workload -> (bytes, capture)
 NCU_TRAFFIC = {
-    "c2": (int((7.51 + 93.64 + 12.94 + 0.004 + 10.55 + 0.86) * 1e6), "profiles/r01f_passes_c2.txt: chaosPassA + chaosPassB + chaosPassC Double"),
+    "c2": (int((8.36 + 92.24 + 11.22 + 0.003 + 10.89 + 0.76) * 1e6), "profiles/r01g_passes_c2.txt: chaosPassA + chaosPassB + chaosPassC Double"),
     "c3": (int((127.08 + 85.31 + 132.73 + 9.60) * 1e6), "profiles/r01b_fast_frame_c3.txt: chaosReusePassFloat + compose "
            "(part of the 133 MB of records written and of the 33 MB frame stays in the 126 MB L2)"),
 }
