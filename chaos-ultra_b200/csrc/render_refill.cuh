@@ -14,18 +14,22 @@
  *
  * Several samples: the reference's early-termination decision (:128-150) is an ALL-vote over the tile after each
  * sample, so sample i+1 of a tile needs sample i of all its pixels.  The frame runs in passes:
- *   pass A   sample 0 of every pixel needs no vote (the decision block is not entered at i = 0 when S >= 2):
- *            independent orbits (kMode 1); escape time, trip count and executed trips wait in the pixel's record;
- *   classify/order   a cost class per tile from those records, counting sort: tile_order, most expensive first;
- *   pass B   rounds 1.. with the votes (render_main_rounds).  Every warp owns CHAOS_REFILL_SLOTS tile slots in shared
+ *   pass A   samples 0 and 1 of every pixel need no vote (the first decision comes after sample 1): independent orbits
+ *            (kMode 1, work item = (tile, sample)); escape times, trip count and executed trips wait in the pixel's record;
+ *   classify/order   one warp per tile takes the decision after sample 1.  Tiles it ends get their final record; tiles
+ *            that go on and are set to use their whole budget are exported (see pass C); the rest get a cost class and are
+ *            counting-sorted: tile_order, most expensive first;
+ *   pass B   rounds 2.. with the votes (render_main_rounds).  Every warp owns CHAOS_REFILL_SLOTS tile slots in shared
  *            memory (per pixel: sum of the decided rounds' escape times + one escape time per round for the first
  *            ten rounds, the state sampleTheFractal keeps in registers, :96-127); lanes take pending orbits of any
  *            slot and any round in flight; when the round that is next in order is complete the warp evaluates the
  *            decision cooperatively, lane p speaking for pixel p, with the reference's predicates and votes -- so
  *            sample counts, sums and therefore every stored record are the reference's;
- *   pass C   the remaining rounds of the tiles pass B EXPORTED (tiles set to use their whole sample budget), as
- *            independent orbits of one GPU-wide pool (kMode 2);
+ *   pass C   the remaining rounds of the EXPORTED tiles (tiles set to use their whole sample budget; every tile when
+ *            few are left), as independent orbits of one GPU-wide pool (kMode 2);
  *   pass D   the decisions of those tiles, replayed over the stored rounds (replay_exported).
+ * Once the tile queue of pass A or C is dry, warps left with few orbits park them in the orbit pool and full warps are
+ * repacked from it (below); a frame is cut into strands whose pass chains run next to each other (chaos_abi.cpp).
  * No result depends on the order in which anything runs; only the launches' tails do.
  */
 #ifndef CHAOS_RENDER_REFILL_CUH
