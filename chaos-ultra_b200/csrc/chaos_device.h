@@ -12,7 +12,7 @@
 
 #include <stdint.h>
 
-#define CHAOS_MODULE_ABI 23u
+#define CHAOS_MODULE_ABI 25u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -121,6 +121,12 @@ struct chaos_render_args {
     uint32_t pool_capacity;            /* entries of all CHAOS_POOL_SHARDS rings together; a ring holds >= 32 x its warps */
     uint32_t pool_min_lanes;
     uint32_t export_all_below;         /* pass B exports every tile it gets when chaosClassifyTiles left it at most this many */
+    /* fast frame, pass R: the pixels it finishes are coloured right away (their record is in registers) instead of being
+     * read back by compose: 16 R + 16 W + 4 W bytes per pixel instead of 16 R + 16 W and 16 R + 4 W.  NULL = compose does
+     * it all.  The tiles pass R hands to pass S are flagged in late_tiles; a filtered compose colours them afterwards. */
+    uint32_t *fuse_rgba;               /* the frame (device, mapped host or a peer's), width*height */
+    const uint32_t *fuse_palette;
+    uint32_t fuse_palette_len;
     uint32_t pool_epoch;               /* distinguishes this launch's entries from older ones (host: += 2 per frame; pass C uses epoch + 1) */
 };
 #define CHAOS_POOL_STRIDE 128u

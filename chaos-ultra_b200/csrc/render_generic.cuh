@@ -488,9 +488,20 @@ template <> __device__ __forceinline__ float warp_origin_1d<float, true>(const c
     return __fmaf_rn(fh, -rel, fh);
 }
 
+static __device__ __forceinline__ uint32_t colorize_sample_count(uint32_t cnt, uint32_t cnt100);
+
 template <class Real>
 static __device__ void advanced_reuse_pass(const chaos_render_args &a)
 {
+    /* fused colouring (chaos_render_args::fuse_rgba): the palette is staged in shared memory once per CTA, as compose does */
+    extern __shared__ uint32_t s_fuse_palette[];
+    const bool fuse = a.fuse_rgba != nullptr;
+    if (fuse) {
+        for (uint32_t k = threadIdx.x; k < a.fuse_palette_len; k += blockDim.x) s_fuse_palette[k] = a.fuse_palette[k];
+        __syncthreads();
+    }
+    const bool visualize = VISUALIZE_SAMPLE_COUNT;
+    const uint32_t cnt100 = __double2uint_rz(fmax((double)a.max_ss, 1.0));
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t fl = a.flags;
     const bool use_fov = (fl & CHAOS_FLAG_FOVEATION) && (fl & CHAOS_FLAG_IS_ZOOMING) && (fl & CHAOS_FLAG_ZOOMING_IN);
@@ -560,11 +571,22 @@ static __device__ void advanced_reuse_pass(const chaos_render_args &a)
         const uint32_t needs_mask = __ballot_sync(CHAOS_FULL_MASK, needs);
         const bool tile_needs = ((needs_mask >> (lane & 24u)) & 0xffu) != 0u;
         if (tile_needs) {
-            if ((lane & 7u) == 0u && tile_ok) a.tile_order[atomicAdd(&a.counters->bucket_count[0], 1u)] = tile;
+            if ((lane & 7u) == 0u && tile_ok) {
+                a.tile_order[atomicAdd(&a.counters->bucket_count[0], 1u)] = tile;
+                if (fuse) {          /* compose colours this tile after pass S */
+                    const uint32_t gt = (y0 >> 2) * a.tiles_x + (x0 >> 3);
+                    atomicOr(&a.late_tiles[gt >> 5], 1u << (gt & 31u));
+                }
+            }
         } else if (col_ok) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                if (y0 + r < a.height) store_record(record_at(a.out, a.out_pitch, px, y0 + r), rv[r], rw[r], 1u, 0.f);
+                if (y0 + r < a.height) {
+                    store_record(record_at(a.out, a.out_pitch, px, y0 + r), rv[r], rw[r], 1u, 0.f);
+                    if (fuse)        /* compose (:455-475) on the record just written: (value, weight, isReused = 1, 0) */
+                        a.fuse_rgba[(size_t)(y0 + r) * a.width + px] =
+                            visualize ? colorize_sample_count(0u, cnt100) : Fractal::colorize(s_fuse_palette, a.fuse_palette_len, rv[r]);
+                }
         }
     }
 }
