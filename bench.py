@@ -277,6 +277,9 @@ def run_ours(args, wl, rank, world, local):
             r.freeRenderingResources()
         r.initializeRendering(W, H, None, mode)
         r.setPartition(rank, world, band_rows)
+        if world == 1 and os.environ.get("CHAOS_EMULATE_PART"):   # diagnostics: what ONE rank of an N-GPU run does
+            pi, pn = map(int, os.environ["CHAOS_EMULATE_PART"].split(":"))
+            r.setPartition(pi, pn, band_rows)
         frame = shared = token = None
         if world > 1:
             frame = torch.as_tensor(DevBuf(r.outputRGBADevicePointer()), device="cuda") if mode == cu.OUTPUT_DEVICE else None

@@ -135,6 +135,7 @@ _API = {
     "chaos_provider_destroy": (C.c_int, [_VP]),
     "chaos_list_fractals": (C.c_int, [_VP, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_uint32)]),
     "chaos_open": (C.c_int, [_VP, C.c_char_p, C.c_int, C.POINTER(_VP)]),
+    "chaos_active_renderer": (_VP, [_VP]),
     "chaos_initialize": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, C.c_uint32, C.c_int]),
     "chaos_free_resources": (C.c_int, [_VP]),
     "chaos_render_quality": (C.c_int, [_VP, C.POINTER(_Params)]),
@@ -482,7 +483,11 @@ class CudaFractalRendererProvider:
         h = _VP()
         old = self._active
         same = old is not None and old._h is not None and not forceReload and old.getFractalName() == fractalName
-        _check(self._lib, self._lib.chaos_open(self._h, fractalName.encode(), int(bool(forceReload)), C.byref(h)))
+        st = self._lib.chaos_open(self._h, fractalName.encode(), int(bool(forceReload)), C.byref(h))
+        if st != 0 and old is not None and not self._lib.chaos_active_renderer(self._h):
+            old._h = None      # the library closed it before the new module failed to load (:52)
+            self._active = None
+        _check(self._lib, st)
         if same:
             return old  # same name and !forceReload: the active renderer is returned (:50-51)
         if old is not None:

@@ -68,6 +68,42 @@ def build_module(src: Path, force: bool = False) -> Path:
     return out
 
 
+COMPAT_DIR = PKG_DIR / "cudaKernels_compat"
+REFERENCE_FRACTALS = Path("/root/reference/src/main/cuda/fractals")
+# reference modules whose build keeps c.y's multiply and subtract apart (see compat/chaos_compat_post.cuh)
+UNFUSED_PLANE_Y = {"mandelbrot", "julia"}
+
+
+def build_compat_module(src: Path, out_dir: Path = COMPAT_DIR, fused_plane_y: bool = True, force: bool = False) -> Path:
+    """A module file written for the REFERENCE's contract (fractal.cuh:7-28: computeFractal / colorize / debugFractal),
+    unmodified, -> <out_dir>/<name>.cubin for this backend.  The translation unit is the counterpart of the one
+    compile.sh:10-15 writes: compat prologue, the author's file (by path, nothing is copied), compat epilogue."""
+    src = Path(src).resolve()
+    out_dir.mkdir(exist_ok=True)
+    out = out_dir / (src.stem + ".cubin")
+    deps = [src] + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((CSRC / "compat").glob("*.cuh")) + [Path(__file__)]
+    if not force and _newer(out, deps):
+        return out
+    wrap = out_dir / ("tmp_compiling_%s.cu" % src.stem)
+    wrap.write_text('#include "compat/chaos_compat_pre.cuh"\n#include "%s"\n#include "compat/chaos_compat_post.cuh"\n' % src)
+    try:
+        # the author's directory first (its own headers), then the compat headers (fractal.cuh / helpers.cuh)
+        cmd = [_nvcc(), "-cubin", *ARCH_FLAGS, *NVCC_FLAGS, "-w", "-DCHAOS_COMPAT_FUSED_PLANE_Y=%d" % int(fused_plane_y),
+               "-I", str(CSRC), "-I", str(CSRC / "compat"), "-I", str(src.parent.parent), str(wrap), "-o", str(out)]
+        _run(cmd, log=out_dir / (src.stem + ".ptxas.log"))
+    finally:
+        wrap.unlink(missing_ok=True)
+    return out
+
+
+def build_compat_reference(force: bool = False):
+    """every module of the reference, from its own unmodified source where it lies (only where /root/reference is
+    mounted: this container; the GPU box gets the built files)"""
+    if not REFERENCE_FRACTALS.is_dir():
+        return []
+    return [build_compat_module(s, fused_plane_y=s.stem not in UNFUSED_PLANE_Y, force=force) for s in sorted(REFERENCE_FRACTALS.glob("*.cu"))]
+
+
 def build_library(force: bool = False) -> Path:
     LIB_DIR.mkdir(exist_ok=True)
     srcs = [CSRC / "chaos_abi.cpp"]
@@ -94,10 +130,16 @@ def build_all(force: bool = False):
     lib = build_library(force)
     mods = [build_module(s, force) for s in module_sources()]
     build_bench_kernels(force)
+    build_compat_reference(force)
     return lib, mods
 
 
 if __name__ == "__main__":
+    if sys.argv[1:2] == ["compat"]:      # python build.py compat <module.cu> [out_dir] [--unfused-plane-y]
+        args = [a for a in sys.argv[2:] if not a.startswith("--")]
+        print(build_compat_module(Path(args[0]), Path(args[1]) if len(args) > 1 else COMPAT_DIR,
+                                  fused_plane_y="--unfused-plane-y" not in sys.argv, force=True))
+        sys.exit(0)
     lib, mods = build_all(force="--force" in sys.argv)
     print(lib)
     for m in mods:

@@ -19,6 +19,8 @@
  * entry point fails with a message.
  */
 #include <dlfcn.h>
+#include <errno.h>
+#include <limits.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -173,9 +175,14 @@ static void defaults_julia(chaos_defaults *d)
 /* modules/ModuleTest.java:9-23 */
 static chaos_status test_custom(chaos_renderer *r, const char *text)
 {
+    /* Integer.parseInt: optional sign, then digits only (no surrounding white space), value within int */
+    const char *t = text ? text : "";
     char *end = nullptr;
-    long v = strtol(text ? text : "", &end, 10);
-    if (!text || end == text || *end != '\0') return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "NumberFormatException: For input string: \"%s\"", text ? text : "");
+    errno = 0;
+    long long v = strtoll(t, &end, 10);
+    const bool shape_ok = (*t == '-' || *t == '+') ? (t[1] >= '0' && t[1] <= '9') : (*t >= '0' && *t <= '9');
+    if (!shape_ok || *end != '\0' || errno == ERANGE || v < INT_MIN || v > INT_MAX)
+        return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "NumberFormatException: For input string: \"%s\"", t);
     int iv = (int)v;
     return write_constant(r, "amplifier", &iv, sizeof iv, "double");
 }
@@ -213,6 +220,12 @@ static chaos_status newton_generic_custom(chaos_renderer *r, const char *text)
     for (const mj_value &root : ro->arr)
         if (root.kind != mj_value::ARR || root.arr.size() != 2)
             return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Found a root that is not represented as [real, imag].");
+    /* Gson's getAsDouble throws on anything that is not a number (strings, null, booleans, nested arrays) */
+    for (const mj_value &root : ro->arr)
+        for (const mj_value &part : root.arr)
+            if (part.kind != mj_value::NUM) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "NumberFormatException: a root component is not a number");
+    for (const mj_value &c : co->arr)
+        if (c.kind != mj_value::NUM) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "NumberFormatException: a coefficient is not a number");
     if (co->arr.size() != 4) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "expecting 4 coefficients");
     if (ro->arr.size() != 3) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "expecting 3 roots");
     double roots[6], coefs[4];
@@ -238,6 +251,8 @@ static chaos_status newton_iterations_custom(chaos_renderer *r, const char *text
     st = newton_parse(text, json);
     if (st != CHAOS_OK) return st;
     if (const mj_value *cm = json.get("colorMagnifier")) {
+        if (cm->kind != mj_value::NUM || !(cm->num >= (double)INT_MIN && cm->num <= (double)INT_MAX))
+            return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "NumberFormatException: colorMagnifier is not an int");
         int v = (int)cm->num;
         return write_constant(r, "colorMagnifier", &v, sizeof v, "double");
     }
@@ -305,6 +320,12 @@ struct chaos_renderer {
     CUfunction k_pass_a[2] = {nullptr, nullptr}, k_pass_b[2] = {nullptr, nullptr}, k_pass_c[2] = {nullptr, nullptr};   /* [0] float, [1] double */
     int blocks_pass_a[2] = {0, 0}, blocks_pass_b[2] = {0, 0}, blocks_pass_c[2] = {0, 0};
     CUfunction k_main_f_sync = nullptr, k_main_d_sync = nullptr;   /* engine 0 (differential check) */
+    /* engine 2 (render_streams.cuh): probe -> long -> finish, [0] float, [1] double */
+    CUfunction k_probe[2] = {nullptr, nullptr}, k_long[2] = {nullptr, nullptr}, k_finish[2] = {nullptr, nullptr};
+    int blocks_probe[2] = {0, 0}, blocks_long[2] = {0, 0}, blocks_finish[2] = {0, 0};
+    CUdeviceptr long_list = 0, finish_list = 0;    /* allocated by the first engine-2 frame of a frame size */
+    size_t list_capacity = 0;                      /* entries */
+    uint32_t probe_trips = 64;
     CUfunction k_classify = nullptr, k_order = nullptr;            /* between the two passes of engine 1 */
     CUfunction k_replay = nullptr;                                 /* pass D */
     chaos_export exp_buf = {0, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -348,6 +369,9 @@ struct chaos_renderer {
     /* threads per CTA of the persistent pass kernels (warps are independent there): a CTA gives its SM share back only
      * when its last warp is done, so smaller CTAs let the next pass in sooner */
     uint32_t pass_threads = 256;
+    /* resident warps per SM of the escape-loop kernels (0 = what fits).  Fewer warps per scheduler make every orbit
+     * advance faster (a trip is a chain of three dependent FP64 instructions) at some cost in pipe utilisation */
+    int loop_warps_per_sm = 0;
     /* orbit pool of the independent-orbit passes (chaos_render_args::pool): one per strand, allocated by the first frame */
     CUdeviceptr pool[CHAOS_MAX_STRANDS] = {};
     uint32_t pool_capacity = 0;
@@ -364,7 +388,7 @@ struct chaos_renderer {
     int host_compose_blocks = 0;   /* CTAs of that compose: 0 = one per SM, -1 = the usual grid (CHAOS_HOST_COMPOSE_BLOCKS) */
     uint32_t part_index = 0, part_count = 1, band_rows = 64;
     chaos_stats stats;
-    uint32_t engine = 1;           /* 1 = lane-refill scheduler (default), 0 = tile-synchronous */
+    uint32_t engine = 2;           /* 2 = orbit streams (default), 1 = lane-refill scheduler, 0 = tile-synchronous */
     uint32_t block_iters = 0;      /* 0 = choose from maxIterations */
     uint32_t shortcuts = CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE;   /* count-preserving shortcuts of the escape loop */
     uint32_t sched_idle_indep = 10, sched_idle_rounds = 16;   /* see take_scheduling_pass (render_refill.cuh) */
@@ -426,6 +450,8 @@ extern "C" chaos_status chaos_provider_destroy(chaos_provider *p)
     return CHAOS_OK;
 }
 
+extern "C" chaos_renderer *chaos_active_renderer(const chaos_provider *p) { return p ? p->active : nullptr; }
+
 extern "C" chaos_status chaos_list_fractals(chaos_provider *p, const char **names, uint32_t capacity, uint32_t *count)
 {
     if (!p) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "provider handle is NULL");
@@ -448,10 +474,11 @@ static void unload_module(chaos_renderer *r)
     if (r->module) { D->p_cuModuleUnload(r->module); r->module = nullptr; }
 }
 
-static int persistent_blocks(chaos_renderer *r, CUfunction fn, int threads, size_t smem = 0)
+static int persistent_blocks(chaos_renderer *r, CUfunction fn, int threads, size_t smem = 0, int max_warps_per_sm = 0)
 {
     int per_sm = 0;
     if (D->p_cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != CUDA_SUCCESS || per_sm < 1) per_sm = 1;
+    if (max_warps_per_sm > 0) per_sm = std::max(1, std::min(per_sm, max_warps_per_sm / (threads / 32)));
     return per_sm * r->provider->sm_count;   /* a whole number of CTAs per SM: 148 x resident CTAs */
 }
 
@@ -485,6 +512,8 @@ static chaos_status load_module(chaos_renderer *r)
         {"fractalRenderMainFloatSync", &r->k_main_f_sync}, {"fractalRenderMainDoubleSync", &r->k_main_d_sync},
         {"chaosClassifyTiles", &r->k_classify}, {"chaosOrderTiles", &r->k_order}, {"chaosReplayExported", &r->k_replay},
         {"chaosReusePassFloat", &r->k_reuse_f}, {"chaosReusePassDouble", &r->k_reuse_d},
+        {"chaosProbeFloat", &r->k_probe[0]}, {"chaosProbeDouble", &r->k_probe[1]}, {"chaosLongFloat", &r->k_long[0]},
+        {"chaosLongDouble", &r->k_long[1]}, {"chaosFinishFloat", &r->k_finish[0]}, {"chaosFinishDouble", &r->k_finish[1]},
     };
     for (auto &k : fns) {
         chaos_status st = get_function(r, k.name, k.fn);
@@ -510,14 +539,17 @@ static chaos_status load_module(chaos_renderer *r)
         CUresult ea = D->p_cuFuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)r->refill_smem);
         if (ea != CUDA_SUCCESS) { unload_module(r); return fail(CHAOS_ERR_CUDA_INIT, "cannot reserve %u B of shared memory: %s", r->refill_smem, cu_err_name(ea)); }
     }
-    r->blocks_main_f = persistent_blocks(r, r->k_main_f, 256);
-    r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256);
+    r->blocks_main_f = persistent_blocks(r, r->k_main_f, 256, 0, r->loop_warps_per_sm);
+    r->blocks_main_d = persistent_blocks(r, r->k_main_d, 256, 0, r->loop_warps_per_sm);
     const int T = (int)r->pass_threads;
     r->refill_smem = r->refill_smem / 8u * (r->pass_threads / 32u);   /* the module states it for 8 warps */
     for (int p = 0; p < 2; ++p) {
-        r->blocks_pass_a[p] = persistent_blocks(r, r->k_pass_a[p], T);
+        r->blocks_pass_a[p] = persistent_blocks(r, r->k_pass_a[p], T, 0, r->loop_warps_per_sm);
         r->blocks_pass_b[p] = persistent_blocks(r, r->k_pass_b[p], T, r->refill_smem);
-        r->blocks_pass_c[p] = persistent_blocks(r, r->k_pass_c[p], T);
+        r->blocks_pass_c[p] = persistent_blocks(r, r->k_pass_c[p], T, 0, r->loop_warps_per_sm);
+        r->blocks_probe[p] = persistent_blocks(r, r->k_probe[p], 256);
+        r->blocks_long[p] = persistent_blocks(r, r->k_long[p], T, 0, r->loop_warps_per_sm);
+        r->blocks_finish[p] = persistent_blocks(r, r->k_finish[p], 256);
     }
     r->blocks_main_f_sync = persistent_blocks(r, r->k_main_f_sync, 256);
     r->blocks_main_d_sync = persistent_blocks(r, r->k_main_d_sync, 256);
@@ -538,15 +570,15 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (!out) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "out is NULL");
     if (!fractal_name) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Unknown fractal: null");
     ctx_guard g(p);
-    if (p->active) {
-        if (!strcmp(p->active->desc->fractal_name, fractal_name) && !force_reload) { *out = p->active; return CHAOS_OK; }
-        chaos_close(p->active);                                    /* closing the previous renderer :52 */
-    }
+    if (p->active && !strcmp(p->active->desc->fractal_name, fractal_name) && !force_reload) { *out = p->active; return CHAOS_OK; }
     *out = nullptr;
+    /* an unknown name leaves the active renderer alone (a C caller's old handle stays valid); from here on the old
+     * renderer is closed first, as the reference does (:52), and chaos_active_renderer() tells what is left */
     const module_desc *desc = nullptr;
     for (uint32_t i = 0; i < g_n_modules; ++i)
         if (!strcmp(g_modules[i].fractal_name, fractal_name)) desc = &g_modules[i];
     if (!desc) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Unknown fractal: %s", fractal_name);
+    if (p->active) chaos_close(p->active);                         /* closing the previous renderer :52 */
     chaos_renderer *r = new chaos_renderer();
     r->provider = p;
     r->desc = desc;
@@ -554,7 +586,9 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     r->stats.struct_size = sizeof(chaos_stats);
     /* debugging knobs (not part of the reference's interface): engine 0 is the differential check of engine 1 */
     const char *eng = getenv("CHAOS_ENGINE");
-    if (eng) r->engine = (uint32_t)atoi(eng) ? 1u : 0u;
+    if (eng) r->engine = (uint32_t)std::min(std::max(atoi(eng), 0), 2);
+    const char *prb = getenv("CHAOS_PROBE_TRIPS");
+    if (prb) r->probe_trips = (uint32_t)std::max(atoi(prb), 8);
     const char *sb = getenv("CHAOS_SYNC_BELOW");
     if (sb) r->sync_below_iters = (uint32_t)atoi(sb);
     const char *nb = getenv("CHAOS_BLOCK_ITERS");
@@ -580,6 +614,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (pm) r->pool_min_lanes = (uint32_t)std::min(std::max(atoi(pm), 0), 32);
     const char *pt = getenv("CHAOS_PASS_THREADS");
     if (pt && (atoi(pt) == 32 || atoi(pt) == 64 || atoi(pt) == 128 || atoi(pt) == 256)) r->pass_threads = (uint32_t)atoi(pt);
+    const char *lw = getenv("CHAOS_LOOP_WARPS_PER_SM");
+    if (lw) r->loop_warps_per_sm = std::max(atoi(lw), 0);
     const char *sc = getenv("CHAOS_SHORTCUTS");   /* 0 = every trip executed and tested, as the reference does */
     if (sc) r->shortcuts = (uint32_t)atoi(sc) & (CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE);
     chaos_status st = load_module(r);
@@ -648,7 +684,8 @@ static CUdeviceptr ensure_pool(chaos_renderer *r, uint32_t s)
     if (!r->pool_min_lanes) return 0;
     if (!r->pool_capacity) {
         int most = std::max(r->blocks_main_f, r->blocks_main_d) * 256;
-        for (int p = 0; p < 2; ++p) most = std::max(most, std::max(r->blocks_pass_a[p], r->blocks_pass_c[p]) * (int)r->pass_threads);
+        for (int p = 0; p < 2; ++p)
+            most = std::max(most, std::max(std::max(r->blocks_pass_a[p], r->blocks_pass_c[p]), r->blocks_long[p]) * (int)r->pass_threads);
         const uint32_t warps = (uint32_t)most / 32u;   /* of the largest launch */
         r->pool_capacity = CHAOS_POOL_SHARDS * 32u * ((warps + CHAOS_POOL_SHARDS - 1u) / CHAOS_POOL_SHARDS);
     }
@@ -660,6 +697,30 @@ static CUdeviceptr ensure_pool(chaos_renderer *r, uint32_t s)
     return r->pool[s];
 }
 
+/* engine 2: the long and finish lists, `entries` each (8 and 32 bytes per entry) */
+static bool ensure_lists(chaos_renderer *r, size_t entries)
+{
+    if (r->list_capacity >= entries) return true;
+    D->p_cuStreamSynchronize(r->stream);
+    if (r->long_list) { D->p_cuMemFree(r->long_list); r->long_list = 0; }
+    if (r->finish_list) { D->p_cuMemFree(r->finish_list); r->finish_list = 0; }
+    r->list_capacity = 0;
+    if (D->p_cuMemAlloc(&r->long_list, entries * 8u) != CUDA_SUCCESS) { r->long_list = 0; return false; }
+    if (D->p_cuMemAlloc(&r->finish_list, entries * 32u) != CUDA_SUCCESS) { D->p_cuMemFree(r->long_list); r->long_list = 0; r->finish_list = 0; return false; }
+    r->list_capacity = entries;
+    return true;
+}
+
+/* engine 2: one probe -> long -> finish chain on stream q; b.phase says which pass it serves */
+static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg, CUstream stream);
+static chaos_status launch_stream_chain(chaos_renderer *r, chaos_render_args &b, int p, CUstream q)
+{
+    chaos_status st = launch(r, r->k_probe[p], r->blocks_probe[p], 256, 0, &b, q);
+    if (st == CHAOS_OK) st = launch(r, r->k_long[p], r->blocks_long[p], (int)r->pass_threads, 0, &b, q);
+    if (st == CHAOS_OK) st = launch(r, r->k_finish[p], r->blocks_finish[p], 256, 0, &b, q);
+    return st;
+}
+
 static void free_frame_memory(chaos_renderer *r)
 {
     for (int i = 0; i < 2; ++i) if (r->buf[i].ptr) { D->p_cuMemFree(r->buf[i].ptr); r->buf[i].ptr = 0; r->buf[i].pitch = 0; }
@@ -667,8 +728,11 @@ static void free_frame_memory(chaos_renderer *r)
     if (r->tile_key) { D->p_cuMemFree(r->tile_key); r->tile_key = 0; }
     if (r->tile_order) { D->p_cuMemFree(r->tile_order); r->tile_order = 0; }
     free_export(r);
+    if (r->long_list) { D->p_cuMemFree(r->long_list); r->long_list = 0; }
+    if (r->finish_list) { D->p_cuMemFree(r->finish_list); r->finish_list = 0; }
+    r->list_capacity = 0;
     if (r->late_tiles) { D->p_cuMemFree(r->late_tiles); r->late_tiles = 0; }
-    if (r->late_tiles) { D->p_cuMemFree(r->late_tiles); r->late_tiles = 0; }
+    if (r->warp_trace) { D->p_cuMemFree(r->warp_trace); r->warp_trace = 0; }
     r->rgba_target = 0;
     if (r->rgba_host) { D->p_cuMemFreeHost(r->rgba_host); r->rgba_host = nullptr; r->rgba_dev = 0; }
     if (r->rgba_dev) { D->p_cuMemFree(r->rgba_dev); r->rgba_dev = 0; }
@@ -918,7 +982,7 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
 
 }
 
-static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg, CUstream stream = nullptr)
+static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg, CUstream stream)
 {
     void *params[1] = {arg};
     CUresult e = D->p_cuLaunchKernel(fn, (unsigned)blocks, 1, 1, (unsigned)threads, 1, 1, smem, stream ? stream : r->stream, params, nullptr);
@@ -973,6 +1037,11 @@ static chaos_status finish_frame(chaos_renderer *r)
     D->p_cuEventElapsedTime(&r->stats.frame_ms, r->ev[0], r->ev[3]);
     r->stats.reuse_ms = 0.f;
     r->stats.pixel_iterations = r->stats.samples = r->stats.skipped_iterations = 0;
+    for (uint32_t s = 0; s < CHAOS_MAX_STRANDS; ++s)
+        if (r->counters_host[s].abort) {     /* a kernel gave up waiting in the orbit pool (bounded spins): the records are not to be trusted */
+            r->primary_dirty = true;
+            return fail(CHAOS_ERR_CUDA, "a render kernel timed out waiting for an orbit hand-over (strand %u); the frame is void", s);
+        }
     for (uint32_t s = 0; s < CHAOS_MAX_STRANDS; ++s) {      /* every strand of the frame counts into its own block */
         r->stats.pixel_iterations += r->counters_host[s].pixel_iterations;
         r->stats.samples += r->counters_host[s].samples;
@@ -1043,14 +1112,25 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         /* Short orbits (low iteration limit) with several samples: the per-orbit scheduling work of the refill
          * engine costs more than the divergence it removes, so those frames take the tile-synchronous kernel
          * (same arithmetic, same records).  CHAOS_ENGINE=0 forces it, with the reference's 7-operation trip. */
-        const bool sync_kernel = r->engine == 0 || (S0 >= 2u && a.max_iter < r->sync_below_iters);
+        const bool sync_kernel = r->engine == 0 || (r->engine == 1 && S0 >= 2u && a.max_iter < r->sync_below_iters);
         a.force_exact = r->engine == 0 ? 1u : 0u;
+        const bool streams = r->engine == 2;
+        a.probe_trips = r->probe_trips;
+        if (streams && !ensure_lists(r, (size_t)((a.tiles_x * (size_t)a.tile_rows)) * (S0 <= 1u ? 32u : 64u)))
+            return fail(CHAOS_ERR_CUDA, "cannot allocate the orbit lists of a %ux%u frame", r->width, r->height);
         if (sync_kernel) {
-            st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a);
+            st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a, r->stream);
+        } else if (S0 <= 1u && streams) {
+            a.long_list = (uint2 *)r->long_list; a.finish_list = (void *)r->finish_list;
+            a.list_capacity = (uint32_t)std::min<size_t>((size_t)a.n_tiles * 32u, r->list_capacity);
+            a.pool = (unsigned char *)ensure_pool(r, 0);
+            a.pool_capacity = r->pool_capacity; a.pool_min_lanes = r->pool_min_lanes; a.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
+            a.phase = 0u;
+            st = launch_stream_chain(r, a, p, r->stream);
         } else if (S0 <= 1u) {
             a.pool = (unsigned char *)ensure_pool(r, 0);
             a.pool_capacity = r->pool_capacity; a.pool_min_lanes = r->pool_min_lanes; a.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
-            st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, 0, &a);
+            st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, 0, &a, r->stream);
         } else {
             /* pass A: sample 0 of every pixel; classify + order: expected-longest tiles first; pass B: the other rounds,
              * except those of tiles set to use their whole budget -> pass C (independent orbits) + pass D (their decisions).
@@ -1092,12 +1172,17 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     b.exp.et += (size_t)tile_base * CHAOS_EXPORT_ROUNDS * 32u;
                     b.exp.iters += (size_t)tile_base * CHAOS_EXPORT_ROUNDS; b.exp.skipped += (size_t)tile_base * CHAOS_EXPORT_ROUNDS;
                 }
+                if (streams) {           /* this strand's slice of the orbit lists: two orbits per pixel of its tiles */
+                    b.long_list = (uint2 *)r->long_list + (size_t)tile_base * 64u;
+                    b.finish_list = (void *)(r->finish_list + (size_t)tile_base * 64u * 32u);
+                    b.list_capacity = b.n_tiles * 64u;
+                }
                 tile_base += b.n_tiles;
                 if (b.n_tiles) {
                     const int small_grid = (int)std::min<uint64_t>((b.n_tiles + 255u) / 256u, (uint64_t)r->provider->sm_count * 4u);
                     const int tile_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);   /* one warp per tile */
                     b.phase = 1u;
-                    st = launch(r, r->k_pass_a[p], r->blocks_pass_a[p], (int)r->pass_threads, 0, &b, q);
+                    st = streams ? launch_stream_chain(r, b, p, q) : launch(r, r->k_pass_a[p], r->blocks_pass_a[p], (int)r->pass_threads, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_classify, tile_grid, 256, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &b, q);
                     b.phase = 2u;
@@ -1122,7 +1207,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                 D->p_cuEventRecord(r->strand_ev_b[s], q);
                 if (exporting && b.n_tiles && st == CHAOS_OK) {
                     b.phase = 3u;
-                    st = launch(r, r->k_pass_c[p], r->blocks_pass_c[p], (int)r->pass_threads, 0, &b, q);
+                    st = streams ? launch_stream_chain(r, b, p, q) : launch(r, r->k_pass_c[p], r->blocks_pass_c[p], (int)r->pass_threads, 0, &b, q);
                     const int replay_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);
                     if (st == CHAOS_OK) st = launch(r, r->k_replay, replay_grid, 256, 0, &b, q);
                 }
@@ -1181,6 +1266,10 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
     if (st != CHAOS_OK) return st;
     /* nothing to reuse -> create it (:164-168) */
     if (m->sample_reuse_cache_dirty || r->primary_dirty || !r->have_last) return render_quality_locked(r, m);
+    /* A rank that renders only its row bands has only its own rows of the previous frame, and the reprojection reads the
+     * previous frame around every pixel: without the other ranks' rows there is nothing valid to reuse outside the own
+     * bands, so the frame is rendered afresh (same fallback as a dirty cache). */
+    if (r->part_count > 1u) return render_quality_locked(r, m);
 
     chaos_precision prec = frame_precision(r, m);
     const bool dbl = prec != CHAOS_PRECISION_SINGLE;
@@ -1215,10 +1304,10 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
             blocks_reuse = persistent_blocks(r, k_reuse, 256, smem_reuse);
             fused = true;
         }
-        st = launch(r, k_reuse, blocks_reuse, 256, smem_reuse, &a);
+        st = launch(r, k_reuse, blocks_reuse, 256, smem_reuse, &a, r->stream);
         D->p_cuEventRecord(r->ev[4], r->stream);
         a.phase = 2u;
-        if (st == CHAOS_OK) st = launch(r, k, blocks, 256, 0, &a);
+        if (st == CHAOS_OK) st = launch(r, k, blocks, 256, 0, &a, r->stream);
         if (st != CHAOS_OK) return st;
         split = true;
     }

@@ -11,8 +11,11 @@
 #define CHAOS_DEVICE_H
 
 #include <stdint.h>
+#ifndef __CUDACC__
+struct uint2 { unsigned int x, y; };   /* host side of the launch contract (vector_types.h is CUDA-only) */
+#endif
 
-#define CHAOS_MODULE_ABI 25u
+#define CHAOS_MODULE_ABI 26u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -36,6 +39,13 @@ struct chaos_pixel_info {
 /* device counters, one block per renderer (zeroed by the host before each render call) */
 #define CHAOS_COST_BUCKETS 37
 #define CHAOS_POOL_SHARDS 128   /* the orbit pool is this many independent rings (warp w uses ring w % shards) */
+/* engine 2 (render_streams.cuh): the long and finish lists of one probe -> long -> finish chain */
+struct chaos_stream_ctl {
+    unsigned int n_long;          /* orbits the probe appended to the long list (may exceed the capacity: clamp) */
+    unsigned int long_cursor;     /* entries the long kernel has claimed */
+    unsigned int n_finish;        /* orbits the long kernel appended to the finish list */
+    unsigned int pad;
+};
 struct chaos_counters {
     unsigned int next_tile;             /* work-stealing cursor over vote tiles */
     unsigned int next_tile_b;           /* pass B: cursor from the expensive end of tile_order (fast frames: the sampling pass' cursor) */
@@ -44,7 +54,7 @@ struct chaos_counters {
     unsigned int n_exported;            /* pass B: tiles whose remaining rounds were handed to pass C (may exceed export.capacity: clamp) */
     unsigned int next_export_item;      /* pass C: work-stealing cursor over (exported tile, round) items */
     unsigned int n_continuing;          /* chaosOrderTiles: tiles whose decision after sample 1 did not end them = pass B's tiles */
-    unsigned int pad0;
+    unsigned int abort;                 /* set by a kernel that gave up waiting for a hand-over in the orbit pool: the frame is void */
     unsigned long long pixel_iterations;
     unsigned long long samples;
     unsigned long long skipped_iterations; /* part of pixel_iterations that was proven, not executed (exact recurrence) */
@@ -55,6 +65,7 @@ struct chaos_counters {
     /* diagnostics, modules built with -DCHAOS_LANE_STATS only (host: CHAOS_LANE_STATS=1 prints them): lane-trips of the
      * escape loop by what the lane was doing, [pass A/B/C/main][tested, untested][CHAOS_LS_*] */
     unsigned long long lane_stats[4][2][8];
+    chaos_stream_ctl stream[2];         /* engine 2: [0] one-sample frame or pass A, [1] pass C */
 };
 #define CHAOS_LS_CAPACITY 0   /* 32 x trips the warp spent in the block */
 #define CHAOS_LS_USEFUL 1     /* trips the lanes advanced */
@@ -128,6 +139,11 @@ struct chaos_render_args {
     const uint32_t *fuse_palette;
     uint32_t fuse_palette_len;
     uint32_t pool_epoch;               /* distinguishes this launch's entries from older ones (host: += 2 per frame; pass C uses epoch + 1) */
+    /* engine 2 (render_streams.cuh) */
+    uint2 *long_list;                  /* [list_capacity] destination words of the orbits that outlived the probe */
+    void *finish_list;                 /* [list_capacity] finish_item<Real>: orbits that need a last group of tested trips */
+    uint32_t list_capacity;
+    uint32_t probe_trips;              /* tested trips an orbit gets in the probe kernel before it goes to the long list */
 };
 #define CHAOS_POOL_STRIDE 128u
 

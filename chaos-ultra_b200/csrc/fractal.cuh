@@ -23,6 +23,9 @@
  *       __device__ bool wants_tested() const;
  *       __device__ void force_exact();                       // drop any exactly-equivalent fast form (may be a no-op)
  *       __device__ uint32_t skipped() const;                 // trips such a proof replaced (0 if none)
+ *       __device__ void save(Real &x, Real &y) const;        // kResumable: the state after the trips run so far, and
+ *       __device__ void resume(Real x, Real y);              // back into an orbit start()ed at the same point (engine 2
+ *                                                            // carries an orbit from its long kernel to its finish kernel)
  *       __device__ uint32_t finish(uint32_t i, uint32_t maxIterations) const;
  *                                     // the value `uint escapeTime = computeFractal(..)` would take
  *     };
@@ -94,6 +97,8 @@ template <class Impl, class Real> struct ClassicOrbit {
     __device__ __forceinline__ void force_exact() {}
     __device__ __forceinline__ uint32_t skipped() const { return 0u; }
     __device__ __forceinline__ bool wants_tested() const { return false; }
+    __device__ __forceinline__ void save(Real &, Real &) const {}
+    __device__ __forceinline__ void resume(Real, Real) {}
     __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit, bool)
     {
         uint32_t trips = 0;

@@ -20,6 +20,8 @@ struct Fractal {
         __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit, bool tested) { return q.run(i, limit, tested); }
         __device__ __forceinline__ bool wants_tested() const { return q.wants_tested(); }
         __device__ __forceinline__ uint32_t skipped() const { return q.skipped(); }
+        __device__ __forceinline__ void save(Real &x, Real &y) const { q.save(x, y); }
+        __device__ __forceinline__ void resume(Real x, Real y) { q.resume(x, y); }
         __device__ __forceinline__ uint32_t finish(uint32_t i, uint32_t) const
         {
             return __float2uint_rz(__uint2float_rn(i));

@@ -7,6 +7,7 @@
 #define CHAOS_MINI_JSON_H
 
 #include <stdlib.h>
+#include <string.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -24,9 +25,11 @@ struct mj_value {
     }
 };
 
+#define MJ_MAX_DEPTH 64   /* user text like "[[[[..." must not overflow the host stack */
 struct mj_parser {
     const char *p;
     bool ok = true;
+    int depth = 0;
     explicit mj_parser(const char *text) : p(text ? text : "") {}
     void ws() { while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') ++p; }
     bool eat(char c) { ws(); if (*p == c) { ++p; return true; } return false; }
@@ -34,6 +37,8 @@ struct mj_parser {
     {
         mj_value v;
         ws();
+        if ((*p == '{' || *p == '[') && depth >= MJ_MAX_DEPTH) { ok = false; return v; }
+        struct nest { int &d; explicit nest(int &x) : d(x) { ++d; } ~nest() { --d; } } guard(depth);
         if (*p == '{') {
             ++p; v.kind = mj_value::OBJ;
             if (eat('}')) return v;

@@ -140,6 +140,10 @@ template <class Real> struct quadratic_orbit {
         }
         mode = 0u;
     }
+    /* the state an orbit is carried through memory with (engine 2: long list -> finish list); start() has set the mode,
+     * which depends on c and the start point only */
+    __device__ __forceinline__ void save(Real &ox, Real &oy) const { ox = x; oy = y; }
+    __device__ __forceinline__ void resume(Real ox, Real oy) { x = ox; y = oy; mode &= ~kReplay; }
     /* trips proven instead of executed (exact recurrence) */
     __device__ __forceinline__ uint32_t skipped() const { return (mode & kPeriodic) ? max_iter - next_save : 0u; }
 

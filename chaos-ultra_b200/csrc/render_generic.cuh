@@ -614,6 +614,7 @@ static __device__ void advanced_sample_pass(const chaos_render_args &a)
  * entry points
  * ======================================================================================== */
 #include "render_refill.cuh"
+#include "render_streams.cuh"
 
 extern "C" __global__ void init() {}
 
@@ -637,6 +638,20 @@ extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
 chaosPassCFloat(const __grid_constant__ chaos_render_args a) { render_main_independent<float, Fractal, 2>(a); }
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
 chaosPassCDouble(const __grid_constant__ chaos_render_args a) { render_main_independent<double, Fractal, 2>(a); }
+
+/* engine 2: probe -> long -> finish (render_streams.cuh); args.phase says which pass the chain serves */
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
+chaosProbeFloat(const __grid_constant__ chaos_render_args a) { stream_probe<float, Fractal>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
+chaosProbeDouble(const __grid_constant__ chaos_render_args a) { stream_probe<double, Fractal>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosLongFloat(const __grid_constant__ chaos_render_args a) { stream_long<float, Fractal>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+chaosLongDouble(const __grid_constant__ chaos_render_args a) { stream_long<double, Fractal>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
+chaosFinishFloat(const __grid_constant__ chaos_render_args a) { stream_finish<float, Fractal>(a); }
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
+chaosFinishDouble(const __grid_constant__ chaos_render_args a) { stream_finish<double, Fractal>(a); }
 
 /* engine 0: tile-synchronous, reference operation sequence; the differential check of engine 1 */
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)

@@ -204,21 +204,21 @@ static __device__ __forceinline__ uint32_t pool_state(uint32_t epoch, uint32_t i
     return (epoch << 8) | ((2u * (index / ring_size) + (full ? 1u : 0u)) & 0xffu);
 }
 static __device__ __forceinline__ unsigned int ld_volatile(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+/* every wait of the hand-over is bounded: a loop that does not end within 2^24 polls (seconds; a hand-over takes
+ * microseconds) raises chaos_counters::abort and leaves; the host then fails the frame with CHAOS_ERR_CUDA */
 #ifdef CHAOS_POOL_DEBUG   /* diagnostics: name the loop that does not end */
-#define CHAOS_SPIN_GUARD(n, what, ...) if (++(n) >= 20000000u) { printf("pool spin: " what "\n", __VA_ARGS__); break; }
+#define CHAOS_SPIN_GUARD(n, what, ...) if (++(n) >= (1u << 24)) { printf("pool spin: " what "\n", __VA_ARGS__); *chaos_abort_flag = 1u; break; }
 #else
-#define CHAOS_SPIN_GUARD(n, what, ...)
+#define CHAOS_SPIN_GUARD(n, what, ...) if (++(n) >= (1u << 24)) { *chaos_abort_flag = 1u; break; }
 #endif
 /* lane 0: claim up to `want` reserved entries; returns how many, first index in `base` */
 static __device__ __forceinline__ uint32_t pool_claim(const pool_ctl_ref &c, uint32_t want, uint32_t &base)
 {
-    uint32_t spins = 0; (void)spins;
-    for (;;) {
+    for (;;) {      /* lock-free: a failed compare-and-swap means another warp made progress */
         const unsigned int h = ld_volatile(c.head), p = ld_volatile(c.reserved);
         if (p <= h) return 0u;
         const uint32_t take = min(want, p - h);
         if (atomicCAS(c.head, h, h + take) == h) { base = h; return take; }
-        CHAOS_SPIN_GUARD(spins, "claim head %u reserved %u", h, p);
     }
 }
 
@@ -280,10 +280,11 @@ static __device__ void render_main_independent(const chaos_render_args &a)
     const pool_ctl_ref pc = {&a.counters->pool[kExport ? 1 : 0][shard].live, &a.counters->pool[kExport ? 1 : 0][shard].reserved,
                              &a.counters->pool[kExport ? 1 : 0][shard].head};
     const uint32_t pool_epoch = a.pool_epoch + (kExport ? 1u : 0u);
+    unsigned int *const chaos_abort_flag = &a.counters->abort;
     bool keep_all = false;                                   /* this warp is the launch's last one: it parks nothing (any more) */
     uint32_t park_cooldown = 0, drain_wait = 0;
     const uint32_t drain_interval = min(max(max_iter / (nb * 64u), 2u), 16u);   /* blocks */
-    uint32_t stay_spins = 0; (void)stay_spins;
+    uint32_t stay_spins = 0;
     if (pooling && lane == 0) atomicAdd(pc.live, 1u);
 
     CHAOS_LS(lane_stats ls; ls.init();)
@@ -400,7 +401,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                         union { parked_t rec; uint4 w[(sizeof(parked_t) + 15u) / 16u]; } u;
                         const unsigned char *entry = ring + (size_t)((base + rank) % ring_size) * CHAOS_POOL_STRIDE;
                         const uint32_t want = pool_state(pool_epoch, base + rank, ring_size, true);
-                        uint32_t spins = 0; (void)spins;
+                        uint32_t spins = 0;
                         while (ld_volatile(reinterpret_cast<const unsigned int *>(entry + CHAOS_POOL_TAG_OFFSET)) != want) {
                             CHAOS_SPIN_GUARD(spins, "tag shard %u index %u want %x have %x head %u reserved %u", shard, base + rank, want,
                                              ld_volatile(reinterpret_cast<const unsigned int *>(entry + CHAOS_POOL_TAG_OFFSET)), ld_volatile(pc.head), ld_volatile(pc.reserved));
@@ -441,7 +442,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                     /* the entry is free once the consumer of the previous lap has read it; anything from an older launch is free */
                     if (index >= ring_size) {
                         const uint32_t free_now = pool_state(pool_epoch, index, ring_size, false);
-                        uint32_t spins = 0; (void)spins;
+                        uint32_t spins = 0;
                         while (ld_volatile(reinterpret_cast<const unsigned int *>(entry + CHAOS_POOL_TAG_OFFSET)) != free_now) {
                             CHAOS_SPIN_GUARD(spins, "free shard %u index %u want %x have %x", shard, index, free_now,
                                              ld_volatile(reinterpret_cast<const unsigned int *>(entry + CHAOS_POOL_TAG_OFFSET)));

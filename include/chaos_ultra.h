@@ -125,6 +125,10 @@ CHAOS_API chaos_status chaos_list_fractals(chaos_provider *p, const char **names
  * !force_reload returns the active one; otherwise the old one is closed (module unloaded) and the
  * module file is read again. */
 CHAOS_API chaos_status chaos_open(chaos_provider *p, const char *fractal_name, int force_reload, chaos_renderer **out);
+/* The provider's active renderer, NULL if there is none.  An unknown name leaves the active renderer untouched; a
+ * chaos_open that fails later (module file missing or corrupt) has already closed it, as the reference does
+ * (CudaFractalRendererProvider.java:52) -- the old handle is then dead and this returns NULL. */
+CHAOS_API chaos_renderer *chaos_active_renderer(const chaos_provider *p);
 
 /* ---- renderer: FractalRenderer.java:14-77 / CudaFractalRenderer.java ---- */
 /* initializeRendering(GLParams) :85-101.  palette_rgba: R in bits 0-7 (ImageHelpers.java:138-158); copied. */
@@ -162,7 +166,9 @@ CHAOS_API chaos_status chaos_get_stats(const chaos_renderer *r, chaos_stats *out
 CHAOS_API int chaos_debug_peek_counters(chaos_renderer *r, void *dst, size_t bytes);
 
 /* Multi-GPU: this renderer renders and composes only the row bands b with b % part_count ==
- * part_index, bands being band_rows pixel rows high (a multiple of 4).  part_count 1 = whole frame. */
+ * part_index, bands being band_rows pixel rows high (a multiple of 4).  part_count 1 = whole frame.
+ * While a partition is set chaos_render_fast renders a quality frame of the own bands: the previous frame's
+ * records of the other ranks' bands are not in this renderer's memory, so there is nothing valid to reproject. */
 CHAOS_API chaos_status chaos_set_partition(chaos_renderer *r, uint32_t part_index, uint32_t part_count, uint32_t band_rows);
 
 /* Multi-GPU, DEVICE mode: compose writes its bands into `device_ptr` instead of the renderer's own frame -- e.g. rank 0's

@@ -259,30 +259,60 @@ def test_partitions_compose_into_one_shared_target(cu, provider):
         r.setOutputTarget(target.data_ptr())
 
 
-def test_partitioned_fast_frame_equals_whole_frame(cu, provider):
+def test_fast_frame_of_a_partitioned_renderer_renders_its_bands_afresh(cu, provider):
+    """a rank that owns only its row bands has no valid previous frame around its pixels (the other bands were never
+    rendered here), so chaos_render_fast must not reproject: it renders a quality frame of the own bands"""
     case = cases.ADV_CASES[2]
     img0, img1 = cases.adv_segments(case)
-    r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
-    r.renderQuality(helpers.model_for(cu, case, image=img0, maxSS=case["maxSS0"]))
-    r.renderFast(helpers.model_for(cu, case, image=img1))
-    whole = r.downloadRecords()
-    # replicas of the previous frame + partitioned fast frame (what a multi-GPU zoom would do after an all-gather)
     part = __import__("importlib").import_module("chaos-ultra_b200.partition")
-    out = np.zeros_like(whole)
+    r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+    r.renderQuality(helpers.model_for(cu, case, image=img1, maxSS=case["maxSS0"]))
+    whole = r.downloadRecords()                            # quality frame of the new segment, unpartitioned
     for rank in range(2):
         r.freeRenderingResources()
         r.initializeRendering(case["W"], case["H"], None, cu.OUTPUT_DEVICE)
-        r.renderQuality(helpers.model_for(cu, case, image=img0, maxSS=case["maxSS0"]))
         r.setPartition(rank, 2, 8)
-        # set_partition marks the cache dirty (a different partition cannot reuse blindly); re-render frame 0 whole
-        r.setPartition(0, 1, 32)
-        r.renderQuality(helpers.model_for(cu, case, image=img0, maxSS=case["maxSS0"]))
-        r._lib.chaos_set_partition  # noqa: B018  (documented entry point)
-        r.renderFast(helpers.model_for(cu, case, image=img1))
+        r.renderQuality(helpers.model_for(cu, case, image=img0, maxSS=case["maxSS0"]))   # the cache is clean now ...
+        r.renderFast(helpers.model_for(cu, case, image=img1, maxSS=case["maxSS0"]))      # ... and still nothing is reprojected
         got = r.downloadRecords()
+        assert r.stats().reuse_ms == 0
         for r0, r1 in part.rows_owned(rank, 2, case["H"], 8):
-            out[r0:r1] = got[r0:r1]
-    helpers.assert_records_equal(out, whole, "fast frame rows")
+            helpers.assert_records_equal(got[r0:r1], whole[r0:r1], "rank %d rows %d..%d" % (rank, r0, r1))
+            assert not got["isReused"][r0:r1].any()
+    r.setPartition(0, 1, 32)
+
+
+def test_custom_parameter_texts_are_validated_like_the_java_parsers(cu, provider):
+    g = provider.getRenderer("newton generic", False)
+    for bad in ('{"coefficients":["a",null,true,1],"roots":[[1,0],[0,1],[0,-1]]}',       # Gson getAsDouble throws
+                '{"coefficients":[1,0,0,-1],"roots":[[1,"x"],[0,1],[0,-1]]}',
+                '"just a string"', "[" * 5000):                                           # nesting limit, no stack overflow
+        with pytest.raises(cu.IllegalArgumentException):
+            g.setFractalCustomParams(bad)
+    g.setFractalCustomParams(cases.N3)
+    n = provider.getRenderer("newton colored by iterations", False)
+    with pytest.raises(cu.IllegalArgumentException, match="colorMagnifier"):
+        n.setFractalCustomParams('{"colorMagnifier": "7",' + cases.N3[1:])
+    t = provider.getRenderer("test", False)
+    for bad in (" 7", "+", "7 ", "99999999999", "0x10", ""):                              # Integer.parseInt
+        with pytest.raises(cu.IllegalArgumentException, match="NumberFormatException"):
+            t.setFractalCustomParams(bad)
+    t.setFractalCustomParams("-3")
+    t.setFractalCustomParams("+12")
+
+
+def test_failed_open_does_not_leave_a_dangling_renderer(cu, tmp_path):
+    shutil.copy(cu.DEFAULT_KERNELS_DIR / "mandelbrot.cubin", tmp_path / "mandelbrot.cubin")
+    with cu.CudaFractalRendererProvider(kernels_dir=tmp_path) as prov:
+        a = prov.getRenderer("mandelbrot", False)
+        with pytest.raises(cu.IllegalArgumentException, match="Unknown fractal"):
+            prov.getRenderer("nope", False)
+        assert a._h is not None and a.getFractalName() == "mandelbrot"     # an unknown name closes nothing
+        with pytest.raises(cu.IllegalArgumentException, match="julia.cubin"):
+            prov.getRenderer("julia", False)                                # registered, file missing: the old one is closed first (:52)
+        assert a._h is None and prov._active is None
+        b = prov.getRenderer("mandelbrot", False)                           # and the provider still works
+        assert b.getFractalName() == "mandelbrot"
 
 
 def test_frame_driver_zoom_session_on_the_gpu(cu, provider, tmp_path):

@@ -13,7 +13,7 @@ import oracle
 
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
-ENGINES = [0, 1]
+ENGINES = [0, 1, 2]
 
 
 def _ids(cs):
@@ -46,7 +46,9 @@ def test_main_matches_oracle(cu, provider, engine, case):
     st = r.stats()
     assert st.pixel_iterations == want.pixel_iterations
     assert st.samples == want.samples
-    assert st.kernel_launches in (2, 5, 8)   # one launch + compose; or passes A, classify, order, B + compose; or A, classify, order, B, compose, C, D, composeTiles
+    # engines 0/1: one launch + compose; or passes A, classify, order, B + compose; or A, classify, order, B, compose, C, D, composeTiles.
+    # engine 2: passes A and C (and the single launch) are probe -> long -> finish chains
+    assert st.kernel_launches in ((4, 7, 12) if engine == 2 else (2, 5, 8))
     # compose: palette lookup must be identical
     pal = cu.createDefaultColorPalette()
     assert (r.outputRGBA() == oracle.compose(case["fractal"], want.records, pal, case["maxSS"])).all()
@@ -191,7 +193,7 @@ FULL_CASES = [
 @pytest.mark.parametrize("case", FULL_CASES, ids=_ids(FULL_CASES))
 def test_engines_agree_at_full_size(cu, provider, case):
     out = {}
-    for eng in (0, 1):
+    for eng in (0, 1, 2):
         os.environ["CHAOS_ENGINE"] = str(eng)
         try:
             provider.getRenderer("test", False)   # drop the active renderer so the engine choice is re-read
@@ -201,9 +203,10 @@ def test_engines_agree_at_full_size(cu, provider, case):
             out[eng] = (r.downloadRecords(), st.pixel_iterations, st.samples, r.outputRGBA())
         finally:
             os.environ.pop("CHAOS_ENGINE", None)
-    helpers.assert_records_equal(out[1][0], out[0][0], case["name"] + " engine 1 vs engine 0")
-    assert out[1][1] == out[0][1] and out[1][2] == out[0][2]
-    assert (out[1][3] == out[0][3]).all()
+    for eng in (1, 2):
+        helpers.assert_records_equal(out[eng][0], out[0][0], case["name"] + " engine %d vs engine 0" % eng)
+        assert out[eng][1] == out[0][1] and out[eng][2] == out[0][2]
+        assert (out[eng][3] == out[0][3]).all()
     # sanity of the exact counter: every sample contributes between 0 and maxIter trips
     assert out[1][2] >= case["W"] * case["H"]
     assert out[1][1] <= out[1][2] * case["maxIter"]
@@ -217,7 +220,7 @@ REF_FULL = [
     dict(name="ref_c2_4k_a8_f64", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.5, 0.0, 2.0, 3840, 2160), maxIter=10000,
          maxSS=8.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
     dict(name="ref_c2ex2_4k_a8_f64", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.235125, 0.827215, 4.0e-5, 3840, 2160),
-         maxIter=2500, maxSS=8.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
+         maxIter=10000, maxSS=8.0, flags=cases.A, double=True, julia_c=(0.0, 0.0), amplifier=10),
     dict(name="ref_c2_4k_a8_f32", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.5, 0.0, 2.0, 3840, 2160), maxIter=2500,
          maxSS=8.0, flags=cases.A, double=False, julia_c=(0.0, 0.0), amplifier=10),
     dict(name="ref_c4_2k_1s_f64", fractal="mandelbrot", W=2048, H=2048,
@@ -246,28 +249,72 @@ def test_full_size_frame_matches_live_reference(cu, provider, case):
     assert (rgba == want_rgba).all()
 
 
+# ---- config c4 at BASELINE.json's full size: 8192 x 8192, maxIter 200000 (2 M vote tiles, 1 GiB of records, 10^11-trip
+# ---- counters), one sample per pixel and adaptive maxSS 4 (every pass of the multi-sample chain at that size)
+C4_FULL = [
+    dict(name="ref_c4_8k_1s_f64", fractal="mandelbrot", W=8192, H=8192,
+         image=cases.seg(-0.551042868375875, 0.62714332109057, 8.00592947491907e-9, 8192, 8192), maxIter=200000, maxSS=1.0, flags=0,
+         double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="ref_c4_8k_a4_f64", fractal="mandelbrot", W=8192, H=8192,
+         image=cases.seg(-0.551042868375875, 0.62714332109057, 8.00592947491907e-9, 8192, 8192), maxIter=200000, maxSS=4.0, flags=cases.A,
+         double=True, julia_c=(0.0, 0.0), amplifier=10),
+]
+
+
+@pytest.mark.skipif(not _have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", C4_FULL, ids=_ids(C4_FULL))
+def test_c4_full_size_matches_live_reference(cu, provider, case):
+    r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+    r.renderQuality(helpers.model_for(cu, case))
+    st = r.stats()
+    got, rgba = r.downloadRecords(), r.outputRGBA()
+    r.freeRenderingResources()                       # 2 GiB of records back before the reference allocates its own
+    with oracle.RefRun(case["fractal"], "src") as rr:
+        want = rr.main(case["W"], case["H"], case["image"], case["maxIter"], case["maxSS"], case["flags"], case["double"])
+        for f in helpers.FIELDS:                     # field by field: a structured 1 GiB compare would need 1 GiB temporaries per field anyway
+            a, b = got[f], want[f]
+            if a.dtype.kind == "f":
+                a, b = a.view(np.uint32), b.view(np.uint32)
+            assert np.array_equal(a, b), "%s: field %s differs at %d pixels" % (case["name"], f, int((a != b).sum()))
+        samples = int(want["weight"].astype(np.uint64).sum())
+        del got
+        want_rgba = rr.compose(want, cu.createDefaultColorPalette(), case["maxSS"], False)
+    assert np.array_equal(rgba, want_rgba)
+    # the exact counters at this size: every sample is counted once, an orbit contributes 1 .. maxIter trips, and for one
+    # sample per pixel the total follows from the records (inside points are stored as 0 and count maxIter)
+    assert st.samples == samples
+    assert st.samples <= st.pixel_iterations <= st.samples * case["maxIter"]
+    if case["maxSS"] == 1.0:
+        v = want["value"].astype(np.uint64)
+        assert st.pixel_iterations == int(v.sum()) + int((v == 0).sum()) * case["maxIter"]
+
+
 @pytest.mark.skipif(not _have_ref(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("double", [False, True], ids=["f32", "f64"])
 def test_zoom_sequence_4k_matches_live_reference(cu, provider, double):
-    """config c3 shape: frame 0 quality, then fast frames, every frame compared with the reference's kernels fed with the
-    reference's own previous frame (so errors cannot hide by accumulating identically)."""
+    """config c3 at full length: frame 0 quality, then 119 fast frames.  Every frame's RGBA is compared with the
+    reference's kernels fed with the reference's own previous frame (so errors cannot hide by accumulating
+    identically); the records are compared bit for bit at frames 1, 2, 3, 4, 30, 60 and 119."""
     W, H, focus = 3840, 2160, (1920, 1080)
     flags = cases.A | cases.FOV | cases.REUSE | cases.ZOOMING | cases.ZOOM_IN
     base = dict(name="zoom4k", fractal="mandelbrot", W=W, H=H, maxIter=1600, maxSS=2.0, flags=flags, double=double,
                 julia_c=(0.0, 0.0), amplifier=10, focus=focus)
     seg = cases.seg(-0.748, 0.1, 2.0 if not double else 1.0e-4, W, H)
+    pal = cu.createDefaultColorPalette()
     r = helpers.open_renderer(cu, provider, dict(base, image=seg), mode=cu.OUTPUT_DEVICE)
     r.renderQuality(helpers.model_for(cu, dict(base, image=seg)))
     with oracle.RefRun("mandelbrot", "src") as rr:
         ref_prev = rr.main(W, H, seg, 1600, 2.0, flags, double)
         helpers.assert_records_equal(r.downloadRecords(), ref_prev, "frame 0")
-        for f in range(1, 5):
+        for f in range(1, 120):
             new_seg = cases.zoom_at(seg, W, H, focus, True)
             r.renderFast(helpers.model_for(cu, dict(base, image=new_seg)))
-            got = r.downloadRecords()
             want = rr.advanced(W, H, new_seg, 1600, 2.0, flags, seg, ref_prev, focus, double)
-            helpers.assert_records_equal(got, want, "frame %d" % f)
-            assert got["isReused"].mean() > 0.9 and (got["weightOfNewSamples"] > 0).sum() > 10000
+            assert np.array_equal(r.outputRGBA(), rr.compose(want, pal, 2.0, False)), "RGBA of frame %d" % f
+            if f in (1, 2, 3, 4, 30, 60, 119):
+                got = r.downloadRecords()
+                helpers.assert_records_equal(got, want, "frame %d" % f)
+                assert got["isReused"].mean() > 0.9 and (got["weightOfNewSamples"] > 0).sum() > 10000
             seg, ref_prev = new_seg, want
 
 
@@ -390,8 +437,8 @@ def test_exported_rounds_change_nothing(cu, provider, case):
     helpers.assert_records_equal(out[1][0], out[0][0], case["name"] + " exported vs kept")
     assert out[1][1] == out[0][1] and out[1][2] == out[0][2]
     assert (out[1][3] == out[0][3]).all()
-    assert out[0][5] == 5
-    assert out[1][5] == (8 if 3 <= round(case["maxSS"]) <= 10 else 5)
+    assert out[0][5] == 7                         # probe, long, finish, classify, order, pass B, compose
+    assert out[1][5] == (12 if 3 <= round(case["maxSS"]) <= 10 else 7)   # + compose of the final tiles, probe, long, finish, replay
 
 
 # ---- strands (chaos_abi.cpp): a multi-pass frame cut into interleaved sets of row bands whose pass chains run next to

@@ -1,11 +1,11 @@
 #!/bin/bash
 # experiment: bench a list of workloads under each of the given environment settings
-# usage: SETTINGS="A=1,B=2 A=2,B=2" WORKLOADS="c2 c4" tools/sweep_env.sh
+# usage: SETTINGS="A=1+B=2 A=2+B=2,3" WORKLOADS="c2 c4" tools/sweep_env.sh     (variables of one setting are joined by +)
 cd "$(dirname "$0")/.."
-for set in ${SETTINGS:-none}; do
+for set in ${SETTINGS:-X=0}; do
   for w in ${WORKLOADS:-c2 c2ex2 c2f32}; do
-    tag=$(echo "$set" | tr ',=/' '___')
-    env $(echo "$set" | tr ',' ' ') timeout 300 python bench.py --workload $w --steps ${STEPS:-20} --warmup 3 --no-cpu-baseline --no-full-trips > gpurun_out/env_${tag}_$w.json 2> /dev/null
+    tag=$(echo "$set" | tr '+,=/:' '_____')
+    env $(echo "$set" | tr '+' ' ') timeout 300 python bench.py --workload $w --steps ${STEPS:-20} --warmup 3 --no-cpu-baseline --no-full-trips > gpurun_out/env_${tag}_$w.json 2> /dev/null
     python - <<P
 import json
 try:
