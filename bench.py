@@ -1,22 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- the headline benchmark of the chaos-ultra B200 render backend.
 
-A *step* is one quality frame of the hot path: iteration kernel (adaptive supersampling) + compose.
-Workloads are the configurations of BASELINE.json; the default is configs[1]:
-mandelbrot 3840x2160, maxIter 10000, adaptive supersampling (maxSS 8), FP64, full-set viewport.
+A *step* is one frame of the hot path through the reference-facing C ABI.  The headline workload is configs[1] of
+BASELINE.json: mandelbrot 3840x2160, maxIter 10000, adaptive supersampling (maxSS 8), FP64, full-set view.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference] [--no-extras]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 ONE JSON line on stdout (rank 0).  Keys beyond the base contract:
-  value      pixel-iterations/s, whole job, records + RGBA staying in HBM (DEVICE output mode)
-  e2e        the same metric through the reference-facing C ABI with HOST output: every step ends with the
-             composed RGBA frame in pinned host memory
-  roofline   dominant kernel (fractalRenderMain*): FP pipe utilisation against the FMA issue peak measured in
-             this run with bench_kernels/peak.cubin (MEASURED_PEAKS.json has no FP64/FP32 figure)
-  cpu_baseline  the oracle port of the same sampling algorithm on the host cores, bounded sample
---impl reference runs the reference's OWN kernels (oracle/_ref: src/main/cuda compiled by nvcc 12.9 for
-sm_100a, launched like the Java host does) on the same device; the reference has no CPU implementation.
+  value        pixel-iterations/s (the reference loop's trip count of the frame per second), whole job, frame in HBM
+  executed_per_s   the trips the FP pipe really iterated per second (the rest is PROVEN, see config.work_accounting)
+  e2e          the same metric with the composed RGBA frame of every step in HOST memory: one GPU -- compose writes the
+               library's pinned frame; N GPUs -- every rank's compose writes its bands over its own PCIe link into one
+               frame in host shared memory; e2e.rgba_crc32 is ASSERTED against tests/golden/workloads.json
+  roofline     the iteration kernels against the FP64/FP32 FMA issue peak measured in this run (bench_kernels/peak.cubin)
+  extra        the other BASELINE.json configurations in the same record (c4 deep zoom at every N, c3/c1/c5 at N = 1)
+  cpu_baseline the oracle port on the host cores, bounded sample; baselines.reference_ptx92 the reference's shipped
+               CUDA 9.2 PTX on this GPU (N = 1)
+--impl reference runs the reference's OWN kernels (oracle/_ref: src/main/cuda compiled by nvcc 12.9 for sm_100a, and
+the shipped PTX) with the Java host's launch sequence; that process never loads this backend's library.
 """
 from __future__ import annotations
 
@@ -28,6 +30,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
@@ -221,6 +224,28 @@ def dist_env():
     return rank, world, local
 
 
+def load_constants():
+    """tests/golden/workloads.json: exact work count and frame checksum of every workload (make_workload_constants.py)"""
+    try:
+        return json.loads((ROOT / "tests" / "golden" / "workloads.json").read_text())
+    except Exception:
+        return {}
+
+
+def frame_crc(frame):
+    import numpy as np
+    return zlib.crc32(np.ascontiguousarray(frame).tobytes()) & 0xFFFFFFFF
+
+
+def workload_config(name, wl):
+    """the `config` object: identical in both arms (the driver compares them)"""
+    return {"workload": name + ": " + wl["desc"], "width": wl["W"], "height": wl["H"], "max_iterations": wl["maxIter"],
+            "max_super_sampling": wl["maxSS"], "adaptive_ss": bool(wl["flags"] & A),
+            "l2": "no input is re-read between steps (inputs are viewport scalars); the %d MB of records written per step exceed the 126 MB L2"
+                  % (wl["W"] * wl["H"] * 16 // 1000000) if wl["W"] * wl["H"] * 16 > 126e6 else
+                  "inputs are viewport scalars, nothing is re-read between steps; every step rewrites all %d MB of records" % (wl["W"] * wl["H"] * 16 // 1000000)}
+
+
 def make_model(cu, wl):
     m = cu.RenderingModel(canvasWidth=wl["W"], canvasHeight=wl["H"])
     m.setPlaneSegmentFromCenter(wl["center"][0], wl["center"][1], wl["zoom"])
@@ -233,288 +258,337 @@ def make_model(cu, wl):
     return m
 
 
-def run_ours(args, wl, rank, world, local):
-    import numpy as np
-    import torch
-    cu = importlib.import_module("chaos-ultra_b200")
+BAND_ROWS = 32
 
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+class Job:
+    """one rank of the run: device, process group, provider, host shared memory of the job"""
+
+    def __init__(self, rank, world, local):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.local = rank, world, local
+        torch.cuda.set_device(local)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            self.dist = dist
+        self.cu = importlib.import_module("chaos-ultra_b200")
+        self.part = importlib.import_module("chaos-ultra_b200.partition")
+        self.prov = self.cu.CudaFractalRendererProvider(kernels_dir=os.environ.get("CHAOS_KERNELS_DIR"), device=local)   # (diagnostic builds)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="max"):
+        if self.dist is None:
+            return list(values)
+        t = self.torch.tensor(list(values), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def renderer(self, wl):
+        r = self.prov.getRenderer(wl["fractal"], False)
+        if wl["fractal"] == "julia":
+            r.setFractalCustomParams("%r;%r" % tuple(wl["julia_c"]))
+        return r
+
+    def close(self):
+        self.prov.close()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_quality_loop(job, wl, to_host, steps, warmup, sampler=None):
+    """W untimed + K timed quality frames.  One GPU: the renderer's own frame (device memory, or the library's pinned host
+    frame when to_host).  N GPUs: every rank renders and composes its row bands straight into ONE frame -- rank 0's device
+    frame (CUDA IPC: the bands cross NVLink as the compose kernel's stores) or, when to_host, a frame in host shared
+    memory that every GPU writes over its own PCIe link -- and every render call ends at the library's frame barrier.
+    Device time of a step = the slowest rank's frame (CUDA events on the launching stream, first kernel .. compose end);
+    wall time = host clock between the barrier + synchronize brackets, MAX over ranks."""
+    cu, world, rank = job.cu, job.world, job.rank
+    W, H = wl["W"], wl["H"]
+    r = job.renderer(wl)
+    if r.getState() == cu.STATE_READY_TO_RENDER:
+        r.freeRenderingResources()
+    model = make_model(cu, wl)
+    shm = None
+    if world == 1:
+        r.initializeRendering(W, H, None, cu.OUTPUT_HOST if to_host else cu.OUTPUT_DEVICE)
+        if os.environ.get("CHAOS_EMULATE_PART"):   # diagnostics: what ONE rank of an N-GPU run does
+            pi, pn = map(int, os.environ["CHAOS_EMULATE_PART"].split(":"))
+            r.setPartition(pi, pn, BAND_ROWS)
+        exchange = "none"
+    else:
+        r.initializeRendering(W, H, None, cu.OUTPUT_DEVICE)
+        r.setPartition(rank, world, BAND_ROWS)
+        shm = job.part.JobSharedMemory(rank, world, H, W, job.dist)
+        if to_host:
+            shm.attach(r, host_target=True, barrier=True)
+            exchange = "every rank's compose kernel writes its bands into one frame in host shared memory over its own PCIe link; frame barrier in host shared memory"
+        else:
+            if not job.part.share_frame_native(r, rank, world, job.dist):
+                raise RuntimeError("CUDA IPC refused: cannot map rank 0's frame")
+            shm.attach(r, host_target=False, barrier=True)
+            exchange = "every rank's compose kernel writes its bands into rank 0's device frame over NVLink (CUDA IPC); frame barrier in host shared memory"
+    per_step = []
+    acc = dict(iters=0, skipped=0, launches=0, render_ms=0.0, compose_ms=0.0)
+    t0 = 0.0
+    for it in range(warmup + steps):
+        if it == warmup:
+            job.barrier()
+            if sampler is not None:
+                sampler.start()
+            t0 = time.perf_counter()
+        r.renderQuality(model)
+        if it >= warmup:
+            st = r.stats()
+            per_step.append(st.frame_ms)
+            acc["iters"] += st.pixel_iterations; acc["skipped"] += st.skipped_iterations; acc["launches"] += st.kernel_launches
+            acc["render_ms"] += st.render_ms; acc["compose_ms"] += st.compose_ms
+    job.barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler is not None else None
+    frame = None
+    if rank == 0:      # the frame of the last step, for the checksum (outside the timed region)
+        frame = (shm.frame.copy() if (shm is not None and to_host) else r.outputRGBA().copy())
+    job.barrier()
+    slowest = job.reduce(per_step, "max")                    # per step: the slowest rank's frame
+    wall, render_ms, compose_ms = job.reduce([wall, acc["render_ms"], acc["compose_ms"]], "max")
+    iters, skipped, launches = [int(v) for v in job.reduce([acc["iters"], acc["skipped"], acc["launches"]], "sum")]
+    if shm is not None:
+        r.setFrameBarrier(0, 0)
+        r.setOutputTarget(0)
+        shm.close(job.dist)
+    r.freeRenderingResources()
+    return dict(device_seconds=sum(slowest) * 1e-3, seconds=wall, iters=iters, skipped=skipped, launches=launches, render_ms=render_ms,
+                compose_ms=compose_ms, clocks=clocks, exchange=exchange, frame=frame, steps=steps)
+
+
+def check_frame(name, frame, constants, what):
+    """the frame that was timed must be THE frame of this workload (tests/golden/workloads.json, cross-checked against the
+    reference kernels by tests/test_bench_constants_gpu.py); a wrong frame voids the number, so it is an error"""
+    crc = frame_crc(frame)
+    want = constants.get(name, {}).get("rgba_crc32")
+    if want is not None and crc != want:
+        raise SystemExit("bench: %s frame of %s has crc32 %08x, expected %08x -- the timed frame is wrong" % (what, name, crc, want))
+    return {"rgba_crc32": crc, "rgba_crc32_expected": want, "rgba_crc32_ok": None if want is None else crc == want}
+
+
+def quality_block(job, name, wl, steps, warmup, constants, sampler=None):
+    """device-resident and end-to-end figures of one quality-frame workload, checked against the committed constants"""
+    dev = timed_quality_loop(job, wl, False, steps, warmup, sampler)
+    e2e = timed_quality_loop(job, wl, True, steps, warmup)
+    out = None
+    if job.rank == 0:
+        px = wl["W"] * wl["H"]
+        want_iters = constants.get(name, {}).get("pixel_iterations")
+        if want_iters is not None and dev["iters"] != want_iters * steps and not os.environ.get("CHAOS_EMULATE_PART"):
+            raise SystemExit("bench: %s counted %d pixel-iterations per step, expected %d" % (name, dev["iters"] // steps, want_iters))
+        out = {"ms_per_step": dev["device_seconds"] * 1e3 / steps, "value": dev["iters"] / dev["device_seconds"], "unit": "pixel-iterations/s",
+               "executed_per_s": (dev["iters"] - dev["skipped"]) / dev["device_seconds"], "frames_per_s": steps / dev["device_seconds"],
+               "wall_ms_per_step": dev["seconds"] * 1e3 / steps, "steps": steps, "warmup": warmup,
+               "pixel_iterations_per_step": dev["iters"] // steps, "executed_pixel_iterations_per_step": (dev["iters"] - dev["skipped"]) // steps,
+               "device_ms_per_step": {"render_kernels": dev["render_ms"] / steps, "compose_kernel": dev["compose_ms"] / steps},
+               "frame_check": check_frame(name, dev["frame"], constants, "device"),
+               "e2e": dict({"value": e2e["iters"] / e2e["seconds"], "unit": "pixel-iterations/s", "ms_per_step": e2e["seconds"] * 1e3 / steps,
+                            "frames_per_s": steps / e2e["seconds"], "h2d_bytes_per_step": 512 * job.world, "d2h_bytes_per_step": px * 4 + 32 * job.world},
+                           **check_frame(name, e2e["frame"], constants, "end-to-end")),
+               "gpu_launches": dev["launches"], "parallelism": "1 GPU" if job.world == 1 else
+               "row bands of %d px dealt round-robin over %d GPUs; %s" % (BAND_ROWS, job.world, dev["exchange"]),
+               "e2e_exchange": e2e["exchange"]}
+    return out, dev
+
+
+def run_ours(args, wl, rank, world, local):
+    job = Job(rank, world, local)
+    cu = job.cu
     if args.engine is not None:
         os.environ["CHAOS_ENGINE"] = str(args.engine)
-    prov = cu.CudaFractalRendererProvider(kernels_dir=os.environ.get("CHAOS_KERNELS_DIR"), device=local)   # (diagnostic builds)
-    r = prov.getRenderer(wl["fractal"], False)
-    if wl["fractal"] == "julia":
-        r.setFractalCustomParams("%r;%r" % tuple(wl["julia_c"]))
+    constants = load_constants()
     W, H = wl["W"], wl["H"]
-    band_rows = 32
-    model = make_model(cu, wl)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    class DevBuf:   # wraps the renderer's device RGBA frame for torch (NCCL gather of row bands)
-        def __init__(self, ptr):
-            self.__cuda_array_interface__ = {"shape": (H, W), "typestr": "<i4", "data": (ptr, False), "version": 2}
-
-    part = importlib.import_module("chaos-ultra_b200.partition")
-
-    def gather_to_rank0(frame):
-        """the one exchange step of the multi-GPU path: composed RGBA row bands -> rank 0, NCCL send/recv over NVLink"""
-        part.gather_bands(frame, rank, world, band_rows, dist)
-
-    def timed_loop(mode, steps, warmup, sampler=None):
-        """W untimed + K timed steps.  Device time: one GPU -- the library's CUDA events around each frame's kernels
-        (stats.frame_ms, recorded on the stream the kernels are launched on), summed; several GPUs -- torch CUDA events
-        bracketing the K steps on the stream that carries the exchange step (every step ends there).  The host clock
-        between the two barriers is kept as well.  All reduced with MAX over ranks."""
-        if r.getState() == cu.STATE_READY_TO_RENDER:
-            r.freeRenderingResources()
-        r.initializeRendering(W, H, None, mode)
-        r.setPartition(rank, world, band_rows)
-        if world == 1 and os.environ.get("CHAOS_EMULATE_PART"):   # diagnostics: what ONE rank of an N-GPU run does
-            pi, pn = map(int, os.environ["CHAOS_EMULATE_PART"].split(":"))
-            r.setPartition(pi, pn, band_rows)
-        frame = shared = token = None
-        if world > 1:
-            frame = torch.as_tensor(DevBuf(r.outputRGBADevicePointer()), device="cuda") if mode == cu.OUTPUT_DEVICE else None
-            # compose straight into rank 0's frame over NVLink (CUDA IPC); falls back to the NCCL band gather
-            shared = part.share_frame(r, rank, world, dist) if (frame is not None and not args.nccl_gather) else None
-            token = torch.zeros(1, device="cuda", dtype=torch.int32)
-        host_frame = torch.empty((H, W), dtype=torch.int32).pin_memory() if (world > 1 and args.e2e_host_copy) else None
-        iters = launches = skipped = 0
-        rms = cms = fms = 0.0
-        e_start = e_end = None
-        for it in range(warmup + steps):
-            if it == warmup:
-                barrier()
-                if sampler is not None:
-                    sampler.start()
-                t0 = time.perf_counter()
-                iters = launches = skipped = 0
-                rms = cms = fms = 0.0
-                if world > 1:
-                    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e_start.record()
-            r.renderQuality(model)
-            st = r.stats()
-            iters += st.pixel_iterations
-            skipped += st.skipped_iterations
-            launches += st.kernel_launches
-            rms += st.render_ms
-            cms += st.compose_ms
-            fms += st.frame_ms
-            if world > 1 and frame is not None:
-                if shared is not None:
-                    dist.all_reduce(token)                  # the exchange step: every rank's bands have landed in rank 0's frame
-                else:
-                    gather_to_rank0(frame)
-                if host_frame is not None:
-                    if rank == 0:
-                        host_frame.copy_(frame, non_blocking=False)
-                    dist.all_reduce(token)                  # nobody composes the next frame into rank 0's before it is out
-        if e_end is not None:
-            e_end.record()
-        barrier()
-        dt = time.perf_counter() - t0
-        clocks = sampler.stop() if sampler is not None else None
-        dev_ms = e_start.elapsed_time(e_end) if e_end is not None else fms
-        if world > 1:
-            t = torch.tensor([dt, rms, cms, dev_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt, rms, cms, dev_ms = t.tolist()
-            c = torch.tensor([iters, launches, skipped], device="cuda", dtype=torch.int64)
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
-            iters, launches, skipped = c.tolist()
-        exchange = "none" if world == 1 else ("compose writes into rank 0's frame over NVLink (CUDA IPC) + completion all-reduce" if shared is not None
-                                              else "NCCL send/recv of row bands to rank 0")
-        if shared is not None:
-            torch.cuda.synchronize()
-            shared.close()
-        return dict(seconds=dt, device_seconds=dev_ms * 1e-3, iters=iters, skipped=skipped, launches=launches, render_ms=rms,
-                    compose_ms=cms, exchange_ms=max(0.0, dev_ms - fms) if world > 1 else 0.0, clocks=clocks, exchange=exchange)
-
     sampler = ClockSampler(local) if rank == 0 else None
-    dev = timed_loop(cu.OUTPUT_DEVICE, args.steps, args.warmup, sampler)
-    # e2e: the public C-ABI call with HOST output (single GPU: compose writes the pinned frame; multi GPU: bands are
-    # gathered on the device, then rank 0 copies the frame to pinned host memory)
-    args.e2e_host_copy = True
-    e2e_mode = cu.OUTPUT_HOST if world == 1 else cu.OUTPUT_DEVICE
-    e2e = timed_loop(e2e_mode, args.steps, args.warmup)
-    if rank == 0 and world == 1:
-        frame_host = r.outputRGBA()
-        checksum = int(np.bitwise_xor.reduce(frame_host.ravel()))
-    else:
-        checksum = None
-    # the same frame with every trip executed and tested (CHAOS_SHORTCUTS=0): what the iteration kernel does at full work
+    head, dev = quality_block(job, args.workload, wl, args.steps, args.warmup, constants, sampler)
+    # the same frame with every trip executed and tested (CHAOS_SHORTCUTS=0): what the iteration kernels do at full work
     full = None
     if world == 1 and not args.no_full_trips and os.environ.get("CHAOS_SHORTCUTS") is None:
         os.environ["CHAOS_SHORTCUTS"] = "0"
         try:
-            r.close()
-            r = prov.getRenderer(wl["fractal"], True)
-            if wl["fractal"] == "julia":
-                r.setFractalCustomParams("%r;%r" % tuple(wl["julia_c"]))
-            full = timed_loop(cu.OUTPUT_DEVICE, max(2, min(args.steps, 5)), 3)
-            full["steps"] = max(2, min(args.steps, 5))
+            job.prov.getRenderer(wl["fractal"], True)        # the knob is read when a renderer is opened
+            full = timed_quality_loop(job, wl, False, max(2, min(args.steps, 5)), 3)
         finally:
             os.environ.pop("CHAOS_SHORTCUTS", None)
-
+            job.prov.getRenderer(wl["fractal"], True)
+    # the other configurations of BASELINE.json in the same record
+    extra = {}
+    if args.extras and args.workload == "c2":
+        blk, _ = quality_block(job, "c4", WORKLOADS["c4"], 5, 3, constants)
+        if rank == 0:
+            extra["c4"] = dict(blk, workload="c4: " + WORKLOADS["c4"]["desc"])
+        if world == 1:
+            for name in ("c1", "c5"):
+                blk, _ = quality_block(job, name, WORKLOADS[name], 20, 3, constants)
+                extra[name] = dict(blk, workload=name + ": " + WORKLOADS[name]["desc"])
+            extra["c3"] = zoom_block(job, "c3", WORKLOADS["c3"], 119, 3, constants)
     out = None
     if rank == 0:
-        # value: pixel-iterations as SURVEY.md 8d defines them -- the trip counts of the reference's loop for this frame
-        # (exact integer from the device counter, equal to the oracle's by the parity tests) -- per second of device time
-        value = dev["iters"] / dev["device_seconds"]
-        e2e_value = e2e["iters"] / e2e["seconds"]
-        px = W * H
         executed = dev["iters"] - dev["skipped"]
         out = {
-            "metric": "pixel-iterations/s", "value": value, "unit": "pixel-iterations/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev["device_seconds"] * 1e3 / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if wl["double"] else "f32",
-            "data": "synthetic", "frames_per_s": args.steps / dev["device_seconds"],
-            "wall_ms_per_step": dev["seconds"] * 1e3 / args.steps,
-            "timing": "ms_per_step = CUDA events on the stream the kernels are launched on (first render kernel .. compose end"
-                      + "), summed over the K steps" + ("" if world == 1 else "; several GPUs: torch CUDA events bracketing the K steps on the stream of the exchange step") + ", MAX over ranks; "
-                      "wall_ms_per_step = host clock between the two barrier+synchronize brackets",
-            "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H, "max_iterations": wl["maxIter"],
-                       "max_super_sampling": wl["maxSS"], "adaptive_ss": bool(wl["flags"] & A),
-                       "parallelism": "1 GPU" if world == 1 else "row bands of %d px dealt round-robin over %d GPUs; %s" % (band_rows, world, dev["exchange"]),
-                       "pixel_iterations_per_step": dev["iters"] // args.steps,
-                       "executed_pixel_iterations_per_step": executed // args.steps,
-                       "work_accounting": "pixel_iterations = trips of the reference's loop for this frame (inside points count maxIterations). "
-                                          "Orbits whose state recurs bit for bit are PROVEN never to escape and stop early with the same result; "
-                                          "executed_pixel_iterations is what the FP pipe actually iterated. CHAOS_SHORTCUTS=0 executes every trip (see full_trips).",
-                       "l2": "no input is re-read between steps (inputs are viewport scalars); the %d MB record buffer written per step exceeds the 126 MB L2" % (px * 16 // 1000000),
-                       "engine": os.environ.get("CHAOS_ENGINE", "default"), "shortcuts": os.environ.get("CHAOS_SHORTCUTS", "default (3)")},
-            "e2e": {"value": e2e_value, "unit": "pixel-iterations/s", "h2d_bytes_per_step": 512, "d2h_bytes_per_step": px * 4 + 32,
-                    "ms_per_step": e2e["seconds"] * 1e3 / args.steps, "frames_per_s": args.steps / e2e["seconds"],
-                    "note": "chaos_render_quality through the C ABI, host clock around K synchronous calls; inputs are the chaos_params viewport struct "
-                            "(kernel parameter space), result = composed RGBA8 frame in pinned host memory" + ("" if world == 1 else " on rank 0 after the NCCL gather"),
-                    "rgba_xor_checksum": checksum},
-            "gpu_launches": dev["launches"],
-            "clocks": dev["clocks"],
-            "device_ms_per_step": {"render_kernel": dev["render_ms"] / args.steps, "compose_kernel": dev["compose_ms"] / args.steps,
-                                   "exchange_and_skew": dev["exchange_ms"] / args.steps},
+            "metric": "pixel-iterations/s", "value": head["value"], "unit": "pixel-iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64" if wl["double"] else "f32", "data": "synthetic", "frames_per_s": head["frames_per_s"],
+            "executed_per_s": head["executed_per_s"], "wall_ms_per_step": head["wall_ms_per_step"],
+            "timing": "ms_per_step = CUDA events on the stream the kernels are launched on (first render kernel .. compose end) per step, "
+                      "the slowest rank's frame of every step, summed over the K steps; wall_ms_per_step = host clock between the two "
+                      "barrier + synchronize brackets, MAX over ranks (several GPUs: it includes the frame barrier of every step)",
+            "config": workload_config(args.workload, wl),
+            "details": {"parallelism": head["parallelism"], "pixel_iterations_per_step": head["pixel_iterations_per_step"],
+                        "executed_pixel_iterations_per_step": head["executed_pixel_iterations_per_step"],
+                        "work_accounting": "pixel_iterations = trips of the reference's loop for this frame (inside points count maxIterations). "
+                                           "Orbits whose state recurs bit for bit are PROVEN never to escape and stop early with the same result; "
+                                           "executed_pixel_iterations is what the FP pipe actually iterated. CHAOS_SHORTCUTS=0 executes every trip (see roofline.full_trips).",
+                        "engine": os.environ.get("CHAOS_ENGINE", "default (2: orbit streams)"), "shortcuts": os.environ.get("CHAOS_SHORTCUTS", "default (3)"),
+                        "frame_check": head["frame_check"], "e2e_exchange": head["e2e_exchange"]},
+            "e2e": dict(head["e2e"], note="chaos_render_quality through the C ABI, host clock around K synchronous calls; inputs are the chaos_params viewport struct "
+                                          "(kernel parameter space), result = the composed RGBA8 frame in host memory, checksum asserted"),
+            "gpu_launches": head["gpu_launches"], "clocks": dev["clocks"], "device_ms_per_step": head["device_ms_per_step"],
         }
-        # roofline of the dominant kernel: the FP pipe.  peak = FMA lane-ops/s measured just now on this device.
-        # achieved counts FP instructions the kernel ISSUED at the least: 5 per executed trip (the untested scaled form;
-        # tested trips issue 6, unscaled ones up to 7), so frac is a lower bound of the pipe's utilisation and cannot
-        # exceed 1.  The reference form of the same work (7 instructions per reference trip, SURVEY.md 8d) is given beside it.
+        if extra:
+            out["extra"] = extra
+        # roofline of the iteration kernels: the FP pipe.  peak = FMA lane-ops/s measured just now on this device.  achieved counts
+        # the FP instructions the kernels issue AT THE LEAST: 5 per executed trip (the untested scaled form; tested trips issue 6,
+        # unscaled ones up to 7), so frac is a lower bound of the pipe's utilisation and cannot exceed 1.
         try:
             peak = measure_fma_peak(local, wl["double"])
             kernel_s = dev["render_ms"] * 1e-3
             min_ops = 5 if wl["double"] else 6
             achieved = executed / world * min_ops / kernel_s
+            multi = round(wl["maxSS"]) > 1
             out["roofline"] = {"bound": "fp64" if wl["double"] else "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9,
                                "unit": "G FP-lane-ops/s", "frac": achieved / peak,
                                "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0] if world == 1 else None,
                                "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1] if world == 1 else None,
-                               "kernel": ("fractalRenderMain%s" if round(wl["maxSS"]) <= 1 else "chaosPassA%s + chaosPassB%s + chaosPassC%s (the iteration kernels of a multi-sample frame)").replace("%s", "Double" if wl["double"] else "Float"),
-                               "peak_source": "measured in this run: bench_kernels/peak.cubin, independent FMA chains, best of 5 (not in MEASURED_PEAKS.json)",
-                               "achieved_definition": "%d FP instructions x %d executed pixel-iterations per launch sequence / render-kernel time (lower bound of issued instructions)"
+                               "kernel": ("chaosProbe%s + chaosLong%s + chaosFinish%s" + (" (passes A and C of a multi-sample frame) + chaosPassB%s" if multi else ""))
+                                         .replace("%s", "Double" if wl["double"] else "Float"),
+                               "peak_source": "measured in this run: bench_kernels/peak.cubin, independent FMA chains, best of 5 (MEASURED_PEAKS.json has no FP64/FP32 figure)",
+                               "achieved_definition": "%d FP instructions x %d executed pixel-iterations per step / time of the render kernels of a step (CUDA events, first render kernel .. last), max over ranks"
                                                       % (min_ops, executed // args.steps // world),
                                "reference_form": {"ops": "7 FP instructions x %d reference pixel-iterations" % (dev["iters"] // args.steps // world),
                                                   "G_ops_per_s": dev["iters"] / world * 7 / kernel_s / 1e9,
                                                   "ratio_to_peak": dev["iters"] / world * 7 / kernel_s / peak,
-                                                  "note": "work the reference's loop needs for this frame per second of this kernel; exceeds 1 when trips are proven instead of executed"},
-                               "note": "tensor cores and HBM do not bound this kernel (16 B stored per pixel)"}
+                                                  "note": "work the reference's loop needs for this frame per second of these kernels; exceeds 1 because trips are proven instead of executed"},
+                               "note": "tensor cores and HBM do not bound these kernels (16 B stored per pixel)"}
             if full is not None:
                 fk = full["render_ms"] * 1e-3
                 out["roofline"]["full_trips"] = {
-                    "ms_per_step": full["device_seconds"] * 1e3 / full["steps"], "render_kernel_ms": full["render_ms"] / full["steps"],
+                    "ms_per_step": full["device_seconds"] * 1e3 / full["steps"], "render_kernels_ms": full["render_ms"] / full["steps"],
                     "pixel_iterations_per_s": full["iters"] / full["device_seconds"],
                     "frac": full["iters"] * (6 if wl["double"] else 7) / fk / peak,
                     "note": "same frame, CHAOS_SHORTCUTS=0: every trip executed with its test (%d FP instructions per trip issued); "
-                            "this is the pipe utilisation of the iteration kernel at the reference's full work" % (6 if wl["double"] else 7)}
+                            "this is the pipe utilisation of the iteration kernels at the reference's full work" % (6 if wl["double"] else 7)}
         except Exception as e:  # measurement helper failed: say so rather than invent a peak
             out["roofline"] = {"bound": "fp64" if wl["double"] else "fp32", "achieved": None, "peak": None, "unit": "G FP-lane-ops/s",
                                "frac": None, "traffic": None, "error": repr(e)}
-        # host baseline: the oracle port on the host cores, bounded sample of the same workload (N=1 only)
-        if world == 1 and not args.no_cpu_baseline:
-            import oracle
-            cores = os.cpu_count() or 1
-            stride = args.cpu_row_stride
-            it_c, smp_c, sec = oracle.render_main_rows_threaded(wl["fractal"], W, H, model.planeSegment, wl["maxIter"], wl["maxSS"],
-                                                               wl["flags"], wl["double"], row_stride=stride, threads=cores,
-                                                               julia_c=wl.get("julia_c", (0.0, 0.0)))
-            out["cpu_baseline"] = {"value": it_c / sec, "unit": "pixel-iterations/s", "cores": cores, "kind": "port",
-                                   "sample": "every %dth vote-tile row of the same frame (%d pixel-iterations, %.1f s), oracle/chaos_oracle.c on %d threads"
-                                             % (stride, it_c, sec, cores)}
-    r.close()
-    prov.close()
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    # the two baselines north_star asks for, same run, N = 1 only (both execute oracle/: the cpu_baseline leg)
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        import oracle
+        cores = os.cpu_count() or 1
+        stride = args.cpu_row_stride
+        model = make_model(cu, wl)
+        it_c, smp_c, sec = oracle.render_main_rows_threaded(wl["fractal"], W, H, model.planeSegment, wl["maxIter"], wl["maxSS"],
+                                                           wl["flags"], wl["double"], row_stride=stride, threads=cores,
+                                                           julia_c=wl.get("julia_c", (0.0, 0.0)))
+        out["cpu_baseline"] = {"value": it_c / sec, "unit": "pixel-iterations/s", "cores": cores, "kind": "port",
+                               "sample": "every %dth vote-tile row of the same frame (%d pixel-iterations, %.1f s), oracle/chaos_oracle.c on %d threads"
+                                         % (stride, it_c, sec, cores)}
+        try:
+            job.prov.close()          # the reference kernels get the device to themselves
+            out["baselines"] = {"reference_ptx92": reference_figures(args.workload, wl, "ptx92", 1, max(3, min(args.steps, 5)), constants),
+                                "note": "the reference's shipped CUDA 9.2 PTX (src/main/cuda/fractals/*.ptx, assembled for sm_100a) on this GPU with the Java host's "
+                                        "launch sequence, timed after this backend's run, outside every timed region; the --impl reference arm times the nvcc 12.9 build of the same sources"}
+        except Exception as e:
+            out["baselines"] = {"reference_ptx92": None, "error": repr(e)}
+    job.close()
     return out
 
 
+def reference_figures(name, wl, kind, warmup, steps, constants):
+    """the reference's own kernels (oracle/_ref/<fractal>.<kind>.cubin) with the Java host's frame sequence; work count from
+    the committed constants, so nothing of this backend runs in (or is loaded into) the timing process"""
+    import numpy as np
+    import oracle
+    W, H = wl["W"], wl["H"]
+    image = seg(wl["center"][0], wl["center"][1], wl["zoom"], W, H)
+    iters_per_step = constants.get(name, {}).get("pixel_iterations")
+    with oracle.RefRun(wl["fractal"], kind) as rr:
+        if wl["fractal"] == "julia":
+            rr.write_constant("julia_c", np.array(wl["julia_c"], dtype=np.float64).tobytes())
+        pal = oracle.default_palette()
+        wall_ms, main_ms, comp_ms, rgba = rr.frames(W, H, image, wl["maxIter"], wl["maxSS"], wl["flags"], pal, wl["double"], warmup, steps, True)
+        wall_dev, main_dev, comp_dev, _ = rr.frames(W, H, image, wl["maxIter"], wl["maxSS"], wl["flags"], pal, wl["double"], 1, steps, False)
+    crc = frame_crc(rgba)
+    want = constants.get(name, {}).get("rgba_crc32")
+    return {"kind": kind, "ms_per_step": wall_dev / steps, "frames_per_s": steps / (wall_dev * 1e-3),
+            "value": None if iters_per_step is None else iters_per_step * steps / (wall_dev * 1e-3), "unit": "pixel-iterations/s",
+            "e2e": {"value": None if iters_per_step is None else iters_per_step * steps / (wall_ms * 1e-3), "unit": "pixel-iterations/s",
+                    "ms_per_step": wall_ms / steps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 4},
+            "device_ms_per_step": {"render_kernel": main_dev / steps, "compose_kernel": comp_dev / steps}, "steps": steps,
+            "rgba_crc32": crc, "same_frame_as_this_backend": None if want is None else (crc == want if kind == "src" else "ptx92 differs from the src build in c.y's rounding (SURVEY.md 8c)")}
+
+
 def run_reference(args, wl, rank, world, local):
-    """The reference's own kernels (oracle/_ref/<fractal>.<kind>.cubin) on the GPU with the Java host's frame sequence."""
+    """The reference arm: the reference's own kernels on the GPU, launched like the Java host launches them (the reference has
+    no CPU implementation of the path).  Rank 0 alone; this backend's library is never loaded here."""
     if rank != 0:
         return None
     import oracle
-    cu = importlib.import_module("chaos-ultra_b200")
-    W, H = wl["W"], wl["H"]
-    model = make_model(cu, wl)
+    constants = load_constants()
+    base = {"metric": "pixel-iterations/s", "unit": "pixel-iterations/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if wl["double"] else "f32",
+            "data": "synthetic", "impl": "reference", "config": workload_config(args.workload, wl)}
     try:
         import torch
         have_gpu = torch.cuda.is_available()
     except Exception:
         have_gpu = False
-    base = {"metric": "pixel-iterations/s", "unit": "pixel-iterations/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if wl["double"] else "f32",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H, "max_iterations": wl["maxIter"],
-                       "max_super_sampling": wl["maxSS"], "adaptive_ss": bool(wl["flags"] & A)}}
-    ref_ok = have_gpu and oracle.REFRUN_LIB.exists() and (oracle.REF_DIR / ("%s.%s.cubin" % (wl["fractal"], args.ref_kind))).exists()
-    if ref_ok:
-        # work count of this workload: exact integer from this backend's device counter (bit-exact with the reference
-        # by the parity tests); taken once, outside the timed region.  The timed path below is reference code only.
-        prov = cu.CudaFractalRendererProvider(device=0)
-        r = prov.getRenderer(wl["fractal"], False)
-        if wl["fractal"] == "julia":
-            r.setFractalCustomParams("%r;%r" % tuple(wl["julia_c"]))
-        r.initializeRendering(W, H, None, cu.OUTPUT_DEVICE)
-        r.renderQuality(model)
-        iters_per_step = r.stats().pixel_iterations
-        r.close(); prov.close()
+    if have_gpu and oracle.REFRUN_LIB.exists() and (oracle.REF_DIR / ("%s.%s.cubin" % (wl["fractal"], args.ref_kind))).exists():
         sampler = ClockSampler(0)
-        with oracle.RefRun(wl["fractal"], args.ref_kind) as rr:
-            if wl["fractal"] == "julia":
-                import numpy as np
-                rr.write_constant("julia_c", np.array(wl["julia_c"], dtype=np.float64).tobytes())
-            sampler.start()
-            wall_ms, main_ms, comp_ms, _ = rr.frames(W, H, model.planeSegment, wl["maxIter"], wl["maxSS"], wl["flags"],
-                                                     oracle.default_palette(), wl["double"], args.warmup, args.steps, True)
-            clocks = sampler.stop()
-            wall_dev, main_dev, comp_dev, _ = rr.frames(W, H, model.planeSegment, wl["maxIter"], wl["maxSS"], wl["flags"],
-                                                        oracle.default_palette(), wl["double"], 1, args.steps, False)
-        v_e2e = iters_per_step * args.steps / (wall_ms * 1e-3)
-        v_dev = iters_per_step * args.steps / (wall_dev * 1e-3)
-        base.update({"value": v_dev, "ms_per_step": wall_dev / args.steps, "frames_per_s": args.steps / (wall_dev * 1e-3),
-                     "e2e": {"value": v_e2e, "unit": "pixel-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 4,
-                             "ms_per_step": wall_ms / args.steps},
-                     "gpu_launches": 2 * args.steps, "clocks": clocks,
-                     "device_ms_per_step": {"render_kernel": main_dev / args.steps, "compose_kernel": comp_dev / args.steps},
-                     "cpu_baseline": {"value": v_e2e, "unit": "pixel-iterations/s", "cores": 0, "kind": "reference",
+        sampler.start()
+        fig = reference_figures(args.workload, wl, args.ref_kind, args.warmup, args.steps, constants)
+        clocks = sampler.stop()
+        base.update({"value": fig["value"], "ms_per_step": fig["ms_per_step"], "frames_per_s": fig["frames_per_s"], "e2e": fig["e2e"],
+                     "gpu_launches": 2 * args.steps, "clocks": clocks, "device_ms_per_step": fig["device_ms_per_step"],
+                     "rgba_crc32": fig["rgba_crc32"], "same_frame_as_this_backend": fig["same_frame_as_this_backend"],
+                     "cpu_baseline": {"value": fig["e2e"]["value"], "unit": "pixel-iterations/s", "cores": 0, "kind": "reference",
                                       "sample": "NOT a CPU run: the reference ships no CPU path; these are its own CUDA kernels "
                                                 "(oracle/_ref/%s.%s.cubin, reference sources compiled by nvcc 12.9 for sm_100a) on the same B200, "
                                                 "block 32x32 / grid ceil(W/32) x ceil(H/32) / sync after every launch as in CudaFractalRenderer.java; "
                                                 "whole frame, %d steps" % (wl["fractal"], args.ref_kind, args.steps)},
-                     "work_count_from": "device counter of this backend for the same frame (parity-verified), outside the timed region"})
+                     "work_count_from": "tests/golden/workloads.json (exact trip count of this frame, equal in both implementations by the parity tests)"})
+        other = "ptx92" if args.ref_kind == "src" else "src"
+        try:
+            base["reference_" + other] = reference_figures(args.workload, wl, other, 1, max(3, min(args.steps, 5)), constants)
+        except Exception as e:
+            base["reference_" + other] = {"error": repr(e)}
+        if args.extras and args.workload == "c2":
+            base["extra"] = {}
+            for name in ("c4", "c1", "c5"):
+                try:
+                    base["extra"][name] = reference_figures(name, WORKLOADS[name], args.ref_kind, 1, 3 if name == "c4" else 10, constants)
+                except Exception as e:
+                    base["extra"][name] = {"error": repr(e)}
         return base
-    # no GPU or no prebuilt reference modules: fall back to the oracle port on the host cores
+    # no GPU or no prebuilt reference modules: the oracle port on the host cores
     cores = os.cpu_count() or 1
+    image = seg(wl["center"][0], wl["center"][1], wl["zoom"], wl["W"], wl["H"])
     tot_it, tot_s = 0, 0.0
     for _ in range(args.warmup + args.steps):
-        it_c, _, sec = oracle.render_main_rows_threaded(wl["fractal"], W, H, model.planeSegment, wl["maxIter"], wl["maxSS"], wl["flags"],
+        it_c, _, sec = oracle.render_main_rows_threaded(wl["fractal"], wl["W"], wl["H"], image, wl["maxIter"], wl["maxSS"], wl["flags"],
                                                         wl["double"], row_stride=args.cpu_row_stride * 4, threads=cores,
                                                         julia_c=wl.get("julia_c", (0.0, 0.0)))
         tot_it, tot_s = tot_it + it_c, tot_s + sec
@@ -566,103 +640,102 @@ def zoom_model(cu, wl, segment):
     return m
 
 
-def run_zoom_ours(args, wl, rank, world, local):
-    """every rank renders the whole sequence (the reuse pass needs the previous frame around every pixel; the
-    sequence is not partitioned in this round): N > 1 = independent replicas, scaling weak"""
-    import torch
-    cu = importlib.import_module("chaos-ultra_b200")
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def zoom_loop(job, wl, to_host, steps, warmup, sampler=None):
+    """frame 0 quality, W untimed + K timed fast frames (the sequence restarts at frame 0 for every loop); one GPU"""
+    cu = job.cu
     W, H = wl["W"], wl["H"]
-    prov = cu.CudaFractalRendererProvider(device=local)
-    r = prov.getRenderer(wl["fractal"], False)
-    segs = zoom_segments(cu, wl, 1 + args.warmup + args.steps)
-
-    def loop(mode, sampler=None):
-        if r.getState() == cu.STATE_READY_TO_RENDER:
-            r.freeRenderingResources()
-        r.initializeRendering(W, H, None, mode)
-        m = zoom_model(cu, wl, segs[0])
-        m.maxSuperSampling = max(1.0, wl["maxSS"])
-        r.renderQuality(m)                                  # frame 0
-        acc = dict(iters=0, launches=0, render_ms=0.0, compose_ms=0.0, reuse_ms=0.0, frame_ms=0.0, precisions=set())
-        for f in range(1, 1 + args.warmup + args.steps):
-            if f == 1 + args.warmup:
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                if sampler is not None:
-                    sampler.start()
-                t0 = time.perf_counter()
-                acc = dict(iters=0, launches=0, render_ms=0.0, compose_ms=0.0, reuse_ms=0.0, frame_ms=0.0, precisions=set())
-            m = zoom_model(cu, wl, segs[f])
-            r.renderFast(m)
+    r = job.renderer(wl)
+    if r.getState() == cu.STATE_READY_TO_RENDER:
+        r.freeRenderingResources()
+    r.initializeRendering(W, H, None, cu.OUTPUT_HOST if to_host else cu.OUTPUT_DEVICE)
+    segs = zoom_segments(cu, wl, 1 + warmup + steps)
+    m = zoom_model(cu, wl, segs[0])
+    m.maxSuperSampling = max(1.0, wl["maxSS"])
+    r.renderQuality(m)
+    acc = dict(iters=0, launches=0, render_ms=0.0, compose_ms=0.0, reuse_ms=0.0, frame_ms=0.0, precisions=set())
+    t0 = 0.0
+    for f in range(1, 1 + warmup + steps):
+        if f == 1 + warmup:
+            job.barrier()
+            if sampler is not None:
+                sampler.start()
+            t0 = time.perf_counter()
+        m = zoom_model(cu, wl, segs[f])
+        r.renderFast(m)
+        if f >= 1 + warmup:
             st = r.stats()
-            acc["iters"] += st.pixel_iterations
-            acc["launches"] += st.kernel_launches
-            acc["render_ms"] += st.render_ms
-            acc["compose_ms"] += st.compose_ms
-            acc["reuse_ms"] += st.reuse_ms
-            acc["frame_ms"] += st.frame_ms
+            acc["iters"] += st.pixel_iterations; acc["launches"] += st.kernel_launches
+            acc["render_ms"] += st.render_ms; acc["compose_ms"] += st.compose_ms; acc["reuse_ms"] += st.reuse_ms; acc["frame_ms"] += st.frame_ms
             acc["precisions"].add(m.floatingPointPrecision)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        acc["seconds"] = time.perf_counter() - t0
-        acc["clocks"] = sampler.stop() if sampler is not None else None
-        if world > 1:
-            t = torch.tensor([acc["seconds"], acc["frame_ms"]], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            acc["seconds"], acc["frame_ms"] = t.tolist()
-        acc["device_seconds"] = acc["frame_ms"] * 1e-3
-        return acc
+    job.barrier()
+    acc["seconds"] = time.perf_counter() - t0
+    acc["clocks"] = sampler.stop() if sampler is not None else None
+    acc["frame"] = r.outputRGBA().copy()
+    acc["last_frame_index"] = warmup + steps
+    acc["device_seconds"] = acc["frame_ms"] * 1e-3
+    r.freeRenderingResources()
+    return acc
 
-    dev = loop(cu.OUTPUT_DEVICE, ClockSampler(local) if rank == 0 else None)
-    e2e = loop(cu.OUTPUT_HOST)
-    out = None
-    if rank == 0:
-        px = W * H
-        peak, peak_src = hbm_peak_gbs()
-        mem_s = (dev["reuse_ms"] + dev["compose_ms"]) * 1e-3 / args.steps   # the two memory passes; the sampling pass is compute
-        # With CHAOS_FUSE_FAST=2 the reuse pass colours the pixels it finishes itself also when the frame stays in device
-        # memory (by default it does so only for host output): those records are not read back, so the bytes the build
-        # MOVES are 16 R + 16 W + 4 W = 36 per pixel, not the reference's 52 -- counted as such.
-        fused = os.environ.get("CHAOS_FUSE_FAST") == "2"
-        bytes_px = 36 if fused else HBM_BYTES_PER_PIXEL_FAST_FRAME
-        achieved = bytes_px * px / mem_s / 1e9
-        out = {
-            "metric": "4K frames/s (zoom sequence, fast frames)", "value": world * args.steps / dev["device_seconds"], "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev["device_seconds"] * 1e3 / args.steps,
-            "wall_ms_per_step": dev["seconds"] * 1e3 / args.steps,
-            "timing": "ms_per_step = CUDA events on the stream the kernels are launched on (reuse pass start .. compose end), summed over "
-                      "the K frames, MAX over ranks; wall_ms_per_step = host clock between the two synchronize brackets",
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if dev["precisions"] == {0} else ("f64" if 0 not in dev["precisions"] else "f32+f64"), "data": "synthetic",
-            "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H, "max_iterations": wl["maxIter"],
-                       "max_super_sampling": wl["maxSS"], "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world,
-                       "pixel_iterations_per_step": dev["iters"] // args.steps,
-                       "l2": "each frame reads the previous frame's 133 MB record buffer and writes another 133 MB one (> 126 MB L2)"},
-            "e2e": {"value": world * args.steps / e2e["seconds"], "unit": "frames/s", "h2d_bytes_per_step": 512,
-                    "d2h_bytes_per_step": px * 4 + 32, "ms_per_step": e2e["seconds"] * 1e3 / args.steps,
-                    "note": "chaos_render_fast through the C ABI, composed RGBA8 frame written to pinned host memory every frame"},
-            "gpu_launches": dev["launches"], "clocks": dev["clocks"],
-            "device_ms_per_step": {"reuse_pass": dev["reuse_ms"] / args.steps, "sample_pass": (dev["render_ms"] - dev["reuse_ms"]) / args.steps,
-                                   "compose_kernel": dev["compose_ms"] / args.steps},
+
+def zoom_block(job, name, wl, steps, warmup, constants, sampler=None):
+    dev = zoom_loop(job, wl, False, steps, warmup, sampler)
+    e2e = zoom_loop(job, wl, True, steps, warmup)
+    px = wl["W"] * wl["H"]
+    peak, peak_src = hbm_peak_gbs()
+    mem_s = (dev["reuse_ms"] + dev["compose_ms"]) * 1e-3 / steps   # the two memory passes; the sampling pass is compute
+    # With CHAOS_FUSE_FAST=2 the reuse pass colours the pixels it finishes itself also when the frame stays in device memory (by
+    # default only for host output): those records are not read back, so the bytes the build MOVES are 16 R + 16 W + 4 W = 36 per
+    # pixel, not the reference's 52 -- counted as such.
+    fused = os.environ.get("CHAOS_FUSE_FAST") == "2"
+    bytes_px = 36 if fused else HBM_BYTES_PER_PIXEL_FAST_FRAME
+    achieved = bytes_px * px / mem_s / 1e9
+    crcs = constants.get(name, {}).get("frame_crc32") or []
+
+    def check(acc, what):
+        crc, idx = frame_crc(acc["frame"]), acc["last_frame_index"]
+        want = crcs[idx] if idx < len(crcs) else None
+        if want is not None and crc != want:
+            raise SystemExit("bench: %s frame %d of %s has crc32 %08x, expected %08x -- the timed sequence is wrong" % (what, idx, name, crc, want))
+        return {"frame": idx, "rgba_crc32": crc, "rgba_crc32_expected": want, "rgba_crc32_ok": None if want is None else crc == want}
+
+    return {"workload": name + ": " + wl["desc"], "metric": "4K frames/s (zoom sequence, fast frames)", "value": steps / dev["device_seconds"], "unit": "frames/s",
+            "ms_per_step": dev["device_seconds"] * 1e3 / steps, "wall_ms_per_step": dev["seconds"] * 1e3 / steps, "steps": steps, "warmup": warmup,
+            "dtype": "f32" if dev["precisions"] == {0} else ("f64" if 0 not in dev["precisions"] else "f32+f64"),
+            "pixel_iterations_per_step": dev["iters"] // steps, "gpu_launches": dev["launches"], "clocks": dev["clocks"],
+            "frame_check": check(dev, "device"),
+            "e2e": dict({"value": steps / e2e["seconds"], "unit": "frames/s", "ms_per_step": e2e["seconds"] * 1e3 / steps, "h2d_bytes_per_step": 512,
+                         "d2h_bytes_per_step": px * 4 + 32,
+                         "note": "chaos_render_fast through the C ABI, composed RGBA8 frame written to pinned host memory every frame"}, **check(e2e, "end-to-end")),
+            "device_ms_per_step": {"reuse_pass": dev["reuse_ms"] / steps, "sample_pass": (dev["render_ms"] - dev["reuse_ms"]) / steps,
+                                   "compose_kernel": dev["compose_ms"] / steps},
+            "l2": "each frame reads the previous frame's 133 MB record buffer and writes another 133 MB one (> 126 MB L2)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
+                         "traffic": NCU_TRAFFIC.get(name, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(name, (None, None))[1],
                          "kernel": "chaosReusePass* + compose (the two memory passes of a fast frame)", "peak_source": peak_src,
                          "algorithmic_bytes": ("%d B/pixel x %d pixels per frame (" % (bytes_px, px)) +
                                               ("reuse pass 16 R + 16 W + 4 W: it colours its own pixels; the reference's two passes move 52)" if fused
                                                else "reuse 16 R + 16 W, compose 16 R + 4 W)"),
-                         "note": "the foveal disc and the pixels without history are resampled by a separate compute-bound launch (sample_pass), not part of this figure"},
-        }
-    r.close()
-    prov.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+                         "note": "the foveal disc and the pixels without history are resampled by a separate compute-bound launch (sample_pass), not part of this figure"}}
+
+
+def run_zoom_ours(args, wl, rank, world, local):
+    """headline = the zoom sequence (--workload c3).  Several GPUs: every rank renders the whole sequence (independent replicas)."""
+    job = Job(rank, world, local)
+    constants = load_constants()
+    blk = zoom_block(job, args.workload, wl, args.steps, args.warmup, constants, ClockSampler(local) if rank == 0 else None)
+    sec = job.reduce([blk["ms_per_step"], blk["e2e"]["ms_per_step"]], "max")
+    out = None
+    if rank == 0:
+        out = {"metric": blk["metric"], "value": world * 1e3 / sec[0], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": sec[0], "wall_ms_per_step": blk["wall_ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": blk["dtype"], "data": "synthetic",
+               "timing": "ms_per_step = CUDA events on the stream the kernels are launched on (reuse pass start .. compose end), summed over the K frames, MAX over ranks",
+               "config": dict(workload_config(args.workload, wl), l2=blk["l2"]),
+               "details": {"parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world, "pixel_iterations_per_step": blk["pixel_iterations_per_step"],
+                           "frame_check": blk["frame_check"]},
+               "e2e": dict(blk["e2e"], value=world * 1e3 / sec[1], ms_per_step=sec[1]),
+               "gpu_launches": blk["gpu_launches"], "clocks": blk["clocks"], "device_ms_per_step": blk["device_ms_per_step"], "roofline": blk["roofline"]}
+    job.close()
     return out
 
 
@@ -670,10 +743,11 @@ def run_zoom_reference(args, wl, rank, world, local):
     if rank != 0:
         return None
     import oracle
-    cu = importlib.import_module("chaos-ultra_b200")
     W, H = wl["W"], wl["H"]
     n = 1 + args.warmup + args.steps
-    segs = zoom_segments(cu, wl, n)
+    segs = [seg(wl["center"][0], wl["center"][1], wl["zoom"], W, H)]
+    for _ in range(n - 1):
+        segs.append(oracle.zoom_at(segs[-1], W, H, wl["focus"], True))
     doubles = [oracle.choose_precision(sg, W, H) != 0 for sg in segs]
     pal = oracle.default_palette()
     with oracle.RefRun(wl["fractal"], args.ref_kind) as rr:
@@ -687,7 +761,7 @@ def run_zoom_reference(args, wl, rank, world, local):
     return {"metric": "4K frames/s (zoom sequence, fast frames)", "value": args.steps / (wall_d * 1e-3), "unit": "frames/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_d / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if all(doubles) else ("f32" if not any(doubles) else "f32+f64"), "data": "synthetic",
-            "impl": "reference", "config": {"workload": args.workload + ": " + wl["desc"], "width": W, "height": H},
+            "impl": "reference", "config": dict(workload_config(args.workload, wl), l2="each frame reads the previous frame's 133 MB record buffer and writes another 133 MB one (> 126 MB L2)"),
             "e2e": {"value": args.steps / (wall * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 4,
                     "ms_per_step": wall / args.steps},
             "gpu_launches": 2 * args.steps, "clocks": clocks,
@@ -710,11 +784,10 @@ def main():
     ap.add_argument("--engine", type=int, default=None)
     ap.add_argument("--ref-kind", default="src", choices=["src", "ptx92"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--nccl-gather", action="store_true", help="multi-GPU: gather the bands with NCCL send/recv instead of composing into rank 0's frame")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="only the headline workload (default: c4 at every N; c1, c5, c3 at N = 1 as well)")
     ap.add_argument("--no-full-trips", action="store_true", help="skip the CHAOS_SHORTCUTS=0 comparison run")
     ap.add_argument("--cpu-row-stride", type=int, default=2, help="host baseline: every n-th vote-tile row of the frame (bounds the CPU time)")
     args = ap.parse_args()
-    args.e2e_host_copy = False
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     quiet_nccl()
     rank, world, local = dist_env()

@@ -157,6 +157,10 @@ _API = {
     "chaos_debug_peek_counters": (C.c_int, [_VP, _VP, C.c_size_t]),
     "chaos_set_partition": (C.c_int, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "chaos_set_output_target": (C.c_int, [_VP, C.c_uint64]),
+    "chaos_ipc_export_frame": (C.c_int, [_VP, _VP]),
+    "chaos_ipc_open_frame": (C.c_int, [_VP, _VP]),
+    "chaos_set_host_target": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "chaos_set_frame_barrier": (C.c_int, [_VP, _VP, C.c_uint32]),
     "chaos_last_error": (C.c_char_p, []),
     "chaos_abi_version": (C.c_uint32, []),
 }
@@ -437,6 +441,25 @@ class CudaFractalRenderer:
     def setOutputTarget(self, device_ptr: int) -> None:
         """DEVICE mode: compose writes into ``device_ptr`` (e.g. rank 0's frame mapped with CUDA IPC) instead of the own frame; 0 resets."""
         _check(self._lib, self._lib.chaos_set_output_target(self._h, int(device_ptr)))
+
+    def exportFrameHandle(self) -> bytes:
+        """DEVICE mode: a 64-byte handle of this renderer's device frame that another process can open."""
+        buf = C.create_string_buffer(64)
+        _check(self._lib, self._lib.chaos_ipc_export_frame(self._h, C.cast(buf, _VP)))
+        return buf.raw
+
+    def openFrameHandle(self, handle: bytes) -> None:
+        """DEVICE mode: compose into the frame another process exported (its bands cross NVLink as compose's stores)."""
+        buf = C.create_string_buffer(bytes(handle), 64)
+        _check(self._lib, self._lib.chaos_ipc_open_frame(self._h, C.cast(buf, _VP)))
+
+    def setHostTarget(self, address: int, nbytes: int) -> None:
+        """DEVICE mode: compose into caller-owned, page-aligned host memory (e.g. shared memory all ranks mapped); 0 releases it."""
+        _check(self._lib, self._lib.chaos_set_host_target(self._h, int(address) or None, int(nbytes)))
+
+    def setFrameBarrier(self, address: int, world: int) -> None:
+        """64 zeroed bytes of host memory shared by all ranks: every render call returns when all ranks' frames are done."""
+        _check(self._lib, self._lib.chaos_set_frame_barrier(self._h, int(address) or None, int(world)))
 
     def downloadRecords(self) -> np.ndarray:
         """The primary pixel_info_t buffer as an (H, W) structured array."""

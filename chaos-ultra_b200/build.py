@@ -106,7 +106,7 @@ def build_compat_reference(force: bool = False):
 
 def build_library(force: bool = False) -> Path:
     LIB_DIR.mkdir(exist_ok=True)
-    srcs = [CSRC / "chaos_abi.cpp"]
+    srcs = [CSRC / "chaos_abi.cpp", CSRC / "chaos_driver.cpp"]
     deps = srcs + sorted(CSRC.glob("*.h")) + [PKG_DIR.parent / "include" / "chaos_ultra.h", Path(__file__)]
     if not force and _newer(LIB_PATH, deps):
         return LIB_PATH

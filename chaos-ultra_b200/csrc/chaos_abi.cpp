@@ -19,6 +19,8 @@
  * entry point fails with a message.
  */
 #include <dlfcn.h>
+#include <sched.h>
+#include <time.h>
 #include <errno.h>
 #include <limits.h>
 #include <math.h>
@@ -326,6 +328,7 @@ struct chaos_renderer {
     CUdeviceptr long_list = 0, finish_list = 0;    /* allocated by the first engine-2 frame of a frame size */
     size_t list_capacity = 0;                      /* entries */
     uint32_t probe_trips = 64;
+    uint32_t hot_first = 1;                        /* pass C: orbits expected to be long are started first (CHAOS_HOT_FIRST=0: list order) */
     CUfunction k_classify = nullptr, k_order = nullptr;            /* between the two passes of engine 1 */
     CUfunction k_replay = nullptr;                                 /* pass D */
     chaos_export exp_buf = {0, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -355,6 +358,12 @@ struct chaos_renderer {
     CUdeviceptr rgba_dev = 0;      /* DEVICE mode frame, or device alias of rgba_host */
     CUdeviceptr rgba_target = 0;   /* chaos_set_output_target: where compose writes instead (0 = rgba_dev) */
     uint32_t *rgba_host = nullptr; /* HOST mode: pinned + mapped */
+    /* multi-GPU: where the target came from (so that it can be given back), and the frame barrier in host shared memory */
+    CUdeviceptr ipc_frame = 0;     /* chaos_ipc_open_frame: a peer's device frame mapped into this process */
+    void *host_target = nullptr;   /* chaos_set_host_target: caller's host memory, registered by us */
+    volatile unsigned long long *barrier = nullptr;
+    uint32_t barrier_world = 0;
+    unsigned long long barrier_seq = 0;
     CUdeviceptr counters = 0;
     chaos_counters *counters_host = nullptr; /* pinned staging for the read-back */
     CUstream stream = nullptr;
@@ -587,6 +596,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     /* debugging knobs (not part of the reference's interface): engine 0 is the differential check of engine 1 */
     const char *eng = getenv("CHAOS_ENGINE");
     if (eng) r->engine = (uint32_t)std::min(std::max(atoi(eng), 0), 2);
+    const char *hf = getenv("CHAOS_HOT_FIRST");
+    if (hf) r->hot_first = (uint32_t)atoi(hf) ? 1u : 0u;
     const char *prb = getenv("CHAOS_PROBE_TRIPS");
     if (prb) r->probe_trips = (uint32_t)std::max(atoi(prb), 8);
     const char *sb = getenv("CHAOS_SYNC_BELOW");
@@ -721,6 +732,13 @@ static chaos_status launch_stream_chain(chaos_renderer *r, chaos_render_args &b,
     return st;
 }
 
+static void release_targets(chaos_renderer *r)
+{
+    if (r->ipc_frame) { D->p_cuIpcCloseMemHandle(r->ipc_frame); r->ipc_frame = 0; }
+    if (r->host_target) { D->p_cuMemHostUnregister(r->host_target); r->host_target = nullptr; }
+    r->rgba_target = 0;
+}
+
 static void free_frame_memory(chaos_renderer *r)
 {
     for (int i = 0; i < 2; ++i) if (r->buf[i].ptr) { D->p_cuMemFree(r->buf[i].ptr); r->buf[i].ptr = 0; r->buf[i].pitch = 0; }
@@ -733,7 +751,7 @@ static void free_frame_memory(chaos_renderer *r)
     r->list_capacity = 0;
     if (r->late_tiles) { D->p_cuMemFree(r->late_tiles); r->late_tiles = 0; }
     if (r->warp_trace) { D->p_cuMemFree(r->warp_trace); r->warp_trace = 0; }
-    r->rgba_target = 0;
+    release_targets(r);
     if (r->rgba_host) { D->p_cuMemFreeHost(r->rgba_host); r->rgba_host = nullptr; r->rgba_dev = 0; }
     if (r->rgba_dev) { D->p_cuMemFree(r->rgba_dev); r->rgba_dev = 0; }
 }
@@ -831,7 +849,101 @@ extern "C" chaos_status chaos_set_output_target(chaos_renderer *r, uint64_t devi
     if (r->state != CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Renderer has to be initialized first");
     if (r->mode != CHAOS_OUTPUT_DEVICE) return fail(CHAOS_ERR_ILLEGAL_STATE, "an output target needs CHAOS_OUTPUT_DEVICE mode");
     if (device_ptr & 15u) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "the output target must be 16-byte aligned");
+    ctx_guard g(r->provider);
+    D->p_cuStreamSynchronize(r->stream);
+    release_targets(r);
     r->rgba_target = (CUdeviceptr)device_ptr;
+    return CHAOS_OK;
+}
+
+static chaos_status check_device_target(chaos_renderer *r)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (r->state != CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Renderer has to be initialized first");
+    if (r->mode != CHAOS_OUTPUT_DEVICE) return fail(CHAOS_ERR_ILLEGAL_STATE, "an output target needs CHAOS_OUTPUT_DEVICE mode");
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_ipc_export_frame(chaos_renderer *r, chaos_ipc_handle *out)
+{
+    chaos_status st = check_device_target(r);
+    if (st != CHAOS_OK) return st;
+    if (!out) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "out is NULL");
+    static_assert(sizeof(CUipcMemHandle) == sizeof(chaos_ipc_handle), "IPC handle size");
+    ctx_guard g(r->provider);
+    CUresult e = D->p_cuIpcGetMemHandle((CUipcMemHandle *)out, r->rgba_dev);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuIpcGetMemHandle failed: %s", cu_err_name(e));
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_ipc_open_frame(chaos_renderer *r, const chaos_ipc_handle *frame)
+{
+    chaos_status st = check_device_target(r);
+    if (st != CHAOS_OK) return st;
+    if (!frame) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "frame handle is NULL");
+    ctx_guard g(r->provider);
+    D->p_cuStreamSynchronize(r->stream);
+    release_targets(r);
+    CUipcMemHandle h;
+    memcpy(&h, frame, sizeof h);
+    CUresult e = D->p_cuIpcOpenMemHandle(&r->ipc_frame, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
+    if (e != CUDA_SUCCESS) { r->ipc_frame = 0; return fail(CHAOS_ERR_CUDA, "cuIpcOpenMemHandle failed: %s", cu_err_name(e)); }
+    r->rgba_target = r->ipc_frame;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_set_host_target(chaos_renderer *r, void *host_frame, size_t bytes)
+{
+    chaos_status st = check_device_target(r);
+    if (st != CHAOS_OK) return st;
+    ctx_guard g(r->provider);
+    D->p_cuStreamSynchronize(r->stream);
+    release_targets(r);
+    if (!host_frame) return CHAOS_OK;
+    if (bytes < (size_t)r->width * r->height * 4u) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "the host target must hold width * height * 4 bytes but holds %zu", bytes);
+    if ((uintptr_t)host_frame & 4095u) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "the host target must be page-aligned");
+    CUresult e = D->p_cuMemHostRegister(host_frame, bytes, CU_MEMHOSTREGISTER_DEVICEMAP | CU_MEMHOSTREGISTER_PORTABLE);
+    if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemHostRegister(%zu bytes) failed: %s", bytes, cu_err_name(e));
+    CUdeviceptr dp = 0;
+    e = D->p_cuMemHostGetDevicePointer(&dp, host_frame, 0);
+    if (e != CUDA_SUCCESS) { D->p_cuMemHostUnregister(host_frame); return fail(CHAOS_ERR_CUDA, "cuMemHostGetDevicePointer failed: %s", cu_err_name(e)); }
+    r->host_target = host_frame;
+    r->rgba_target = dp;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_set_frame_barrier(chaos_renderer *r, void *shm_block, uint32_t world)
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (shm_block && world == 0) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "a frame barrier needs world >= 1");
+    if ((uintptr_t)shm_block & 7u) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "the barrier block must be 8-byte aligned");
+    r->barrier = (volatile unsigned long long *)shm_block;
+    r->barrier_world = shm_block ? world : 0u;
+    r->barrier_seq = 0;
+    return CHAOS_OK;
+}
+
+/* end of a render call under a frame barrier: this rank's kernels are done (the stream was synchronised), so its bands
+ * are in the shared frame; announce it and wait for the others */
+static chaos_status frame_barrier(chaos_renderer *r)
+{
+    if (!r->barrier) return CHAOS_OK;
+    r->barrier_seq += 1;
+    __atomic_fetch_add((unsigned long long *)r->barrier, 1ull, __ATOMIC_SEQ_CST);
+    const unsigned long long want = r->barrier_seq * r->barrier_world;
+    struct timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (unsigned spins = 0; __atomic_load_n((unsigned long long *)r->barrier, __ATOMIC_SEQ_CST) < want; ++spins) {
+        if ((spins & 255u) == 255u) {
+            struct timespec t;
+            clock_gettime(CLOCK_MONOTONIC, &t);
+            if ((t.tv_sec - t0.tv_sec) > 10) return fail(CHAOS_ERR_CUDA, "frame barrier: %llu of %llu announcements after 10 s (a rank died or renders a different number of frames)",
+                                                        __atomic_load_n((unsigned long long *)r->barrier, __ATOMIC_SEQ_CST), want);
+            sched_yield();
+        }
+    }
     return CHAOS_OK;
 }
 
@@ -1007,7 +1119,7 @@ static chaos_status launch_compose(chaos_renderer *r, const chaos_params *m, CUs
     /* The frame-wide compose that runs next to passes C and D into pinned host memory moves at PCIe speed (33 MB: 0.6 ms)
      * whatever its grid; a small grid leaves the SMs (and their register files: a pass C CTA needs a quarter of one) to
      * the passes it runs next to. */
-    if (stream == r->stream2 && stream && r->mode == CHAOS_OUTPUT_HOST && !r->rgba_target && r->host_compose_blocks >= 0)
+    if (stream == r->stream2 && stream && ((r->mode == CHAOS_OUTPUT_HOST && !r->rgba_target) || r->host_target) && r->host_compose_blocks >= 0)
         max_blocks = r->host_compose_blocks ? r->host_compose_blocks : r->provider->sm_count;   /* measured: 16 / 37 / 148 / 1184 CTAs -> c2 4.13 / 3.99 / 3.91 / 3.93 ms, c2ex2 7.63 / 7.61 / 7.70 / 7.91 ms end to end */
     int blocks = (int)std::min<uint64_t>((quads + 255u) / 256u, (uint64_t)max_blocks);
     if (blocks < 1) blocks = 1;
@@ -1065,7 +1177,7 @@ static chaos_status finish_frame(chaos_renderer *r)
                     v[CHAOS_LS_BLOCKS], v[CHAOS_LS_PASSES]);
         }
     }
-    return CHAOS_OK;
+    return frame_barrier(r);
 }
 
 static chaos_status set_module_constants(chaos_renderer *r, const chaos_params *m)
@@ -1207,6 +1319,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                 D->p_cuEventRecord(r->strand_ev_b[s], q);
                 if (exporting && b.n_tiles && st == CHAOS_OK) {
                     b.phase = 3u;
+                    if (streams && r->hot_first) { b.hot_capacity = b.list_capacity / 4u; b.hot_trips = std::max(b.max_iter / 4u, 64u); }
                     st = streams ? launch_stream_chain(r, b, p, q) : launch(r, r->k_pass_c[p], r->blocks_pass_c[p], (int)r->pass_threads, 0, &b, q);
                     const int replay_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);
                     if (st == CHAOS_OK) st = launch(r, r->k_replay, replay_grid, 256, 0, &b, q);
@@ -1292,7 +1405,7 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
         CUfunction k_reuse = dbl ? r->k_reuse_d : r->k_reuse_f;
         int blocks_reuse = dbl ? r->blocks_reuse_d : r->blocks_reuse_f;
         unsigned smem_reuse = 0;
-        if (r->fuse_fast == 2u || (r->fuse_fast == 1u && r->mode == CHAOS_OUTPUT_HOST && !r->rgba_target)) {
+        if (r->fuse_fast == 2u || (r->fuse_fast == 1u && ((r->mode == CHAOS_OUTPUT_HOST && !r->rgba_target) || r->host_target))) {
             const size_t frame_tiles = (size_t)a.tiles_x * a.tile_rows;
             if (D->p_cuMemsetD32Async(r->late_tiles, 0u, (frame_tiles + 31u) / 32u, r->stream) != CUDA_SUCCESS)
                 return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed");

@@ -15,7 +15,7 @@
 struct uint2 { unsigned int x, y; };   /* host side of the launch contract (vector_types.h is CUDA-only) */
 #endif
 
-#define CHAOS_MODULE_ABI 26u
+#define CHAOS_MODULE_ABI 27u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -44,7 +44,7 @@ struct chaos_stream_ctl {
     unsigned int n_long;          /* orbits the probe appended to the long list (may exceed the capacity: clamp) */
     unsigned int long_cursor;     /* entries the long kernel has claimed */
     unsigned int n_finish;        /* orbits the long kernel appended to the finish list */
-    unsigned int pad;
+    unsigned int n_hot;           /* orbits the probe put into the list's hot region (expected to be long: the long kernel starts them first) */
 };
 struct chaos_counters {
     unsigned int next_tile;             /* work-stealing cursor over vote tiles */
@@ -144,6 +144,8 @@ struct chaos_render_args {
     void *finish_list;                 /* [list_capacity] finish_item<Real>: orbits that need a last group of tested trips */
     uint32_t list_capacity;
     uint32_t probe_trips;              /* tested trips an orbit gets in the probe kernel before it goes to the long list */
+    uint32_t hot_capacity;             /* the first hot_capacity entries of long_list are the hot region (0 = none) */
+    uint32_t hot_trips;                /* pass C: a pixel whose sample 0 executed at least this many trips is expected to be long */
 };
 #define CHAOS_POOL_STRIDE 128u
 

@@ -34,6 +34,11 @@
     X(cuMemHostAlloc)                           \
     X(cuMemFreeHost)                            \
     X(cuMemHostGetDevicePointer)                \
+    X(cuMemHostRegister)                        \
+    X(cuMemHostUnregister)                      \
+    X(cuIpcGetMemHandle)                        \
+    X(cuIpcOpenMemHandle)                       \
+    X(cuIpcCloseMemHandle)                      \
     X(cuMemcpyHtoD)                             \
     X(cuMemcpyDtoH)                             \
     X(cuMemcpyHtoDAsync)                        \

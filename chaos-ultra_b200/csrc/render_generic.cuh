@@ -644,9 +644,12 @@ extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
 chaosProbeFloat(const __grid_constant__ chaos_render_args a) { stream_probe<float, Fractal>(a); }
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
 chaosProbeDouble(const __grid_constant__ chaos_render_args a) { stream_probe<double, Fractal>(a); }
-extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+#ifndef CHAOS_LONG_MIN_BLOCKS
+#define CHAOS_LONG_MIN_BLOCKS 4
+#endif
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, CHAOS_LONG_MIN_BLOCKS)
 chaosLongFloat(const __grid_constant__ chaos_render_args a) { stream_long<float, Fractal>(a); }
-extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, 4)
+extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS, CHAOS_LONG_MIN_BLOCKS)
 chaosLongDouble(const __grid_constant__ chaos_render_args a) { stream_long<double, Fractal>(a); }
 extern "C" __global__ void __launch_bounds__(CHAOS_RENDER_THREADS)
 chaosFinishFloat(const __grid_constant__ chaos_render_args a) { stream_finish<float, Fractal>(a); }

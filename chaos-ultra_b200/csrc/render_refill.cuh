@@ -109,7 +109,10 @@ static __device__ __forceinline__ void shared_add64(unsigned long long *p, uint3
  *   - otherwise it is untested.
  * (Two orbits per lane with interleaved chains was measured in round 1 and removed: no gain once the loop is
  * pipe-bound, a loss with sample rounds.) */
-#define CHAOS_TESTED_BLOCK 40u   /* >= quadratic_orbit::kGroup + 1: the replay of a failed group ends inside one tested block */
+#ifndef CHAOS_GROUP
+#define CHAOS_GROUP 32u          /* (quadratic.cuh; modules without that loop still need the block length) */
+#endif
+#define CHAOS_TESTED_BLOCK (CHAOS_GROUP + 8u)   /* >= quadratic_orbit::kGroup + 1: the replay of a failed group ends inside one tested block */
 
 /* A scheduling pass costs the warp some hundred instructions, a lane that waits for one costs nothing but its share
  * of the next blocks.  So a pass is not taken for every finished orbit: finished lanes wait until `idle_lanes` lanes

@@ -137,16 +137,14 @@ static __device__ void stream_probe(const chaos_render_args &a)
     const uint32_t S0 = min(64u, __float2uint_rz(roundf(a.max_ss)));
     const uint32_t rounds_per_tile = pass_c ? S0 - 2u : pass_a ? 2u : 1u;
     const uint32_t n_items = pass_c ? min(a.counters->n_exported, a.exp.capacity) * rounds_per_tile : a.n_tiles * rounds_per_tile;
-    unsigned int *cursor = pass_c ? &a.counters->next_export_item : &a.counters->next_tile;
     chaos_stream_ctl *ctl = &a.counters->stream[pass_c ? 1 : 0];
     const uint32_t T0 = min(max_iter, a.probe_trips);
     stream_totals tot = {0ull, 0ull, 0ull};
-
-    for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(cursor, 1u);
-        t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
-        if (t >= n_items) break;
+    /* Items are dealt statically, warp w takes items w, w + warps, ...: an item's work is bounded (T0 trips), neighbouring
+     * items go to neighbouring warps, and a common cursor would be the bottleneck -- half a million atomics on one
+     * address take longer than the arithmetic of this kernel. */
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_items; t += warps) {
         uint32_t x0, y0, rnd = 0u, e = 0u;
         if (pass_c) {
             e = t / rounds_per_tile;
@@ -184,13 +182,31 @@ static __device__ void stream_probe(const chaos_render_args &a)
             sf.deliver(a, d, o.finish(it, max_iter), it, o.skipped());
             tot.add(it, o.skipped());
         }
-        const uint32_t surv = __ballot_sync(CHAOS_FULL_MASK, inb && !ended);
+        /* survivors go to the long list.  Longest first: the launch ends when its last orbit does, and an orbit of maxIterations
+         * trips that starts when the list runs dry IS the tail.  Pass C knows what to expect -- the executed trips of the
+         * pixel's sample 0 are still in its record -- and puts those orbits into the list's hot region, which the long
+         * kernel hands out first. */
+        bool hot = false;
+        if (pass_c && a.hot_capacity && inb && !ended)
+            hot = __float_as_uint(record_at(a.out, a.out_pitch, px, py)->weight_of_new_samples) >= a.hot_trips;
+        const uint32_t surv_hot = __ballot_sync(CHAOS_FULL_MASK, hot);
+        if (surv_hot) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->n_hot, (unsigned int)__popc(surv_hot));
+            base = __shfl_sync(CHAOS_FULL_MASK, base, 0);
+            if (hot) {
+                const uint32_t idx = base + __popc(surv_hot & lanemask_lt());
+                if (idx < a.hot_capacity) a.long_list[idx] = make_uint2(d.a, d.b);
+                else hot = false;                                   /* region full: an ordinary entry */
+            }
+        }
+        const uint32_t surv = __ballot_sync(CHAOS_FULL_MASK, inb && !ended && !hot);
         if (surv) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(&ctl->n_long, (unsigned int)__popc(surv));
             base = __shfl_sync(CHAOS_FULL_MASK, base, 0);
-            if (inb && !ended) {
-                const uint32_t idx = base + __popc(surv & lanemask_lt());
+            if (inb && !ended && !hot) {
+                const uint32_t idx = a.hot_capacity + base + __popc(surv & lanemask_lt());
                 if (idx < a.list_capacity) {
                     a.long_list[idx] = make_uint2(d.a, d.b);
                 } else {                 /* list full (never with the host's sizing for passes 0 and A): the orbit is finished here */
@@ -329,7 +345,8 @@ static __device__ void stream_long(const chaos_render_args &a)
     const orbit_ctx ctx = {a.max_iter, a.shortcuts};
     const uint32_t which = a.phase == 3u ? 1u : 0u;
     chaos_stream_ctl *ctl = &a.counters->stream[which];
-    const uint32_t n = min(ctl->n_long, a.list_capacity);
+    const uint32_t n_hot = min(ctl->n_hot, a.hot_capacity);      /* entries 0 .. n_hot-1: the hot region; then the ordinary ones */
+    const uint32_t n = n_hot + min(ctl->n_long, a.list_capacity - a.hot_capacity);
     fin_t *const finish_list = reinterpret_cast<fin_t *>(a.finish_list);
     const uint32_t max_debt = max(a.sched_idle_lanes_indep, 1u) * 64u;
     stream_totals tot = {0ull, 0ull, 0ull};
@@ -344,17 +361,28 @@ static __device__ void stream_long(const chaos_render_args &a)
     bool busy = false, fin = false, stall = false;   /* fin: over, result known; stall: needs tested trips (finish list) */
     bool dry = n == 0u, keep_all = false;
     uint32_t debt = 0, drain_wait = 0, park_cooldown = 0;
+    CHAOS_LS(lane_stats ls; ls.init();)
     for (;;) {
-        if (busy && !fin && !stall) {
+        CHAOS_LS(ls.before(busy, fin || stall, false, false, dry, it);)
+        /* one block: up to nb trips per running orbit, group by group in lock step.  Lanes that are out (empty, over,
+         * stalled) run up the warp's debt with every group; at max_debt the block ends early and the warp refills. */
+        {
             const uint32_t lim = min(it + nb, max_iter);
-            const bool e = o.run(it, lim, false);
-            fin = e || it >= max_iter;
-            stall = !fin && o.wants_tested();
+            bool f = fin;
+            o.run_voted(it, lim, busy && !stall, f, [&](bool live) {
+                const uint32_t running_now = __ballot_sync(CHAOS_FULL_MASK, live);
+                if (!running_now) return true;
+                if (dry) return false;
+                debt += (32u - (uint32_t)__popc(running_now)) * CHAOS_GROUP;
+                return debt >= max_debt;
+            });
+            fin = f;
+            stall = busy && !fin && o.wants_tested();
         }
+        CHAOS_LS(ls.after((fin ? it - o.skipped() : it) - ls.it0);)
         const uint32_t running = __ballot_sync(CHAOS_FULL_MASK, busy && !fin && !stall);
         if (running) {
             if (!dry) {
-                debt += (32u - (uint32_t)__popc(running)) * nb;
                 if (debt < max_debt) continue;
             } else {
                 /* nothing to refill from but the pool: a look every few blocks while lanes are out -- the orbits still running
@@ -363,6 +391,7 @@ static __device__ void stream_long(const chaos_render_args &a)
             }
         }
         debt = 0u; drain_wait = 0u;
+        CHAOS_LS(ls.pass();)
         /* retire */
         if (fin) {
             sf.deliver(a, d, o.finish(it, max_iter), it, o.skipped());
@@ -398,7 +427,7 @@ static __device__ void stream_long(const chaos_render_args &a)
             base = __shfl_sync(CHAOS_FULL_MASK, base, 0);
             const uint32_t idx = base + __popc(idle & lanemask_lt());
             if (!busy && idx < n) {
-                const uint2 ent = a.long_list[idx];
+                const uint2 ent = a.long_list[idx < n_hot ? idx : a.hot_capacity + (idx - n_hot)];
                 d.a = ent.x; d.b = ent.y;
                 uint32_t px, py, rnd;
                 sf.decode(a, d, px, py, rnd);
@@ -428,6 +457,7 @@ static __device__ void stream_long(const chaos_render_args &a)
         }
     }
     tot.flush(a);
+    CHAOS_LS(ls.flush(a, a.phase == 1u ? 0 : a.phase == 3u ? 2 : 3);)
 }
 
 /* ---- finish ----------------------------------------------------------------------------------------------- */

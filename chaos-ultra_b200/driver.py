@@ -1,191 +1,182 @@
-"""Frame driver: the reference's rendering-mode state machine and automatic-quality controller around a renderer.
+"""Frame driver: ctypes face of the native driver in libchaos_ultra.so (csrc/chaos_driver.cpp).
 
-SURVEY.md 8(f)2.  In the reference this logic lives in the GUI layer and is driven by AWT events and the JOGL
-animator; here it is a plain object so that a zoom session can be replayed (and benchmarked) with the reference's
-closed-loop behaviour -- maxSuperSampling retargeted every frame so that a frame takes 15 ms while zooming/moving,
-and 30, 60, ... ms while refining progressively -- instead of a fixed sample budget.
-
-Mirrors, method for method:
-  RenderingModeFSM        rendering/RenderingModeFSM.java:9-155
-  FrameDriver.display     rendering/GLRenderer.java:113-162 (display), :167-185 (cudaRender),
-                          :200-237 (determineRenderingModeQuality), :239-245 (setParamsToBeRenderedIn)
-  FrameDriver.zoom_at     rendering/RenderingController.java:130-150
-  on_rendering_done       rendering/RenderingController.java:264-269
-`renderer` is anything with renderFast(model) / renderQuality(model): a CudaFractalRenderer, or a stub in tests.
-`clock` returns milliseconds (System.currentTimeMillis in the reference).
+SURVEY.md 8(f)2.  The reference's rendering-mode state machine (rendering/RenderingModeFSM.java:9-155) and automatic
+quality controller (rendering/GLRenderer.java:113-245) live in its GUI layer; here they sit behind the C ABI
+(``chaos_driver_*`` in include/chaos_ultra.h), so the Java host, a benchmark or a test can replay a zoom session with the
+reference's closed-loop behaviour -- maxSuperSampling retargeted every frame so that a frame takes 15 ms while zooming or
+moving and 30, 60, ... ms while refining progressively.  This module only marshals: no logic of the controller is in Python.
 """
 from __future__ import annotations
 
-import time
+import ctypes as C
+import importlib
 from typing import Callable, List, Optional, Sequence
 
-MAX_SUPER_SAMPLING = 64
-WAITING, ZOOMING_AUTO, ZOOMING_ONCE, MOVING, PROGRESSIVE = "Waiting", "ZoomingAuto", "ZoomingOnce", "Moving", "ProgressiveRendering"
+_pkg = importlib.import_module(__name__.rsplit(".", 1)[0])
+_Params, _check_status = _pkg._Params, _pkg._STATUS_TO_EXC
+
+WAITING, ZOOMING_AUTO, ZOOMING_ONCE, MOVING, PROGRESSIVE = 0, 1, 2, 3, 4
+MODE_NAMES = ["Waiting", "ZoomingAuto", "ZoomingOnce", "Moving", "ProgressiveRendering"]
+CLOCK_DEVICE, CLOCK_WALL_INT = 0, 1
+MAX_PROGRESSIVE_RENDERING_LEVEL = 6
+_VP = C.c_void_p
 
 
-class RenderingModeFSM:
-    MAX_PROGRESSIVE_RENDERING_LEVEL = 6
+class _State(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mode", C.c_int), ("last_mode", C.c_int), ("progressive_rendering_level", C.c_int32),
+                ("zooming", C.c_uint8), ("moving", C.c_uint8), ("zooming_in", C.c_uint8), ("last_kind", C.c_uint8),
+                ("last_frame_render_time_ms", C.c_float), ("frames", C.c_uint64), ("model", _Params)]
 
-    def __init__(self):
-        self.current = WAITING
-        self.last = WAITING
-        self.pr_lvl = 0
-        self.zooming_and_moving = False
-        self.zooming_direction = False
 
-    def resetState(self):
-        self.last, self.current, self.zooming_and_moving = self.current, WAITING, False
+RENDER_FN = C.CFUNCTYPE(C.c_int, _VP, C.POINTER(_Params), C.POINTER(C.c_float))
+_DRIVER_API = {
+    "chaos_driver_create": (C.c_int, [_VP, C.POINTER(_Params), C.POINTER(_VP)]),
+    "chaos_driver_create_custom": (C.c_int, [RENDER_FN, RENDER_FN, _VP, C.POINTER(_Params), C.c_uint32, C.c_uint32, C.POINTER(_VP)]),
+    "chaos_driver_destroy": (C.c_int, [_VP]),
+    "chaos_driver_mouse": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "chaos_driver_start_zooming": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "chaos_driver_zoom_once": (C.c_int, [_VP, C.c_int]),
+    "chaos_driver_stop_zooming": (C.c_int, [_VP]),
+    "chaos_driver_start_moving": (C.c_int, [_VP]),
+    "chaos_driver_stop_moving": (C.c_int, [_VP]),
+    "chaos_driver_start_progressive_rendering": (C.c_int, [_VP, C.c_int]),
+    "chaos_driver_step": (C.c_int, [_VP]),
+    "chaos_driver_set_automatic_quality": (C.c_int, [_VP, C.c_int]),
+    "chaos_driver_set_clock": (C.c_int, [_VP, C.c_int]),
+    "chaos_driver_set_model": (C.c_int, [_VP, C.POINTER(_Params)]),
+    "chaos_driver_display": (C.c_int, [_VP, C.POINTER(C.c_int)]),
+    "chaos_driver_get_state": (C.c_int, [_VP, C.POINTER(_State)]),
+    "chaos_driver_run_zoom_session": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "chaos_driver_last_error": (C.c_char_p, []),
+}
 
-    def step(self):
-        if (self.current == WAITING and self.last in (ZOOMING_AUTO, MOVING)) or self.current == ZOOMING_ONCE:
-            new, self.pr_lvl = PROGRESSIVE, -1
-        elif self.current == PROGRESSIVE and self.pr_lvl >= self.MAX_PROGRESSIVE_RENDERING_LEVEL:
-            new = WAITING
-        else:
-            new = self.current
-        self.last, self.current = self.current, new
-        if self.current == PROGRESSIVE:
-            self.pr_lvl = min(self.MAX_PROGRESSIVE_RENDERING_LEVEL, self.pr_lvl + 1)
 
-    def doZoomingManualOnce(self, inside: bool):
-        self.last, self.current, self.zooming_direction, self.zooming_and_moving = self.current, ZOOMING_ONCE, inside, False
-
-    def startZooming(self, inside: bool):
-        self.last, self.current, self.zooming_direction, self.zooming_and_moving = self.current, ZOOMING_AUTO, inside, False
-
-    def startZoomingAndMoving(self, inside: bool):
-        self.startZooming(inside)
-        self.zooming_and_moving = True
-
-    def stopZooming(self):
-        self.last = self.current
-        self.current = MOVING if self.zooming_and_moving else WAITING
-        self.zooming_and_moving = False
-
-    def startMoving(self):
-        self.last, self.current = self.current, MOVING
-
-    def stopMoving(self):
-        self.last = self.current
-        if not self.zooming_and_moving:
-            self.current = WAITING
-        self.zooming_and_moving = False
-
-    def startProgressiveRendering(self):
-        self.last, self.current, self.pr_lvl, self.zooming_and_moving = self.current, PROGRESSIVE, 0, False
-
-    def isZooming(self) -> bool:
-        return self.current in (ZOOMING_AUTO, ZOOMING_ONCE) or self.zooming_and_moving
-
-    def getZoomingDirection(self) -> bool:
-        if not self.isZooming():
-            raise RuntimeError("cannot ask for zooming direction when not zooming")
-        return self.zooming_direction
-
-    def isMoving(self) -> bool:
-        return self.current == MOVING or self.zooming_and_moving
-
-    def isProgressiveRendering(self) -> bool:
-        return self.current == PROGRESSIVE
-
-    def getProgressiveRenderingLevel(self) -> int:
-        if not self.isProgressiveRendering():
-            raise RuntimeError("cannot ask for Progressive rendering level when not Progressive rendering")
-        return self.pr_lvl
-
-    def isWaiting(self) -> bool:
-        return self.current == WAITING
-
-    def isDifferentThanLast(self) -> bool:
-        return self.current != self.last
+def _lib():
+    lib = _pkg.load_library()
+    if not getattr(lib, "_chaos_driver_bound", False):
+        for name, (res, args) in _DRIVER_API.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        lib._chaos_driver_bound = True
+    return lib
 
 
 class FrameDriver:
-    SHORTEST_FRAME_RENDER_TIME = 15    # ms, GLRenderer.java:190
-    MAX_FRAME_RENDER_TIME = 1000       # ms, GLRenderer.java:194
+    """``renderer``: a CudaFractalRenderer (frames are rendered by chaos_render_fast / chaos_render_quality and timed on the
+    device), or any object with renderFast(model) / renderQuality(model) returning the frame's milliseconds (a stub: the
+    controller then runs without a GPU).  ``model`` is a RenderingModel; it is kept up to date after every call."""
 
-    def __init__(self, renderer, model, clock: Optional[Callable[[], float]] = None, automatic_quality: bool = True):
-        self.renderer = renderer
-        self.model = model
-        self.state = RenderingModeFSM()
-        self.clock = clock or (lambda: time.perf_counter() * 1e3)
-        self.automatic_quality = automatic_quality
-        self.last_frame_render_time = self.SHORTEST_FRAME_RENDER_TIME
-        self.last_mouse_position: Sequence[int] = (0, 0)
-        self.log: List[tuple] = []     # (mode, kind, maxSuperSampling, frame_ms) per rendered frame
-
-    # --- RenderingController.zoomAt --------------------------------------------------------------------------
-    def zoom_at(self, where: Sequence[int], into: bool):
-        self.model.zoomAt(where, into)
-
-    # --- GLRenderer.setParamsToBeRenderedIn -----------------------------------------------------------------
-    def _set_params_to_be_rendered_in(self, ms: int):
-        new_ss = self.model.maxSuperSampling * ms / float(self.last_frame_render_time)
-        self.model.setMaxSuperSampling(min(new_ss, MAX_SUPER_SAMPLING))
-
-    # --- GLRenderer.determineRenderingModeQuality -----------------------------------------------------------
-    def _determine_quality(self) -> bool:
-        if not self.automatic_quality:
-            return True
-        st = self.state
-        if st.isDifferentThanLast():
-            self.model.setMaxSuperSampling(1)
-            return True
-        prev = self.model.maxSuperSampling
-        if st.isZooming() or st.isMoving():
-            self._set_params_to_be_rendered_in(self.SHORTEST_FRAME_RENDER_TIME)
-        elif st.isProgressiveRendering():
-            desired = self.SHORTEST_FRAME_RENDER_TIME * 2 << st.getProgressiveRenderingLevel()
-            desired = max(self.last_frame_render_time * 2, desired)
-            if desired > self.MAX_FRAME_RENDER_TIME or self.model.maxSuperSampling >= MAX_SUPER_SAMPLING:
-                if st.getProgressiveRenderingLevel() != 0:
-                    st.resetState()
-                    self.model.setMaxSuperSampling(prev)
-                    return False
-            else:
-                self._set_params_to_be_rendered_in(desired)
-        return True
-
-    # --- GLRenderer.display + cudaRender + RenderingController.onRenderingDone ---------------------------------
-    def display(self) -> bool:
-        """one frame; returns True if something was rendered"""
-        start = self.clock()
-        st = self.state
-        if st.isZooming():
-            self.zoom_at(self.last_mouse_position, st.getZoomingDirection())
-        if st.isWaiting():
-            return False
-        if not self._determine_quality():
-            return False
-        self.model.zooming = st.isZooming()
-        if st.isZooming():
-            self.model.zoomingIn = st.getZoomingDirection()
-        self.model.mouseFocus = tuple(self.last_mouse_position)
-        mode = st.current
-        if st.isProgressiveRendering():
-            self.renderer.renderQuality(self.model)
-            kind = "quality"
+    def __init__(self, renderer, model, clock: int = CLOCK_DEVICE, automatic_quality: bool = True):
+        self._l = _lib()
+        self.renderer, self.model = renderer, model
+        self.log: List[tuple] = []     # (mode name, kind, maxSuperSampling, frame ms) per rendered frame
+        self._h = _VP()
+        p = model._to_c()
+        if hasattr(renderer, "_h") and hasattr(renderer, "_lib"):
+            self._ok(self._l.chaos_driver_create(renderer._h, C.byref(p), C.byref(self._h)))
+            self._cbs = None
         else:
-            self.renderer.renderFast(self.model)
-            kind = "fast"
-        self.last_frame_render_time = max(1, int(self.clock() - start))   # the reference divides by it; never let it be 0
-        self.log.append((mode, kind, self.model.maxSuperSampling, self.last_frame_render_time))
-        st.step()                                                          # onRenderingDone
-        return True
+            def call(kind):
+                def cb(_user, params, frame_ms):
+                    try:
+                        m = self.model
+                        m.planeSegment = list(params.contents.segment)
+                        m.maxSuperSampling = float(params.contents.max_super_sampling)
+                        m.zooming, m.zoomingIn = bool(params.contents.is_zooming), bool(params.contents.is_zooming_in)
+                        m.mouseFocus = tuple(params.contents.mouse_focus)
+                        ms = getattr(renderer, kind)(m)
+                        frame_ms[0] = float(ms) if ms is not None else -1.0
+                        return 0
+                    except Exception:
+                        return 5
+                return RENDER_FN(cb)
+            self._cbs = (call("renderFast"), call("renderQuality"))
+            self._ok(self._l.chaos_driver_create_custom(self._cbs[0], self._cbs[1], None, C.byref(p), model.canvasWidth, model.canvasHeight,
+                                                         C.byref(self._h)))
+        self._ok(self._l.chaos_driver_set_clock(self._h, clock))
+        self._ok(self._l.chaos_driver_set_automatic_quality(self._h, int(automatic_quality)))
 
-    # --- sessions ---------------------------------------------------------------------------------------------
+    def _ok(self, st):
+        if st != 0:
+            msg = (self._l.chaos_driver_last_error() or b"").decode("utf-8", "replace")
+            raise _check_status.get(st, _pkg.ChaosError)(msg)
+
+    def state(self) -> _State:
+        s = _State()
+        s.struct_size = C.sizeof(_State)
+        self._ok(self._l.chaos_driver_get_state(self._h, C.byref(s)))
+        return s
+
+    def _sync_model(self, s: Optional[_State] = None):
+        s = s or self.state()
+        m = self.model
+        m.planeSegment = list(s.model.segment)
+        m.maxSuperSampling = float(s.model.max_super_sampling)
+        m.zooming, m.zoomingIn = bool(s.model.is_zooming), bool(s.model.is_zooming_in)
+        m.mouseFocus = tuple(s.model.mouse_focus)
+        m.sampleReuseCacheDirty = bool(s.model.sample_reuse_cache_dirty)
+        m.floatingPointPrecision = int(s.model.float_precision)
+        return s
+
+    # RenderingModeFSM / RenderingController's mouse handlers
+    def mouse(self, x: int, y: int): self._ok(self._l.chaos_driver_mouse(self._h, int(x), int(y)))
+    def startZooming(self, inside: bool): self._ok(self._l.chaos_driver_start_zooming(self._h, int(inside), 0))
+    def startZoomingAndMoving(self, inside: bool): self._ok(self._l.chaos_driver_start_zooming(self._h, int(inside), 1))
+    def doZoomingManualOnce(self, inside: bool): self._ok(self._l.chaos_driver_zoom_once(self._h, int(inside)))
+    def stopZooming(self): self._ok(self._l.chaos_driver_stop_zooming(self._h))
+    def startMoving(self): self._ok(self._l.chaos_driver_start_moving(self._h))
+    def stopMoving(self): self._ok(self._l.chaos_driver_stop_moving(self._h))
+    def startProgressiveRendering(self, reset_first: bool = False): self._ok(self._l.chaos_driver_start_progressive_rendering(self._h, int(reset_first)))
+    def step(self): self._ok(self._l.chaos_driver_step(self._h))
+
+    def isWaiting(self) -> bool: return self.state().mode == WAITING
+    def isZooming(self) -> bool: return bool(self.state().zooming)
+    def isMoving(self) -> bool: return bool(self.state().moving)
+    def isProgressiveRendering(self) -> bool: return self.state().mode == PROGRESSIVE
+    def getProgressiveRenderingLevel(self) -> int: return int(self.state().progressive_rendering_level)
+    def isDifferentThanLast(self) -> bool:
+        s = self.state()
+        return s.mode != s.last_mode
+
+    def display(self) -> int:
+        """one animator tick (GLRenderer.display); 0 = nothing rendered, 1 = a fast frame, 2 = a quality frame"""
+        before = self.state().mode
+        k = C.c_int(0)
+        self._ok(self._l.chaos_driver_display(self._h, C.byref(k)))
+        s = self._sync_model()
+        if k.value:
+            self.log.append((MODE_NAMES[before], "quality" if k.value == 2 else "fast", float(s.model.max_super_sampling), float(s.last_frame_render_time_ms)))
+        return k.value
+
     def run_zoom_session(self, where: Sequence[int], into: bool, frames: int) -> int:
-        """mouse pressed at `where` for `frames` animator ticks, then released; progressive refinement until the FSM
-        goes back to Waiting.  Returns the number of frames rendered."""
-        self.last_mouse_position = tuple(where)
-        self.state.startZooming(into)
+        """the button pressed at `where` for `frames` animator ticks, released, progressive refinement until Waiting; tick by
+        tick so that every frame is logged (chaos_driver_run_zoom_session does the same in one native call)"""
+        self.mouse(where[0], where[1])
+        self.startZooming(into)
         n = 0
         for _ in range(frames):
-            n += int(self.display())
-        self.state.stopZooming()
-        self.state.step()                # the timer-fired repaint after release (RenderingController.java:103-106)
-        while not self.state.isWaiting():
+            n += 1 if self.display() else 0
+        self.stopZooming()
+        self.startProgressiveRendering()
+        while not self.isWaiting():
             if not self.display():
                 break
             n += 1
         return n
+
+    def run_zoom_session_native(self, where: Sequence[int], into: bool, frames: int) -> int:
+        n = C.c_uint32(0)
+        self._ok(self._l.chaos_driver_run_zoom_session(self._h, int(where[0]), int(where[1]), int(into), int(frames), C.byref(n)))
+        self._sync_model()
+        return int(n.value)
+
+    def close(self):
+        if self._h:
+            self._l.chaos_driver_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -74,6 +74,88 @@ def gather_bands(frame, rank: int, world: int, band_rows: int, dist) -> int:
     return nbytes
 
 
+class JobSharedMemory:
+    """Host shared memory of an N-process job: [ 64-byte barrier block | pad to a page | RGBA frame ].
+
+    Rank 0 creates the segment, the others attach by name (``dist.broadcast_object_list``).  The frame part is what
+    ``chaos_set_host_target`` takes: every rank's compose kernel writes its bands there over its own PCIe link, so the
+    whole frame of an N-GPU render arrives in host memory N links wide and nothing is gathered on a device first.  The
+    barrier block is what ``chaos_set_frame_barrier`` takes.  Collective: every rank constructs it."""
+
+    PAGE = 4096
+
+    def __init__(self, rank: int, world: int, height: int, width: int, dist=None):
+        from multiprocessing import resource_tracker, shared_memory
+        import numpy as np
+        self.rank, self.world = rank, world
+        self.frame_bytes = height * width * 4
+        size = self.PAGE + ((self.frame_bytes + self.PAGE - 1) // self.PAGE) * self.PAGE
+        name = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=size)
+            self.shm.buf[:self.PAGE] = bytes(self.PAGE)
+            name[0] = self.shm.name
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:    # the creator unlinks it; an attaching process must not (Python < 3.13 registers it regardless)
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        base = np.frombuffer(self.shm.buf, dtype=np.uint8)
+        self.barrier_address = base.ctypes.data
+        self.frame_address = base.ctypes.data + self.PAGE
+        self.frame = base[self.PAGE:self.PAGE + self.frame_bytes].view(np.uint32).reshape(height, width)
+        self._base = base
+
+    def attach(self, renderer, host_target: bool = True, barrier: bool = True):
+        if host_target:
+            renderer.setHostTarget(self.frame_address, self.frame_bytes)
+        if barrier:
+            renderer.setFrameBarrier(self.barrier_address, self.world)
+
+    def close(self, dist=None):
+        self.frame = self._base = None
+        if dist is not None and self.world > 1:
+            dist.barrier()
+        try:
+            self.shm.close()
+        except BufferError:
+            pass
+        if self.rank == 0:
+            try:
+                self.shm.unlink()
+            except FileNotFoundError:
+                pass
+
+
+def share_frame_native(renderer, rank: int, world: int, dist) -> bool:
+    """Rank 0 exports its device frame (chaos_ipc_export_frame), the others open it as their compose target
+    (chaos_ipc_open_frame).  Collective.  False if some rank could not map it (nobody then uses it)."""
+    import torch
+    payload = [None]
+    if rank == 0:
+        try:
+            payload = [renderer.exportFrameHandle()]
+        except Exception:
+            payload = [None]
+    dist.broadcast_object_list(payload, src=0)
+    ok = 1 if payload[0] is not None else 0
+    if rank != 0 and ok:
+        try:
+            renderer.openFrameHandle(payload[0])
+        except Exception:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if rank != 0:
+            renderer.setOutputTarget(0)
+        return False
+    return True
+
+
 def share_frame(renderer, rank: int, world: int, dist):
     """Map rank 0's device frame into the other ranks (CUDA IPC) and make it their compose target.
     Returns an object that must stay alive while the target is in use (close() unmaps), or None if this cannot be

@@ -177,6 +177,68 @@ CHAOS_API chaos_status chaos_set_partition(chaos_renderer *r, uint32_t part_inde
  * chaos_free_resources resets it. */
 CHAOS_API chaos_status chaos_set_output_target(chaos_renderer *r, uint64_t device_ptr);
 
+/* ---- multi-GPU plumbing: one process per GPU (the reference has none of this: device 0 only, CudaHelpers.java:36-41) ----
+ * The frame of an N-GPU render is assembled by the compose kernels themselves: every rank composes its bands straight
+ * into ONE frame, either rank 0's device frame (chaos_ipc_export_frame / chaos_ipc_open_frame: the bands cross NVLink
+ * as 128-bit stores) or a frame in host shared memory that every rank's process has mapped (chaos_set_host_target:
+ * every GPU writes its bands over its own PCIe link).  chaos_set_frame_barrier makes every render call end when all
+ * ranks' bands have landed. */
+typedef struct chaos_ipc_handle { unsigned char bytes[64]; } chaos_ipc_handle;
+/* DEVICE mode, the rank that owns the frame: a handle other processes can open */
+CHAOS_API chaos_status chaos_ipc_export_frame(chaos_renderer *r, chaos_ipc_handle *out);
+/* DEVICE mode, the other ranks: map that frame into this process and make it the compose target
+ * (chaos_set_output_target with the mapped address); chaos_free_resources / chaos_close unmap it */
+CHAOS_API chaos_status chaos_ipc_open_frame(chaos_renderer *r, const chaos_ipc_handle *frame);
+/* DEVICE mode: compose writes into caller-owned HOST memory instead (width*height*4 bytes, page-aligned, e.g. a POSIX
+ * shared-memory segment all ranks have mapped).  The library pins and maps it (cuMemHostRegister) for as long as it is
+ * the target; NULL, chaos_free_resources and chaos_close release it. */
+CHAOS_API chaos_status chaos_set_host_target(chaos_renderer *r, void *host_frame, size_t bytes);
+/* `shm_block`: 64 zero-initialised bytes of host memory shared by the `world` processes of the job (NULL = no barrier).
+ * Every later render call announces its frame there when its own kernels are done and returns when all ranks have
+ * announced theirs -- on return the target frame holds every rank's bands.  Waits are bounded (10 s -> CHAOS_ERR_CUDA). */
+CHAOS_API chaos_status chaos_set_frame_barrier(chaos_renderer *r, void *shm_block, uint32_t world);
+
+/* ---- frame driver: rendering/RenderingModeFSM.java:9-155 + the automatic-quality controller of
+ * rendering/GLRenderer.java:113-245 + RenderingController.zoomAt (:130-150), see csrc/chaos_driver.cpp ---- */
+typedef enum chaos_rendering_mode {      /* RenderingModeFSM.RenderingMode */
+    CHAOS_MODE_WAITING = 0, CHAOS_MODE_ZOOMING_AUTO = 1, CHAOS_MODE_ZOOMING_ONCE = 2, CHAOS_MODE_MOVING = 3, CHAOS_MODE_PROGRESSIVE_RENDERING = 4
+} chaos_rendering_mode;
+typedef enum chaos_driver_clock {
+    CHAOS_CLOCK_DEVICE = 0,    /* the controller sees the frame's device time (CUDA events, float ms) */
+    CHAOS_CLOCK_WALL_INT = 1   /* host clock truncated to int ms, as the reference (GLRenderer.java:129,145) */
+} chaos_driver_clock;
+typedef struct chaos_driver chaos_driver;
+/* a frame rendered by somebody else (tests; a host that wraps the render calls): fill *frame_ms or leave it negative */
+typedef chaos_status (*chaos_render_fn)(void *user, chaos_params *model, float *frame_ms);
+typedef struct chaos_driver_state {
+    uint32_t struct_size;
+    chaos_rendering_mode mode, last_mode;
+    int32_t progressive_rendering_level;
+    uint8_t zooming, moving, zooming_in, last_kind;   /* last_kind: 0 nothing rendered yet, 1 fast, 2 quality */
+    float last_frame_render_time_ms;
+    uint64_t frames;
+    chaos_params model;                                /* the model as the driver has left it (segment, maxSuperSampling, flags) */
+} chaos_driver_state;
+CHAOS_API chaos_status chaos_driver_create(chaos_renderer *r, const chaos_params *model, chaos_driver **out);
+CHAOS_API chaos_status chaos_driver_create_custom(chaos_render_fn fast, chaos_render_fn quality, void *user, const chaos_params *model,
+                                                  uint32_t canvas_width, uint32_t canvas_height, chaos_driver **out);
+CHAOS_API chaos_status chaos_driver_destroy(chaos_driver *d);
+CHAOS_API chaos_status chaos_driver_mouse(chaos_driver *d, int x, int y);                        /* lastMousePosition, mouseFocus */
+CHAOS_API chaos_status chaos_driver_start_zooming(chaos_driver *d, int inside, int moving_too);  /* startZooming / startZoomingAndMoving */
+CHAOS_API chaos_status chaos_driver_zoom_once(chaos_driver *d, int inside);                      /* doZoomingManualOnce */
+CHAOS_API chaos_status chaos_driver_stop_zooming(chaos_driver *d);
+CHAOS_API chaos_status chaos_driver_start_moving(chaos_driver *d);
+CHAOS_API chaos_status chaos_driver_stop_moving(chaos_driver *d);
+CHAOS_API chaos_status chaos_driver_start_progressive_rendering(chaos_driver *d, int reset_first);
+CHAOS_API chaos_status chaos_driver_step(chaos_driver *d);                                       /* RenderingModeFSM.step() alone */
+CHAOS_API chaos_status chaos_driver_set_automatic_quality(chaos_driver *d, int on);
+CHAOS_API chaos_status chaos_driver_set_clock(chaos_driver *d, chaos_driver_clock clock);
+CHAOS_API chaos_status chaos_driver_set_model(chaos_driver *d, const chaos_params *model);
+CHAOS_API chaos_status chaos_driver_display(chaos_driver *d, int *rendered);                     /* GLRenderer.display(): one tick */
+CHAOS_API chaos_status chaos_driver_get_state(const chaos_driver *d, chaos_driver_state *out);
+CHAOS_API chaos_status chaos_driver_run_zoom_session(chaos_driver *d, int x, int y, int inside, uint32_t ticks, uint32_t *frames_rendered);
+CHAOS_API const char *chaos_driver_last_error(void);
+
 CHAOS_API const char *chaos_last_error(void);
 CHAOS_API uint32_t chaos_abi_version(void);
 

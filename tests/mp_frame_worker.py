@@ -1,0 +1,68 @@
+"""Worker of tests/test_multi_gpu.py: one rank of an N-process render, launched by torch.distributed.run.
+
+Every rank renders its bands of the same frame; the frame is assembled by the compose kernels (host shared memory or
+rank 0's device frame) under the library's frame barrier, and rank 0 compares it with the unpartitioned frame it rendered
+first.  Exit code 0 = every check passed on every rank.  With fewer devices than ranks all ranks share device 0."""
+import importlib
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import cases
+    import helpers
+    cu = importlib.import_module("chaos-ultra_b200")
+    part = importlib.import_module("chaos-ultra_b200.partition")
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dev = int(os.environ["LOCAL_RANK"]) if torch.cuda.device_count() >= world else 0
+    dist.init_process_group("gloo")
+    mode = sys.argv[1]
+    case = dict(cases.MAIN_CASES[2], W=1531, H=1077, image=cases.seg(-0.5, 0.0, 2.0, 1531, 1077), maxIter=2100)   # ragged, several samples
+    W, H, band = case["W"], case["H"], 32
+    with cu.CudaFractalRendererProvider(device=dev) as prov:
+        r = prov.getRenderer("mandelbrot", False)
+        r.initializeRendering(W, H, None, cu.OUTPUT_DEVICE)
+        m = helpers.model_for(cu, case)
+        r.renderQuality(m)
+        whole, whole_it = r.outputRGBA().copy(), r.stats().pixel_iterations
+        job = part.JobSharedMemory(rank, world, H, W, dist)
+        r.setPartition(rank, world, band)
+        if mode == "host":
+            job.attach(r, host_target=True, barrier=True)
+        else:
+            assert part.share_frame_native(r, rank, world, dist)
+            job.attach(r, host_target=False, barrier=True)
+        its = []
+        for frame in range(3):          # several frames: the barrier counts announcements, not a flag
+            r.renderQuality(helpers.model_for(cu, case))
+            its.append(r.stats().pixel_iterations)
+            if rank == 0:               # on return every rank's bands are in the frame
+                got = job.frame if mode == "host" else r.outputRGBA()
+                assert np.array_equal(got, whole), "frame %d assembled from %d ranks differs from the whole frame" % (frame, world)
+            dist.barrier()              # nobody composes the next frame over the one rank 0 is looking at
+        t = torch.tensor([its[-1]], dtype=torch.int64)
+        dist.all_reduce(t)
+        assert int(t.item()) == whole_it, "pixel-iterations of the parts %d != whole frame %d" % (int(t.item()), whole_it)
+        # a fast frame of a partitioned renderer renders the own bands afresh (include/chaos_ultra.h)
+        r.renderFast(helpers.model_for(cu, case))
+        assert r.stats().reuse_ms == 0
+        dist.barrier()
+        r.setFrameBarrier(0, 0)
+        if mode == "host":
+            r.setHostTarget(0, 0)
+        else:
+            r.setOutputTarget(0)
+        job.close(dist)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -328,11 +328,12 @@ def test_frame_driver_zoom_session_on_the_gpu(cu, provider, tmp_path):
     m = cu.RenderingModel(canvasWidth=W, canvasHeight=H)
     m.resetRenderingValuesToDefault()
     r.supplyDefaultValues(m)
-    d = drv.FrameDriver(r, m)
+    d = drv.FrameDriver(r, m)                                 # native controller, frames timed on the device (CUDA events)
     h0 = m.planeSegment[3] - m.planeSegment[1]
     n = d.run_zoom_session((W // 2, H // 2), True, frames=20)
-    assert n >= 21 and d.state.isWaiting()
+    assert n >= 21 and d.isWaiting()
     assert [k for _, k, _, _ in d.log[:20]] == ["fast"] * 20 and d.log[-1][1] == "quality"
+    assert all(0.0 < ms < 1000.0 for _, _, _, ms in d.log)
     assert abs((m.planeSegment[3] - m.planeSegment[1]) / h0 - float(np.float32(0.977)) ** 20) < 1e-9
     assert 1.0 <= m.maxSuperSampling <= 64.0
     io.save_png(tmp_path / "last.png", r.outputRGBA())

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 for set in ${SETTINGS:-X=0}; do
   for w in ${WORKLOADS:-c2 c2ex2 c2f32}; do
     tag=$(echo "$set" | tr '+,=/:' '_____')
-    env $(echo "$set" | tr '+' ' ') timeout 300 python bench.py --workload $w --steps ${STEPS:-20} --warmup 3 --no-cpu-baseline --no-full-trips > gpurun_out/env_${tag}_$w.json 2> /dev/null
+    env $(echo "$set" | tr '+' ' ') timeout 300 python bench.py --workload $w --steps ${STEPS:-20} --warmup 3 --no-cpu-baseline --no-full-trips --no-extras > gpurun_out/env_${tag}_$w.json 2> /dev/null
     python - <<P
 import json
 try:
