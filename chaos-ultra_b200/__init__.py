@@ -134,6 +134,7 @@ _API = {
     "chaos_provider_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_VP)]),
     "chaos_provider_destroy": (C.c_int, [_VP]),
     "chaos_list_fractals": (C.c_int, [_VP, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_uint32)]),
+    "chaos_register_module": (C.c_int, [_VP, C.c_char_p, C.c_char_p]),
     "chaos_open": (C.c_int, [_VP, C.c_char_p, C.c_int, C.POINTER(_VP)]),
     "chaos_active_renderer": (_VP, [_VP]),
     "chaos_initialize": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP, C.c_uint32, C.c_int]),
@@ -159,6 +160,8 @@ _API = {
     "chaos_set_output_target": (C.c_int, [_VP, C.c_uint64]),
     "chaos_ipc_export_frame": (C.c_int, [_VP, _VP]),
     "chaos_ipc_open_frame": (C.c_int, [_VP, _VP]),
+    "chaos_ipc_export_records": (C.c_int, [_VP, _VP]),
+    "chaos_ipc_open_records": (C.c_int, [_VP, C.c_uint32, _VP]),
     "chaos_set_host_target": (C.c_int, [_VP, _VP, C.c_size_t]),
     "chaos_set_frame_barrier": (C.c_int, [_VP, _VP, C.c_uint32]),
     "chaos_last_error": (C.c_char_p, []),
@@ -453,6 +456,16 @@ class CudaFractalRenderer:
         buf = C.create_string_buffer(bytes(handle), 64)
         _check(self._lib, self._lib.chaos_ipc_open_frame(self._h, C.cast(buf, _VP)))
 
+    def exportRecordHandles(self) -> bytes:
+        """128 bytes: handles of this renderer's two record buffers (multi-GPU fast frames)."""
+        buf = C.create_string_buffer(128)
+        _check(self._lib, self._lib.chaos_ipc_export_records(self._h, C.cast(buf, _VP)))
+        return buf.raw
+
+    def openRecordHandles(self, peer_rank: int, handles: bytes) -> None:
+        buf = C.create_string_buffer(bytes(handles), 128)
+        _check(self._lib, self._lib.chaos_ipc_open_records(self._h, int(peer_rank), C.cast(buf, _VP)))
+
     def setHostTarget(self, address: int, nbytes: int) -> None:
         """DEVICE mode: compose into caller-owned, page-aligned host memory (e.g. shared memory all ranks mapped); 0 releases it."""
         _check(self._lib, self._lib.chaos_set_host_target(self._h, int(address) or None, int(nbytes)))
@@ -498,6 +511,10 @@ class CudaFractalRendererProvider:
         arr = (C.c_char_p * n.value)()
         _check(self._lib, self._lib.chaos_list_fractals(self._h, arr, n.value, C.byref(n)))
         return [a.decode() for a in arr]
+
+    def registerModule(self, fractalName: str, fileStem: str) -> None:
+        """a fractal author's module <kernels_dir>/<fileStem>.cubin under a display name of its own"""
+        _check(self._lib, self._lib.chaos_register_module(self._h, fractalName.encode(), fileStem.encode()))
 
     def getDefaultRenderer(self) -> CudaFractalRenderer:
         return self.getRenderer("mandelbrot", False)

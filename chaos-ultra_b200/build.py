@@ -34,6 +34,15 @@ def _cuda_include() -> str:
     return str(Path(_nvcc()).resolve().parent.parent / "include")
 
 
+BUILD_LOG = []      # (action, artefact): what the last build_all() rebuilt and what it found up to date
+
+
+def _note(action: str, out: Path):
+    BUILD_LOG.append((action, str(out.relative_to(PKG_DIR.parent)) if str(out).startswith(str(PKG_DIR.parent)) else str(out)))
+    if os.environ.get("CHAOS_BUILD_QUIET") != "1":
+        sys.stderr.write("[build] %-7s %s\n" % (action, BUILD_LOG[-1][1]))
+
+
 def _newer(target: Path, sources) -> bool:
     if not target.exists():
         return False
@@ -61,7 +70,9 @@ def build_module(src: Path, force: bool = False) -> Path:
     out = KERNELS_DIR / (src.stem + ".cubin")
     deps = [src] + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [Path(__file__)]
     if not force and _newer(out, deps):
+        _note("reused", out)
         return out
+    _note("rebuilt", out)
     extra = os.environ.get("CHAOS_NVCC_EXTRA", "").split()    # experiments only, e.g. -DCHAOS_REFILL_SLOTS=6
     cmd = [_nvcc(), "-cubin", *ARCH_FLAGS, *NVCC_FLAGS, *extra, "-I", str(CSRC), str(src), "-o", str(out)]
     _run(cmd, log=KERNELS_DIR / (src.stem + ".ptxas.log"))
@@ -83,7 +94,9 @@ def build_compat_module(src: Path, out_dir: Path = COMPAT_DIR, fused_plane_y: bo
     out = out_dir / (src.stem + ".cubin")
     deps = [src] + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((CSRC / "compat").glob("*.cuh")) + [Path(__file__)]
     if not force and _newer(out, deps):
+        _note("reused", out)
         return out
+    _note("rebuilt", out)
     wrap = out_dir / ("tmp_compiling_%s.cu" % src.stem)
     wrap.write_text('#include "compat/chaos_compat_pre.cuh"\n#include "%s"\n#include "compat/chaos_compat_post.cuh"\n' % src)
     try:
@@ -109,7 +122,9 @@ def build_library(force: bool = False) -> Path:
     srcs = [CSRC / "chaos_abi.cpp", CSRC / "chaos_driver.cpp"]
     deps = srcs + sorted(CSRC.glob("*.h")) + [PKG_DIR.parent / "include" / "chaos_ultra.h", Path(__file__)]
     if not force and _newer(LIB_PATH, deps):
+        _note("reused", LIB_PATH)
         return LIB_PATH
+    _note("rebuilt", LIB_PATH)
     cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-fvisibility=hidden",
            "-I", _cuda_include(), *map(str, srcs), "-o", str(LIB_PATH), "-ldl", "-lm"]
     _run(cmd)
@@ -121,12 +136,19 @@ def build_bench_kernels(force: bool = False) -> Path:
     src = PKG_DIR.parent / "bench_kernels" / "peak.cu"
     out = src.with_suffix(".cubin")
     if not force and _newer(out, [src]):
+        _note("reused", out)
         return out
+    _note("rebuilt", out)
     _run([_nvcc(), "-cubin", *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", str(src), "-o", str(out)])
     return out
 
 
 def build_all(force: bool = False):
+    """Everything, in-tree.  An artefact is reused only if it is newer than every source it depends on (all headers of csrc/
+    and this script included); what was rebuilt and what was reused is logged line by line (stderr) and kept in BUILD_LOG.
+    CHAOS_BUILD_FORCE=1 rebuilds regardless."""
+    force = force or os.environ.get("CHAOS_BUILD_FORCE") == "1"
+    del BUILD_LOG[:]
     lib = build_library(force)
     mods = [build_module(s, force) for s in module_sources()]
     build_bench_kernels(force)

@@ -290,7 +290,13 @@ static const uint32_t g_n_modules = sizeof g_modules / sizeof g_modules[0];
 /* ------------------------------------------------------------------------------------------
  * objects
  * ---------------------------------------------------------------------------------------- */
+struct registered_module {      /* chaos_register_module: owns the strings its module_desc points at */
+    std::string name, stem;
+    module_desc desc;
+};
+
 struct chaos_provider {
+    std::vector<registered_module *> registered;
     std::string kernels_dir;
     int device = 0;
     CUdevice cu_device = 0;
@@ -349,6 +355,10 @@ struct chaos_renderer {
     uint32_t width = 0, height = 0;
     chaos_output_mode mode = CHAOS_OUTPUT_HOST;
     record_buffer buf[2];          /* DeviceMemoryDoubleBuffer2D: [0] primary, [1] secondary */
+    CUdeviceptr alloc[2] = {0, 0}; /* the two buffers in allocation order; buf[0].ptr == alloc[primary_alloc] */
+    uint32_t primary_alloc = 0;
+    /* multi-GPU fast frames: the other ranks' two record buffers mapped into this process (chaos_ipc_open_records) */
+    CUdeviceptr peer_records[CHAOS_MAX_PEERS][2] = {};
     bool buffers_switched = false;
     bool primary_dirty = true;
     bool have_last = false;        /* lastRendering != null */
@@ -397,7 +407,11 @@ struct chaos_renderer {
     int host_compose_blocks = 0;   /* CTAs of that compose: 0 = one per SM, -1 = the usual grid (CHAOS_HOST_COMPOSE_BLOCKS) */
     uint32_t part_index = 0, part_count = 1, band_rows = 64;
     chaos_stats stats;
-    uint32_t engine = 2;           /* 2 = orbit streams (default), 1 = lane-refill scheduler, 0 = tile-synchronous */
+    /* which kernels iterate: 0 = tile-synchronous with the reference's operation sequence (differential check), 1 = lane-refill
+     * scheduler (render_refill.cuh), 2 = orbit streams (render_streams.cuh), 3 = by frame (default): one sample per pixel ->
+     * the single refill launch (c4 35.0 ms against 36.1 with streams: nothing to sort, every orbit is long); several samples
+     * with an iteration limit under sync_below_iters -> tile-synchronous kernel; several samples otherwise -> streams */
+    uint32_t engine = 3;
     uint32_t block_iters = 0;      /* 0 = choose from maxIterations */
     uint32_t shortcuts = CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE;   /* count-preserving shortcuts of the escape loop */
     uint32_t sched_idle_indep = 10, sched_idle_rounds = 16;   /* see take_scheduling_pass (render_refill.cuh) */
@@ -454,6 +468,7 @@ extern "C" chaos_status chaos_provider_destroy(chaos_provider *p)
 {
     if (!p) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "provider handle is NULL");
     if (p->active) { chaos_close(p->active); }
+    for (registered_module *m : p->registered) delete m;
     if (p->ctx) D->p_cuDevicePrimaryCtxRelease(p->cu_device);
     delete p;
     return CHAOS_OK;
@@ -464,8 +479,31 @@ extern "C" chaos_renderer *chaos_active_renderer(const chaos_provider *p) { retu
 extern "C" chaos_status chaos_list_fractals(chaos_provider *p, const char **names, uint32_t capacity, uint32_t *count)
 {
     if (!p) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "provider handle is NULL");
-    if (count) *count = g_n_modules;
-    if (names) for (uint32_t i = 0; i < g_n_modules && i < capacity; ++i) names[i] = g_modules[i].fractal_name;
+    const uint32_t n = g_n_modules + (uint32_t)p->registered.size();
+    if (count) *count = n;
+    if (names)
+        for (uint32_t i = 0; i < n && i < capacity; ++i)
+            names[i] = i < g_n_modules ? g_modules[i].fractal_name : p->registered[i - g_n_modules]->desc.fractal_name;
+    return CHAOS_OK;
+}
+
+static void defaults_none(chaos_defaults *d) { defaults_base(d); }
+
+/* the counterpart of adding a Module*.java and registering it (CudaFractalRendererProvider.java:19-31): a fractal author's
+ * module <kernels_dir>/<file_stem>.cubin under a display name of its own; no defaults, constants through chaos_write_constant */
+extern "C" chaos_status chaos_register_module(chaos_provider *p, const char *fractal_name, const char *file_stem)
+{
+    if (!p) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "provider handle is NULL");
+    if (!fractal_name || !*fractal_name || !file_stem || !*file_stem) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "a module needs a name and a file");
+    if (strchr(file_stem, '/') || strstr(file_stem, "..")) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "the module file must lie in the kernels directory: %s", file_stem);
+    for (uint32_t i = 0; i < g_n_modules; ++i)
+        if (!strcmp(g_modules[i].fractal_name, fractal_name)) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Fractal %s is already registered", fractal_name);
+    for (registered_module *m : p->registered)
+        if (m->name == fractal_name) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Fractal %s is already registered", fractal_name);
+    registered_module *m = new registered_module();
+    m->name = fractal_name; m->stem = file_stem;
+    m->desc = module_desc{m->name.c_str(), m->stem.c_str(), nullptr, custom_none, defaults_none};
+    p->registered.push_back(m);
     return CHAOS_OK;
 }
 
@@ -586,6 +624,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     const module_desc *desc = nullptr;
     for (uint32_t i = 0; i < g_n_modules; ++i)
         if (!strcmp(g_modules[i].fractal_name, fractal_name)) desc = &g_modules[i];
+    for (registered_module *m : p->registered)
+        if (m->name == fractal_name) desc = &m->desc;
     if (!desc) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "Unknown fractal: %s", fractal_name);
     if (p->active) chaos_close(p->active);                         /* closing the previous renderer :52 */
     chaos_renderer *r = new chaos_renderer();
@@ -595,7 +635,7 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     r->stats.struct_size = sizeof(chaos_stats);
     /* debugging knobs (not part of the reference's interface): engine 0 is the differential check of engine 1 */
     const char *eng = getenv("CHAOS_ENGINE");
-    if (eng) r->engine = (uint32_t)std::min(std::max(atoi(eng), 0), 2);
+    if (eng) r->engine = (uint32_t)std::min(std::max(atoi(eng), 0), 3);
     const char *hf = getenv("CHAOS_HOT_FIRST");
     if (hf) r->hot_first = (uint32_t)atoi(hf) ? 1u : 0u;
     const char *prb = getenv("CHAOS_PROBE_TRIPS");
@@ -732,6 +772,13 @@ static chaos_status launch_stream_chain(chaos_renderer *r, chaos_render_args &b,
     return st;
 }
 
+static void release_peer_records(chaos_renderer *r)
+{
+    for (uint32_t q = 0; q < CHAOS_MAX_PEERS; ++q)
+        for (int i = 0; i < 2; ++i)
+            if (r->peer_records[q][i]) { D->p_cuIpcCloseMemHandle(r->peer_records[q][i]); r->peer_records[q][i] = 0; }
+}
+
 static void release_targets(chaos_renderer *r)
 {
     if (r->ipc_frame) { D->p_cuIpcCloseMemHandle(r->ipc_frame); r->ipc_frame = 0; }
@@ -741,7 +788,8 @@ static void release_targets(chaos_renderer *r)
 
 static void free_frame_memory(chaos_renderer *r)
 {
-    for (int i = 0; i < 2; ++i) if (r->buf[i].ptr) { D->p_cuMemFree(r->buf[i].ptr); r->buf[i].ptr = 0; r->buf[i].pitch = 0; }
+    release_peer_records(r);
+    for (int i = 0; i < 2; ++i) if (r->buf[i].ptr) { D->p_cuMemFree(r->buf[i].ptr); r->buf[i].ptr = 0; r->buf[i].pitch = 0; r->alloc[i] = 0; }
     if (r->palette) { D->p_cuMemFree(r->palette); r->palette = 0; }
     if (r->tile_key) { D->p_cuMemFree(r->tile_key); r->tile_key = 0; }
     if (r->tile_order) { D->p_cuMemFree(r->tile_order); r->tile_order = 0; }
@@ -775,7 +823,9 @@ extern "C" chaos_status chaos_initialize(chaos_renderer *r, uint32_t width, uint
     for (int i = 0; i < 2; ++i) {
         CUresult e = D->p_cuMemAllocPitch(&r->buf[i].ptr, &r->buf[i].pitch, (size_t)width * 16u, height, 16);
         if (e != CUDA_SUCCESS) { free_frame_memory(r); return fail(CHAOS_ERR_CUDA, "cuMemAllocPitch(%ux%u) failed: %s", width, height, cu_err_name(e)); }
+        r->alloc[i] = r->buf[i].ptr;
     }
+    r->primary_alloc = 0;
     const size_t all_tiles = (size_t)((width + 7u) / 8u) * ((height + 3u) / 4u);
     CUresult e = D->p_cuMemAlloc(&r->tile_key, all_tiles * 4u);
     if (e == CUDA_SUCCESS) e = D->p_cuMemAlloc(&r->tile_order, all_tiles * 4u);
@@ -890,6 +940,38 @@ extern "C" chaos_status chaos_ipc_open_frame(chaos_renderer *r, const chaos_ipc_
     CUresult e = D->p_cuIpcOpenMemHandle(&r->ipc_frame, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
     if (e != CUDA_SUCCESS) { r->ipc_frame = 0; return fail(CHAOS_ERR_CUDA, "cuIpcOpenMemHandle failed: %s", cu_err_name(e)); }
     r->rgba_target = r->ipc_frame;
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_ipc_export_records(chaos_renderer *r, chaos_ipc_handle out[2])
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (r->state != CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Renderer has to be initialized first");
+    if (!out) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "out is NULL");
+    ctx_guard g(r->provider);
+    for (int i = 0; i < 2; ++i) {
+        CUresult e = D->p_cuIpcGetMemHandle((CUipcMemHandle *)&out[i], r->alloc[i]);
+        if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuIpcGetMemHandle failed: %s", cu_err_name(e));
+    }
+    return CHAOS_OK;
+}
+
+extern "C" chaos_status chaos_ipc_open_records(chaos_renderer *r, uint32_t peer_rank, const chaos_ipc_handle in[2])
+{
+    chaos_status st = check_renderer(r);
+    if (st != CHAOS_OK) return st;
+    if (r->state != CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Renderer has to be initialized first");
+    if (!in || peer_rank >= CHAOS_MAX_PEERS) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "peer rank %u out of range (0..%d)", peer_rank, CHAOS_MAX_PEERS - 1);
+    ctx_guard g(r->provider);
+    D->p_cuStreamSynchronize(r->stream);
+    for (int i = 0; i < 2; ++i) {
+        if (r->peer_records[peer_rank][i]) { D->p_cuIpcCloseMemHandle(r->peer_records[peer_rank][i]); r->peer_records[peer_rank][i] = 0; }
+        CUipcMemHandle h;
+        memcpy(&h, &in[i], sizeof h);
+        CUresult e = D->p_cuIpcOpenMemHandle(&r->peer_records[peer_rank][i], h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
+        if (e != CUDA_SUCCESS) { r->peer_records[peer_rank][i] = 0; return fail(CHAOS_ERR_CUDA, "cuIpcOpenMemHandle(records of rank %u) failed: %s", peer_rank, cu_err_name(e)); }
+    }
     return CHAOS_OK;
 }
 
@@ -1084,7 +1166,7 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
     a->n_tiles = owned_tile_rows(a->tile_rows, a->band_tile_rows, r->part_index, r->part_count) * a->tiles_x;
     a->tile_key = (uint32_t *)r->tile_key;
     a->tile_order = (uint32_t *)r->tile_order;
-    a->engine = r->engine;
+    a->engine = r->engine ? 1u : 0u;
     /* trips between scheduling points: long enough to amortise a scheduling pass, short enough that a lane whose
      * orbit ended does not idle long; orbits are at most max_iter long */
     a->block_iters = r->block_iters ? r->block_iters : 128u;
@@ -1209,7 +1291,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         return fail(CHAOS_ERR_RENDERER, "maxSuperSampling must be >= 1 for a quality render but is %g (device assert, fractalRendererGeneric.cu:174)", m->max_super_sampling);
     chaos_precision prec = frame_precision(r, m);
     const bool dbl = prec != CHAOS_PRECISION_SINGLE;               /* tooBig still runs the double kernel :213-217 */
-    if (r->buffers_switched) { std::swap(r->buf[0], r->buf[1]); r->buffers_switched = false; }  /* resetBufferOrder */
+    if (r->buffers_switched) { std::swap(r->buf[0], r->buf[1]); r->buffers_switched = false; r->primary_alloc = 0; }  /* resetBufferOrder */
     chaos_render_args a;
     fill_render_args(r, m, &a);
     a.out = (chaos_pixel_info *)r->buf[0].ptr; a.out_pitch = r->buf[0].pitch;
@@ -1224,9 +1306,10 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         /* Short orbits (low iteration limit) with several samples: the per-orbit scheduling work of the refill
          * engine costs more than the divergence it removes, so those frames take the tile-synchronous kernel
          * (same arithmetic, same records).  CHAOS_ENGINE=0 forces it, with the reference's 7-operation trip. */
-        const bool sync_kernel = r->engine == 0 || (r->engine == 1 && S0 >= 2u && a.max_iter < r->sync_below_iters);
+        const bool low_limit = S0 >= 2u && a.max_iter < r->sync_below_iters;
+        const bool sync_kernel = r->engine == 0 || ((r->engine == 1 || r->engine == 3) && low_limit);
         a.force_exact = r->engine == 0 ? 1u : 0u;
-        const bool streams = r->engine == 2;
+        const bool streams = r->engine == 2 || (r->engine == 3 && S0 >= 2u && !low_limit);
         a.probe_trips = r->probe_trips;
         if (streams && !ensure_lists(r, (size_t)((a.tiles_x * (size_t)a.tile_rows)) * (S0 <= 1u ? 32u : 64u)))
             return fail(CHAOS_ERR_CUDA, "cannot allocate the orbit lists of a %ux%u frame", r->width, r->height);
@@ -1368,6 +1451,17 @@ extern "C" chaos_status chaos_render_quality(chaos_renderer *r, chaos_params *m)
     return render_quality_locked(r, m);
 }
 
+/* multi-GPU fast frames are possible when the partition is one slab per rank, every other rank's record buffers are mapped
+ * and the ranks run in step (frame barrier) */
+static bool peers_ready(const chaos_renderer *r)
+{
+    if (r->part_count > CHAOS_MAX_PEERS || !r->barrier) return false;
+    if ((uint64_t)r->band_rows * r->part_count < r->height) return false;
+    for (uint32_t q = 0; q < r->part_count; ++q)
+        if (q != r->part_index && !(r->peer_records[q][0] && r->peer_records[q][1])) return false;
+    return true;
+}
+
 extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
 {
     chaos_status st = check_renderer(r);
@@ -1382,7 +1476,8 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
     /* A rank that renders only its row bands has only its own rows of the previous frame, and the reprojection reads the
      * previous frame around every pixel: without the other ranks' rows there is nothing valid to reuse outside the own
      * bands, so the frame is rendered afresh (same fallback as a dirty cache). */
-    if (r->part_count > 1u) return render_quality_locked(r, m);
+    const bool slabs = r->part_count > 1u && peers_ready(r);
+    if (r->part_count > 1u && !slabs) return render_quality_locked(r, m);
 
     chaos_precision prec = frame_precision(r, m);
     const bool dbl = prec != CHAOS_PRECISION_SINGLE;
@@ -1391,6 +1486,11 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
     for (int i = 0; i < 4; ++i) { a.image_reused[i] = r->last.segment[i]; a.image_reusedf[i] = (float)r->last.segment[i]; }
     bool split = false, fused = false;
     a.in = (const chaos_pixel_info *)r->buf[0].ptr; a.in_pitch = r->buf[0].pitch;   /* input = primary */
+    if (slabs) {     /* every rank's primary buffer is its alloc[primary_alloc]: the ranks make the same calls in the same order */
+        a.slab_rows = r->band_rows;
+        for (uint32_t q = 0; q < r->part_count; ++q)
+            a.in_peer[q] = (const chaos_pixel_info *)(q == r->part_index ? r->buf[0].ptr : r->peer_records[q][r->primary_alloc]);
+    }
     a.out = (chaos_pixel_info *)r->buf[1].ptr; a.out_pitch = r->buf[1].pitch;       /* output = secondary */
     r->stats.kernel_launches = 0;
     CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters) * CHAOS_MAX_STRANDS, r->stream);
@@ -1427,6 +1527,7 @@ extern "C" chaos_status chaos_render_fast(chaos_renderer *r, chaos_params *m)
     D->p_cuEventRecord(r->ev[1], r->stream);
     std::swap(r->buf[0], r->buf[1]);                               /* switch2DBuffers :180 */
     r->buffers_switched = !r->buffers_switched;
+    r->primary_alloc ^= 1u;
     /* (Starting the frame-wide compose right after the reuse pass, next to the sampling pass, was measured: no gain --
      * with host output a fast frame is the 33 MB PCIe write, 0.63 ms of 0.84, and the sampling pass is 0.1 ms.) */
     D->p_cuEventRecord(r->ev[2], r->stream);

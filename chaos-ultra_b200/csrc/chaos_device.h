@@ -15,7 +15,7 @@
 struct uint2 { unsigned int x, y; };   /* host side of the launch contract (vector_types.h is CUDA-only) */
 #endif
 
-#define CHAOS_MODULE_ABI 27u
+#define CHAOS_MODULE_ABI 28u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -37,6 +37,7 @@ struct chaos_pixel_info {
 #define CHAOS_SHORTCUT_RECURRENCE (1u << 1)  /* an orbit whose state recurs bit for bit is reported as never escaping */
 
 /* device counters, one block per renderer (zeroed by the host before each render call) */
+#define CHAOS_MAX_PEERS 8          /* ranks of one NVSwitch domain */
 #define CHAOS_COST_BUCKETS 37
 #define CHAOS_POOL_SHARDS 128   /* the orbit pool is this many independent rings (warp w uses ring w % shards) */
 /* engine 2 (render_streams.cuh): the long and finish lists of one probe -> long -> finish chain */
@@ -144,6 +145,13 @@ struct chaos_render_args {
     void *finish_list;                 /* [list_capacity] finish_item<Real>: orbits that need a last group of tested trips */
     uint32_t list_capacity;
     uint32_t probe_trips;              /* tested trips an orbit gets in the probe kernel before it goes to the long list */
+    /* Multi-GPU fast frames: the frame is cut into one slab of slab_rows pixel rows per rank (slab q = rows q * slab_rows ...),
+     * every rank keeps the records of its own slab, and the reprojection reads the previous frame's row j from the rank that
+     * owns it: in_peer[j / slab_rows], that rank's primary buffer mapped into this process (CUDA IPC; the own slab is plain
+     * local memory).  Under a zoom about a point a pixel's origin lies in its own slab except for a thin ring at the slab's
+     * edges, so almost all taps are local and the rest are peer loads over NVLink.  0 = one buffer (`in`). */
+    const chaos_pixel_info *in_peer[CHAOS_MAX_PEERS];
+    uint32_t slab_rows;
     uint32_t hot_capacity;             /* the first hot_capacity entries of long_list are the hot region (0 = none) */
     uint32_t hot_trips;                /* pass C: a pixel whose sample 0 executed at least this many trips is expected to be long */
 };

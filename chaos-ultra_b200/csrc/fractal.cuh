@@ -23,9 +23,6 @@
  *       __device__ bool wants_tested() const;
  *       __device__ void force_exact();                       // drop any exactly-equivalent fast form (may be a no-op)
  *       __device__ uint32_t skipped() const;                 // trips such a proof replaced (0 if none)
- *       template <class Vote> __device__ void run_voted(uint32_t &i, uint32_t limit, bool busy, bool &fin, Vote vote);
- *                                     // kResumable: a block of the cheap stream in warp lock step; every lane of the
- *                                     // warp calls vote(still running) after each piece, true = leave the block
  *       __device__ void save(Real &x, Real &y) const;        // kResumable: the state after the trips run so far, and
  *       __device__ void resume(Real x, Real y);              // back into an orbit start()ed at the same point (engine 2
  *                                                            // carries an orbit from its long kernel to its finish kernel)
@@ -102,11 +99,7 @@ template <class Impl, class Real> struct ClassicOrbit {
     __device__ __forceinline__ bool wants_tested() const { return false; }
     __device__ __forceinline__ void save(Real &, Real &) const {}
     __device__ __forceinline__ void resume(Real, Real) {}
-    template <class Vote> __device__ __forceinline__ void run_voted(uint32_t &i, uint32_t limit, bool busy, bool &fin, Vote vote)
-    {
-        if (busy && !fin) fin = run(i, limit, true);
-        while (!vote(false)) {}
-    }
+
     __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit, bool)
     {
         uint32_t trips = 0;

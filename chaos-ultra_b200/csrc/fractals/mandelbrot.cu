@@ -14,10 +14,6 @@ struct Fractal {
         __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit, bool tested) { return q.run(i, limit, tested); }
         __device__ __forceinline__ bool wants_tested() const { return q.wants_tested(); }
         __device__ __forceinline__ uint32_t skipped() const { return q.skipped(); }
-        template <class Vote> __device__ __forceinline__ void run_voted(uint32_t &i, uint32_t limit, bool busy, bool &fin, Vote vote)
-        {
-            q.run_voted(i, limit, busy, fin, vote);
-        }
         __device__ __forceinline__ void save(Real &x, Real &y) const { q.save(x, y); }
         __device__ __forceinline__ void resume(Real x, Real y) { q.resume(x, y); }
         /* mandelbrot.cu:22-24: points that never left report 0 */

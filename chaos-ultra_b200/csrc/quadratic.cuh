@@ -241,68 +241,6 @@ template <class Real> struct quadratic_orbit {
         if (i < limit) mode |= kReplay;             /* a tail shorter than a group needs its tests */
         return false;
     }
-    /* one untested group from a state whose squares are xx, yy: 0 = passed (i advanced), 1 = a test in it fails (state
-     * back to where the group began, wants_tested()), 2 = the state recurred: i = maxIterations is proven */
-    template <bool kS> __device__ __forceinline__ uint32_t group(uint32_t &i, Real &xx, Real &yy)
-    {
-        const Real bx = x, by = y;
-#pragma unroll kGroupUnroll
-        for (uint32_t r = 0; r < kGroup / 8u; ++r) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) advance<kS>(xx, yy);
-        }
-        if (!below<kS>(op::add(xx, yy))) {
-            x = bx; y = by;
-            mode |= kReplay;
-            return 1u;
-        }
-        i += kGroup;
-        if (mode & kDetectCycle) {
-            if (qb::same(x, sx) && qb::same(y, sy)) {
-                mode |= kPeriodic;
-                next_save = i;
-                i = max_iter;
-                return 2u;
-            }
-            if (i >= next_save) {
-                sx = x; sy = y;
-                next_save = i + max(kGroup, (i >> CHAOS_SAVE_SHIFT) & ~(kGroup - 1u));
-            }
-        }
-        return 0u;
-    }
-    /* Engine 2 (render_streams.cuh): a block of untested groups in warp lock step.  ALL lanes of the warp call this
-     * together.  A lane that holds a running orbit (`busy`, not `fin`, not waiting for tests) is live and runs one group
-     * per round; after every round vote(live) -- evaluated by every lane, so it may hold warp votes -- says whether the
-     * warp leaves the block early.  The squares stay in registers from group to group, so a round costs the group's
-     * arithmetic plus the vote, and a lane that drops out (test failed, recurrence proven, limit reached) costs the
-     * warp at most one group of its slot, not the rest of a long block.  Orbits that may not defer their tests run the
-     * group's trips tested.  fin: the loop is over (the test failed at trip i, or i = maxIterations). */
-    template <class Vote> __device__ __forceinline__ void run_voted(uint32_t &i, uint32_t limit, bool busy, bool &fin, Vote vote)
-    {
-        const bool scaled = qb::kCanScale && (mode & kScaled);
-        bool live = busy && !fin && !(mode & kReplay);
-        Real xx = (Real)0, yy = (Real)0;
-        if (live && (mode & kDeferTest)) { xx = op::mul(x, x); yy = op::mul(y, y); }
-        for (;;) {
-            if (live) {
-                if (!(mode & kDeferTest)) {
-                    const uint32_t stop = min(i + kGroup, limit);
-                    const bool e = scaled ? run_tested<true>(i, stop) : run_tested<false>(i, stop);
-                    if (e || i >= max_iter) { fin = true; live = false; }
-                    else if (i >= limit) live = false;
-                } else if (i + kGroup <= limit) {
-                    const uint32_t st = scaled ? group<true>(i, xx, yy) : group<false>(i, xx, yy);
-                    if (st) { live = false; fin = st == 2u; }
-                } else {
-                    if (i < limit) mode |= kReplay;     /* a tail shorter than a group needs its tests */
-                    live = false;
-                }
-            }
-            if (vote(live)) break;
-        }
-        fin = fin || (busy && i >= max_iter);
-    }
     /* One phase of the loop, while i < limit.  `tested` must be uniform over the warp: all lanes then execute ONE
      * instruction stream.  tested = true: every trip with its test (the first trips of an orbit, the replay of a
      * failed group, tails).  tested = false: untested groups; an orbit whose group fails goes back to the state

@@ -341,15 +341,22 @@ __device__ __forceinline__ void warp_origin<float>(const chaos_render_args &a, u
     oy = __fmaf_rn(fh, -rely, fh);
 }
 
+/* row j of the previous frame: one buffer, or (multi-GPU fast frames) the primary buffer of the rank whose slab holds it */
+static __device__ __forceinline__ const char *previous_row(const chaos_render_args &a, uint32_t j)
+{
+    const chaos_pixel_info *base = a.in;
+    if (a.slab_rows) base = a.in_peer[min(j / a.slab_rows, a.part_count - 1u)];
+    return (const char *)base + (size_t)j * a.in_pitch;
+}
+
 /* 4-tap filter of value and weight at (ox,oy) (:259-302); only value/weight are read, as one
  * 64-bit load per tap */
-static __device__ __forceinline__ void gather_bilinear(const chaos_pixel_info *in, uint64_t pitch, float ox, float oy,
-                                                       float &value, float &weight)
+static __device__ __forceinline__ void gather_bilinear(const chaos_render_args &a, float ox, float oy, float &value, float &weight)
 {
     uint32_t i = __float2uint_rz(floorf(ox)), j = __float2uint_rz(floorf(oy));
     float al = __fsub_rn(ox, __uint2float_rn(i)), be = __fsub_rn(oy, __uint2float_rn(j));
-    const char *row0 = (const char *)in + (size_t)j * pitch;
-    const char *row1 = row0 + pitch;
+    const char *row0 = previous_row(a, j);
+    const char *row1 = previous_row(a, j + 1u);
     float2 t00 = __ldg(reinterpret_cast<const float2 *>(row0 + (size_t)i * 16u));
     float2 t10 = __ldg(reinterpret_cast<const float2 *>(row0 + (size_t)(i + 1u) * 16u));
     float2 t01 = __ldg(reinterpret_cast<const float2 *>(row1 + (size_t)i * 16u));
@@ -393,7 +400,7 @@ static __device__ __forceinline__ void advanced_tile(const chaos_render_args &a,
         warp_origin<Real>(a, px, py, ox, oy);
         int oix = __float2int_rz(roundf(ox)), oiy = __float2int_rz(roundf(oy));
         if (!(oix < 2 || (uint32_t)oix >= a.width - 2u || oiy < 2 || (uint32_t)oiy >= a.height - 2u)) {
-            gather_bilinear(a.in, a.in_pitch, ox, oy, rv, rw);
+            gather_bilinear(a, ox, oy, rv, rw);
             reusing = !((double)rw < 0.1);
         }
     }
@@ -546,8 +553,8 @@ static __device__ void advanced_reuse_pass(const chaos_render_args &a)
             be[r] = __fsub_rn(oy, __uint2float_rn(j));
             t00[r] = t10[r] = t01[r] = t11[r] = make_float2(0.f, 0.f);
             if (tap[r]) {
-                const char *row0 = (const char *)a.in + (size_t)j * a.in_pitch + (size_t)i * 16u;
-                const char *row1 = row0 + a.in_pitch;
+                const char *row0 = previous_row(a, j) + (size_t)i * 16u;
+                const char *row1 = previous_row(a, j + 1u) + (size_t)i * 16u;
                 t00[r] = __ldg(reinterpret_cast<const float2 *>(row0));
                 t10[r] = __ldg(reinterpret_cast<const float2 *>(row0 + 16));
                 t01[r] = __ldg(reinterpret_cast<const float2 *>(row1));

@@ -364,25 +364,17 @@ static __device__ void stream_long(const chaos_render_args &a)
     CHAOS_LS(lane_stats ls; ls.init();)
     for (;;) {
         CHAOS_LS(ls.before(busy, fin || stall, false, false, dry, it);)
-        /* one block: up to nb trips per running orbit, group by group in lock step.  Lanes that are out (empty, over,
-         * stalled) run up the warp's debt with every group; at max_debt the block ends early and the warp refills. */
-        {
+        if (busy && !fin && !stall) {
             const uint32_t lim = min(it + nb, max_iter);
-            bool f = fin;
-            o.run_voted(it, lim, busy && !stall, f, [&](bool live) {
-                const uint32_t running_now = __ballot_sync(CHAOS_FULL_MASK, live);
-                if (!running_now) return true;
-                if (dry) return false;
-                debt += (32u - (uint32_t)__popc(running_now)) * CHAOS_GROUP;
-                return debt >= max_debt;
-            });
-            fin = f;
-            stall = busy && !fin && o.wants_tested();
+            const bool e = o.run(it, lim, false);
+            fin = e || it >= max_iter;
+            stall = !fin && o.wants_tested();
         }
         CHAOS_LS(ls.after((fin ? it - o.skipped() : it) - ls.it0);)
         const uint32_t running = __ballot_sync(CHAOS_FULL_MASK, busy && !fin && !stall);
         if (running) {
             if (!dry) {
+                debt += (32u - (uint32_t)__popc(running)) * nb;
                 if (debt < max_debt) continue;
             } else {
                 /* nothing to refill from but the pool: a look every few blocks while lanes are out -- the orbits still running

@@ -156,6 +156,22 @@ def share_frame_native(renderer, rank: int, world: int, dist) -> bool:
     return True
 
 
+def slab_rows(height: int, world: int) -> int:
+    """rows of one rank's slab: the frame cut into `world` contiguous slabs whose height is a multiple of the 4-row vote tile"""
+    return ((height + world - 1) // world + 3) // 4 * 4
+
+
+def share_records(renderer, rank: int, world: int, dist) -> None:
+    """Multi-GPU fast frames: every rank exports its two record buffers and opens every other rank's pair
+    (chaos_ipc_export_records / chaos_ipc_open_records).  Collective; raises where a mapping is refused."""
+    mine = renderer.exportRecordHandles()
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    for q, handles in enumerate(everyone):
+        if q != rank:
+            renderer.openRecordHandles(q, handles)
+
+
 def share_frame(renderer, rank: int, world: int, dist):
     """Map rank 0's device frame into the other ranks (CUDA IPC) and make it their compose target.
     Returns an object that must stay alive while the target is in use (close() unmaps), or None if this cannot be

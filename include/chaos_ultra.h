@@ -121,6 +121,11 @@ CHAOS_API chaos_status chaos_provider_create(const char *kernels_dir, int device
 CHAOS_API chaos_status chaos_provider_destroy(chaos_provider *p);
 /* getAvailableFractals(): the registered display names, independent of which files exist. */
 CHAOS_API chaos_status chaos_list_fractals(chaos_provider *p, const char **names, uint32_t capacity, uint32_t *count);
+/* A fractal author's own module: <kernels_dir>/<file_stem>.cubin becomes available under `fractal_name` -- what adding a
+ * Module*.java and registering it does in the reference (CudaFractalRendererProvider.java:19-31).  The module is built from
+ * a file written for the reference's contract by `python chaos-ultra_b200/build.py compat <file.cu>` (csrc/compat/) or from a
+ * `struct Fractal` file; it has no defaults, and its constants are written with chaos_write_constant. */
+CHAOS_API chaos_status chaos_register_module(chaos_provider *p, const char *fractal_name, const char *file_stem);
 /* getRenderer(name, forceReload) :47-66 -- at most one active renderer per provider; same name and
  * !force_reload returns the active one; otherwise the old one is closed (module unloaded) and the
  * module file is read again. */
@@ -193,6 +198,14 @@ CHAOS_API chaos_status chaos_ipc_open_frame(chaos_renderer *r, const chaos_ipc_h
  * shared-memory segment all ranks have mapped).  The library pins and maps it (cuMemHostRegister) for as long as it is
  * the target; NULL, chaos_free_resources and chaos_close release it. */
 CHAOS_API chaos_status chaos_set_host_target(chaos_renderer *r, void *host_frame, size_t bytes);
+/* Multi-GPU fast frames (zoom sequences).  The frame is cut into one slab of rows per rank: chaos_set_partition(rank, world,
+ * band_rows) with band_rows * world >= height.  Every rank keeps the records of its slab and exports its two record buffers;
+ * every rank opens every other rank's pair.  chaos_render_fast then reprojects for real: a tap into another slab is a peer
+ * load from the owner's primary buffer over NVLink.  Needs a frame barrier (a rank must not start frame f + 1 before every
+ * rank has finished frame f) and the same sequence of render calls on all ranks.  Without the peers' buffers a fast frame
+ * of a partitioned renderer renders its bands afresh (see chaos_set_partition). */
+CHAOS_API chaos_status chaos_ipc_export_records(chaos_renderer *r, chaos_ipc_handle out[2]);
+CHAOS_API chaos_status chaos_ipc_open_records(chaos_renderer *r, uint32_t peer_rank, const chaos_ipc_handle in[2]);
 /* `shm_block`: 64 zero-initialised bytes of host memory shared by the `world` processes of the job (NULL = no barrier).
  * Every later render call announces its frame there when its own kernels are done and returns when all ranks have
  * announced theirs -- on return the target frame holds every rank's bands.  Waits are bounded (10 s -> CHAOS_ERR_CUDA). */

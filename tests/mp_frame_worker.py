@@ -25,6 +25,10 @@ def main():
     dev = int(os.environ["LOCAL_RANK"]) if torch.cuda.device_count() >= world else 0
     dist.init_process_group("gloo")
     mode = sys.argv[1]
+    if mode.startswith("zoom"):
+        zoom_sequence(cu, part, dist, rank, world, dev, mode)
+        dist.destroy_process_group()
+        return
     case = dict(cases.MAIN_CASES[2], W=1531, H=1077, image=cases.seg(-0.5, 0.0, 2.0, 1531, 1077), maxIter=2100)   # ragged, several samples
     W, H, band = case["W"], case["H"], 32
     with cu.CudaFractalRendererProvider(device=dev) as prov:
@@ -62,6 +66,57 @@ def main():
             r.setOutputTarget(0)
         job.close(dist)
     dist.destroy_process_group()
+
+
+def zoom_sequence(cu, part, dist, rank, world, dev, mode):
+    """multi-GPU fast frames: one slab of rows per rank, previous-frame taps into other slabs are peer loads; every frame's
+    records (own slab) and RGBA (whole frame, rank 0) must equal those of the same sequence rendered whole by one renderer"""
+    import cases
+    import helpers
+    W, H, focus = 643, 362, (200, 301)                     # ragged; the focus near the bottom: origins cross slab edges in both directions
+    flags = cases.A | cases.FOV | cases.REUSE | cases.ZOOMING | (cases.ZOOM_IN if mode != "zoom_out" else 0)
+    base = dict(name="mpzoom", fractal="mandelbrot", W=W, H=H, maxIter=600, maxSS=2.0, flags=flags, double=(mode == "zoom_f64"),
+                julia_c=(0.0, 0.0), amplifier=10, focus=focus)
+    segs = [cases.seg(-0.748, 0.1, 2.0 if not base["double"] else 1.0e-4, W, H)]
+    for _ in range(7):
+        segs.append(cases.zoom_at(segs[-1], W, H, focus, mode != "zoom_out"))
+    with cu.CudaFractalRendererProvider(device=dev) as prov:
+        r = prov.getRenderer("mandelbrot", False)
+        r.initializeRendering(W, H, None, cu.OUTPUT_DEVICE)
+        whole = []
+        r.renderQuality(helpers.model_for(cu, dict(base, image=segs[0])))
+        whole.append((r.downloadRecords(), r.outputRGBA().copy(), r.stats().pixel_iterations))
+        for sg in segs[1:]:
+            r.renderFast(helpers.model_for(cu, dict(base, image=sg)))
+            whole.append((r.downloadRecords(), r.outputRGBA().copy(), r.stats().pixel_iterations))
+        assert whole[3][0]["isReused"].mean() > 0.8
+        # the same sequence on `world` ranks
+        r.freeRenderingResources()
+        r.initializeRendering(W, H, None, cu.OUTPUT_DEVICE)
+        slab = part.slab_rows(H, world)
+        r.setPartition(rank, world, slab)
+        job = part.JobSharedMemory(rank, world, H, W, dist)
+        job.attach(r, host_target=True, barrier=True)
+        part.share_records(r, rank, world, dist)
+        r0, r1 = rank * slab, min(H, (rank + 1) * slab)
+        import torch
+        for f, sg in enumerate(segs):
+            m = helpers.model_for(cu, dict(base, image=sg))
+            (r.renderQuality if f == 0 else r.renderFast)(m)
+            st = r.stats()
+            if f:
+                assert st.reuse_ms > 0, "frame %d was not reprojected" % f
+            got = r.downloadRecords()
+            helpers.assert_records_equal(got[r0:r1], whole[f][0][r0:r1], "rank %d frame %d rows %d..%d" % (rank, f, r0, r1))
+            t = torch.tensor([st.pixel_iterations], dtype=torch.int64)
+            dist.all_reduce(t)
+            assert int(t.item()) == whole[f][2], "frame %d: pixel-iterations of the slabs %d != whole %d" % (f, int(t.item()), whole[f][2])
+            if rank == 0:
+                assert np.array_equal(job.frame, whole[f][1]), "frame %d assembled from %d slabs differs" % (f, world)
+            dist.barrier()
+        r.setFrameBarrier(0, 0)
+        r.setHostTarget(0, 0)
+        job.close(dist)
 
 
 if __name__ == "__main__":

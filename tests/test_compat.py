@@ -149,3 +149,47 @@ def test_unmodified_reference_module_in_a_fast_frame_and_debug(cu, compat_provid
     helpers.assert_records_equal(got, want, "compat test module, fast frame")
     r.launchDebugKernel()
     assert "hello from test" in capfd.readouterr().out
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _have_nvcc(), reason="nvcc not available")
+def test_an_authors_module_registers_and_renders(cu, tmp_path):
+    """the burning ship written against the reference's contract: built unmodified, registered under its own name, rendered;
+    checked against the same loop in numpy (the author's expressions leave contraction to nvcc, so a handful of boundary
+    pixels may differ by a trip: that freedom is the module's, not the backend's)"""
+    build = importlib.import_module("chaos-ultra_b200.build")
+    (tmp_path / "fractals").mkdir()
+    src = tmp_path / "fractals" / "burning_ship.cu"
+    src.write_text(AUTHOR_MODULE)
+    kd = tmp_path / "kernels"
+    build.build_compat_module(src, kd, force=True)
+    W, H, max_iter = 160, 120, 60
+    with cu.CudaFractalRendererProvider(kernels_dir=kd) as prov:
+        with pytest.raises(cu.IllegalArgumentException, match="Unknown fractal"):
+            prov.getRenderer("burning ship", False)
+        prov.registerModule("burning ship", "burning_ship")
+        assert "burning ship" in prov.getAvailableFractals() and len(prov.getAvailableFractals()) == 8
+        with pytest.raises(cu.IllegalArgumentException, match="already registered"):
+            prov.registerModule("mandelbrot", "burning_ship")
+        r = prov.getRenderer("burning ship", False)
+        r.writeToConstantMemory("power_shift", np.array([0.0, 0.0], dtype=np.float64).tobytes())
+        r.initializeRendering(W, H)
+        m = cu.RenderingModel(canvasWidth=W, canvasHeight=H)
+        m.setPlaneSegmentFromCenter(-0.5, -0.5, 3.0)
+        m.maxIterations, m.maxSuperSampling, m.useAdaptiveSuperSampling, m.forcePrecision = max_iter, 1.0, False, 2
+        r.renderQuality(m)
+        got = r.downloadRecords()["value"].astype(np.int64)
+        lbx, lby, rtx, rty = m.planeSegment
+        xs = lbx + (rtx - lbx) / W * np.arange(W)
+        ys = rty - (rty - lby) / H * np.arange(H)
+        cx, cy = np.meshgrid(xs, ys)
+        zx, zy, it = np.zeros_like(cx), np.zeros_like(cy), np.zeros(cx.shape, dtype=np.int64)
+        for _ in range(max_iter):
+            live = zx * zx + zy * zy < 4
+            xn = zx * zx - zy * zy + cx
+            zy = np.where(live, np.abs(2 * zx * zy) + cy, zy)
+            zx = np.where(live, xn, zx)
+            it += live
+        assert (got != it).mean() < 0.01 and np.abs(got - it).max() <= 2
+        assert r.outputRGBA().shape == (H, W)
+        r.launchDebugKernel()

@@ -28,3 +28,15 @@ def test_frame_assembled_by_several_processes_equals_the_whole_frame(mode, world
            "--master-port", str(_free_port()), str(ROOT / "tests" / "mp_frame_worker.py"), mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["zoom", "zoom_f64", "zoom_out"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_zoom_sequence_on_several_ranks_equals_the_whole_sequence(mode, world):
+    """multi-GPU fast frames: one slab per rank, taps into other slabs are peer loads from the owner's record buffer"""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(ROOT / "tests" / "mp_frame_worker.py"), mode]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
