@@ -116,6 +116,7 @@ class _Stats(C.Structure):
         ("pixel_iterations", C.c_uint64),
         ("samples", C.c_uint64),
         ("launches_total", C.c_uint64),
+        ("foreign_orbits", C.c_uint64),
         ("skipped_iterations", C.c_uint64),
     ]
 
@@ -298,6 +299,7 @@ class RenderStats:
     launches_total: int
     skipped_iterations: int = 0   # part of pixel_iterations proven (exact recurrence) instead of executed
     frame_ms: float = 0.0         # device time of the whole frame (render kernels + compose)
+    foreign_orbits: int = 0       # several GPUs: orbits of this rank's tiles that other ranks iterated (tile stealing)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -457,13 +459,13 @@ class CudaFractalRenderer:
         _check(self._lib, self._lib.chaos_ipc_open_frame(self._h, C.cast(buf, _VP)))
 
     def exportRecordHandles(self) -> bytes:
-        """128 bytes: handles of this renderer's two record buffers (multi-GPU fast frames)."""
-        buf = C.create_string_buffer(128)
+        """192 bytes: handles of this renderer's two record buffers and of its scheduler counters (multi-GPU fast frames, tile stealing)."""
+        buf = C.create_string_buffer(192)
         _check(self._lib, self._lib.chaos_ipc_export_records(self._h, C.cast(buf, _VP)))
         return buf.raw
 
     def openRecordHandles(self, peer_rank: int, handles: bytes) -> None:
-        buf = C.create_string_buffer(bytes(handles), 128)
+        buf = C.create_string_buffer(bytes(handles), 192)
         _check(self._lib, self._lib.chaos_ipc_open_records(self._h, int(peer_rank), C.cast(buf, _VP)))
 
     def setHostTarget(self, address: int, nbytes: int) -> None:
@@ -485,7 +487,7 @@ class CudaFractalRenderer:
         s = _Stats()
         s.struct_size = C.sizeof(_Stats)
         _check(self._lib, self._lib.chaos_get_stats(self._h, C.byref(s)))
-        return RenderStats(s.kernel_launches, s.render_ms, s.compose_ms, s.reuse_ms, s.pixel_iterations, s.samples, s.launches_total, s.skipped_iterations, s.frame_ms)
+        return RenderStats(s.kernel_launches, s.render_ms, s.compose_ms, s.reuse_ms, s.pixel_iterations, s.samples, s.launches_total, s.skipped_iterations, s.frame_ms, s.foreign_orbits)
 
     def __enter__(self):
         return self

@@ -334,9 +334,12 @@ struct chaos_renderer {
     CUdeviceptr long_list = 0, finish_list = 0;    /* allocated by the first engine-2 frame of a frame size */
     size_t list_capacity = 0;                      /* entries */
     uint32_t probe_trips = 64;
-    uint32_t hot_first = 1;                        /* pass C: orbits expected to be long are started first (CHAOS_HOT_FIRST=0: list order) */
+    uint32_t long_occ[3] = {2, 4, 8};             /* chaos_render_args::occ_orbits_per_lane (CHAOS_LONG_OCC=a,b,c; 0,0,0 = always the full grid) */
+    uint32_t hot_first = 3;                        /* orbits expected to be long are started first: bit 0 pass C (by sample 0's cost), bit 1 the
+                                                    * other passes (survivors of tiles next to the boundary); CHAOS_HOT_FIRST=0: list order */
     CUfunction k_classify = nullptr, k_order = nullptr;            /* between the two passes of engine 1 */
     CUfunction k_replay = nullptr;                                 /* pass D */
+    CUfunction k_export_all = nullptr;                             /* between order and pass B: few tiles left -> all exported */
     chaos_export exp_buf = {0, nullptr, nullptr, nullptr, nullptr, nullptr};
     CUdeviceptr late_tiles = 0;    /* one bit per vote tile of the frame, see chaos_render_args::late_tiles */   /* pass B -> pass C -> pass D (device memory) */
     uint32_t export_enabled = 1;
@@ -359,6 +362,10 @@ struct chaos_renderer {
     uint32_t primary_alloc = 0;
     /* multi-GPU fast frames: the other ranks' two record buffers mapped into this process (chaos_ipc_open_records) */
     CUdeviceptr peer_records[CHAOS_MAX_PEERS][2] = {};
+    CUdeviceptr peer_counters[CHAOS_MAX_PEERS] = {};   /* their scheduler counters: the tile cursor other ranks steal from */
+    CUfunction k_wait_foreign = nullptr;
+    uint32_t frame_seq = 0;                            /* quality frames rendered: what a cursor's frame_seq must say before it is stolen from */
+    uint32_t steal = 1;                                /* CHAOS_STEAL=0: every rank renders exactly its own tiles */
     bool buffers_switched = false;
     bool primary_dirty = true;
     bool have_last = false;        /* lastRendering != null */
@@ -557,7 +564,7 @@ static chaos_status load_module(chaos_renderer *r)
         {"fractalRenderUnderSampled", &r->k_undersampled}, {"compose", &r->k_compose}, {"debug", &r->k_debug},
 
         {"fractalRenderMainFloatSync", &r->k_main_f_sync}, {"fractalRenderMainDoubleSync", &r->k_main_d_sync},
-        {"chaosClassifyTiles", &r->k_classify}, {"chaosOrderTiles", &r->k_order}, {"chaosReplayExported", &r->k_replay},
+        {"chaosClassifyTiles", &r->k_classify}, {"chaosOrderTiles", &r->k_order}, {"chaosReplayExported", &r->k_replay}, {"chaosExportAll", &r->k_export_all}, {"chaosWaitForeign", &r->k_wait_foreign},
         {"chaosReusePassFloat", &r->k_reuse_f}, {"chaosReusePassDouble", &r->k_reuse_d},
         {"chaosProbeFloat", &r->k_probe[0]}, {"chaosProbeDouble", &r->k_probe[1]}, {"chaosLongFloat", &r->k_long[0]},
         {"chaosLongDouble", &r->k_long[1]}, {"chaosFinishFloat", &r->k_finish[0]}, {"chaosFinishDouble", &r->k_finish[1]},
@@ -636,8 +643,12 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     /* debugging knobs (not part of the reference's interface): engine 0 is the differential check of engine 1 */
     const char *eng = getenv("CHAOS_ENGINE");
     if (eng) r->engine = (uint32_t)std::min(std::max(atoi(eng), 0), 3);
+    const char *stl = getenv("CHAOS_STEAL");
+    if (stl) r->steal = (uint32_t)atoi(stl) ? 1u : 0u;
+    const char *lo = getenv("CHAOS_LONG_OCC");
+    if (lo) { unsigned x = 0, y = 0, z = 0; if (sscanf(lo, "%u,%u,%u", &x, &y, &z) == 3) { r->long_occ[0] = x; r->long_occ[1] = y; r->long_occ[2] = z; } }
     const char *hf = getenv("CHAOS_HOT_FIRST");
-    if (hf) r->hot_first = (uint32_t)atoi(hf) ? 1u : 0u;
+    if (hf) r->hot_first = (uint32_t)atoi(hf) & 3u;
     const char *prb = getenv("CHAOS_PROBE_TRIPS");
     if (prb) r->probe_trips = (uint32_t)std::max(atoi(prb), 8);
     const char *sb = getenv("CHAOS_SYNC_BELOW");
@@ -774,9 +785,11 @@ static chaos_status launch_stream_chain(chaos_renderer *r, chaos_render_args &b,
 
 static void release_peer_records(chaos_renderer *r)
 {
-    for (uint32_t q = 0; q < CHAOS_MAX_PEERS; ++q)
+    for (uint32_t q = 0; q < CHAOS_MAX_PEERS; ++q) {
         for (int i = 0; i < 2; ++i)
             if (r->peer_records[q][i]) { D->p_cuIpcCloseMemHandle(r->peer_records[q][i]); r->peer_records[q][i] = 0; }
+        if (r->peer_counters[q]) { D->p_cuIpcCloseMemHandle(r->peer_counters[q]); r->peer_counters[q] = 0; }
+    }
 }
 
 static void release_targets(chaos_renderer *r)
@@ -943,21 +956,21 @@ extern "C" chaos_status chaos_ipc_open_frame(chaos_renderer *r, const chaos_ipc_
     return CHAOS_OK;
 }
 
-extern "C" chaos_status chaos_ipc_export_records(chaos_renderer *r, chaos_ipc_handle out[2])
+extern "C" chaos_status chaos_ipc_export_records(chaos_renderer *r, chaos_ipc_handle out[3])
 {
     chaos_status st = check_renderer(r);
     if (st != CHAOS_OK) return st;
     if (r->state != CHAOS_STATE_READY_TO_RENDER) return fail(CHAOS_ERR_ILLEGAL_STATE, "Renderer has to be initialized first");
     if (!out) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "out is NULL");
     ctx_guard g(r->provider);
-    for (int i = 0; i < 2; ++i) {
-        CUresult e = D->p_cuIpcGetMemHandle((CUipcMemHandle *)&out[i], r->alloc[i]);
+    for (int i = 0; i < 3; ++i) {
+        CUresult e = D->p_cuIpcGetMemHandle((CUipcMemHandle *)&out[i], i < 2 ? r->alloc[i] : r->counters);
         if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuIpcGetMemHandle failed: %s", cu_err_name(e));
     }
     return CHAOS_OK;
 }
 
-extern "C" chaos_status chaos_ipc_open_records(chaos_renderer *r, uint32_t peer_rank, const chaos_ipc_handle in[2])
+extern "C" chaos_status chaos_ipc_open_records(chaos_renderer *r, uint32_t peer_rank, const chaos_ipc_handle in[3])
 {
     chaos_status st = check_renderer(r);
     if (st != CHAOS_OK) return st;
@@ -965,12 +978,13 @@ extern "C" chaos_status chaos_ipc_open_records(chaos_renderer *r, uint32_t peer_
     if (!in || peer_rank >= CHAOS_MAX_PEERS) return fail(CHAOS_ERR_ILLEGAL_ARGUMENT, "peer rank %u out of range (0..%d)", peer_rank, CHAOS_MAX_PEERS - 1);
     ctx_guard g(r->provider);
     D->p_cuStreamSynchronize(r->stream);
-    for (int i = 0; i < 2; ++i) {
-        if (r->peer_records[peer_rank][i]) { D->p_cuIpcCloseMemHandle(r->peer_records[peer_rank][i]); r->peer_records[peer_rank][i] = 0; }
+    for (int i = 0; i < 3; ++i) {
+        CUdeviceptr *slot = i < 2 ? &r->peer_records[peer_rank][i] : &r->peer_counters[peer_rank];
+        if (*slot) { D->p_cuIpcCloseMemHandle(*slot); *slot = 0; }
         CUipcMemHandle h;
         memcpy(&h, &in[i], sizeof h);
-        CUresult e = D->p_cuIpcOpenMemHandle(&r->peer_records[peer_rank][i], h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
-        if (e != CUDA_SUCCESS) { r->peer_records[peer_rank][i] = 0; return fail(CHAOS_ERR_CUDA, "cuIpcOpenMemHandle(records of rank %u) failed: %s", peer_rank, cu_err_name(e)); }
+        CUresult e = D->p_cuIpcOpenMemHandle(slot, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
+        if (e != CUDA_SUCCESS) { *slot = 0; return fail(CHAOS_ERR_CUDA, "cuIpcOpenMemHandle(%s of rank %u) failed: %s", i < 2 ? "records" : "counters", peer_rank, cu_err_name(e)); }
     }
     return CHAOS_OK;
 }
@@ -1173,6 +1187,8 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
     a->shortcuts = r->shortcuts;
     a->sched_idle_lanes_indep = r->sched_idle_indep;
     a->sched_idle_lanes_rounds = r->sched_idle_rounds;
+    a->sm_count = (uint32_t)r->provider->sm_count;
+    for (int i = 0; i < 3; ++i) a->occ_orbits_per_lane[i] = r->long_occ[i];
 
 }
 
@@ -1231,6 +1247,7 @@ static chaos_status finish_frame(chaos_renderer *r)
     D->p_cuEventElapsedTime(&r->stats.frame_ms, r->ev[0], r->ev[3]);
     r->stats.reuse_ms = 0.f;
     r->stats.pixel_iterations = r->stats.samples = r->stats.skipped_iterations = 0;
+    r->stats.foreign_orbits = r->counters_host[0].foreign_done;
     for (uint32_t s = 0; s < CHAOS_MAX_STRANDS; ++s)
         if (r->counters_host[s].abort) {     /* a kernel gave up waiting in the orbit pool (bounded spins): the records are not to be trusted */
             r->primary_dirty = true;
@@ -1282,6 +1299,8 @@ static chaos_precision frame_precision(const chaos_renderer *r, chaos_params *m)
     return p;
 }
 
+static bool peers_open(const chaos_renderer *r);
+
 static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
 {
     chaos_status st = set_module_constants(r, m);
@@ -1321,11 +1340,30 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
             a.pool = (unsigned char *)ensure_pool(r, 0);
             a.pool_capacity = r->pool_capacity; a.pool_min_lanes = r->pool_min_lanes; a.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
             a.phase = 0u;
+            if (r->hot_first & 2u) a.hot_capacity = a.list_capacity;
             st = launch_stream_chain(r, a, p, r->stream);
         } else if (S0 <= 1u) {
             a.pool = (unsigned char *)ensure_pool(r, 0);
             a.pool_capacity = r->pool_capacity; a.pool_min_lanes = r->pool_min_lanes; a.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
+            /* several GPUs: a rank whose own tiles are handed out goes on with the other ranks' (chaos_render_args::steal_world) */
+            const bool stealing = r->steal && peers_open(r);
+            if (stealing) {
+                a.steal_world = r->part_count; a.steal_rank = r->part_index; a.frame_seq = ++r->frame_seq;
+                for (uint32_t q = 0; q < r->part_count; ++q) {
+                    a.steal_n_tiles[q] = owned_tile_rows(a.tile_rows, a.band_tile_rows, q, r->part_count) * a.tiles_x;
+                    a.steal_counters[q] = (chaos_counters *)(q == r->part_index ? r->counters : r->peer_counters[q]);
+                    a.steal_out[q] = (chaos_pixel_info *)(q == r->part_index ? r->buf[0].ptr : r->peer_records[q][0]);   /* a quality frame goes to the first buffer */
+                }
+                const uint32_t bands = (r->height + r->band_rows - 1u) / r->band_rows;
+                for (uint32_t bnd = r->part_index; bnd < bands; bnd += r->part_count)
+                    a.own_pixels += (unsigned long long)std::min(r->band_rows, r->height - bnd * r->band_rows) * r->width;
+            }
             st = launch(r, dbl ? r->k_main_d : r->k_main_f, dbl ? r->blocks_main_d : r->blocks_main_f, 256, 0, &a, r->stream);
+            if (stealing && st == CHAOS_OK) {
+                void *params[1] = {&a};
+                CUresult le = D->p_cuLaunchKernel(r->k_wait_foreign, 1, 1, 1, 32, 1, 1, 0, r->stream, params, nullptr);
+                if (le != CUDA_SUCCESS) st = fail(CHAOS_ERR_CUDA, "Error just after launching a kernel:%s", cu_err_name(le));
+            }
         } else {
             /* pass A: sample 0 of every pixel; classify + order: expected-longest tiles first; pass B: the other rounds,
              * except those of tiles set to use their whole budget -> pass C (independent orbits) + pass D (their decisions).
@@ -1377,6 +1415,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     const int small_grid = (int)std::min<uint64_t>((b.n_tiles + 255u) / 256u, (uint64_t)r->provider->sm_count * 4u);
                     const int tile_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);   /* one warp per tile */
                     b.phase = 1u;
+                    if (streams && (r->hot_first & 2u)) b.hot_capacity = b.list_capacity;      /* the two ends cannot meet: the list holds every orbit of pass A */
                     st = streams ? launch_stream_chain(r, b, p, q) : launch(r, r->k_pass_a[p], r->blocks_pass_a[p], (int)r->pass_threads, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_classify, tile_grid, 256, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &b, q);
@@ -1387,6 +1426,10 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     if (trace_path) {
                         if (!r->warp_trace && D->p_cuMemAlloc(&r->warp_trace, trace_bytes) != CUDA_SUCCESS) r->warp_trace = 0;
                         if (r->warp_trace) { D->p_cuMemsetD8Async(r->warp_trace, 0, trace_bytes, q); b.warp_trace = (unsigned long long *)r->warp_trace; }
+                    }
+                    if (exporting && st == CHAOS_OK) {
+                        b.export_all_done = 1u;
+                        st = launch(r, r->k_export_all, small_grid, 256, 0, &b, q);
                     }
                     if (st == CHAOS_OK) st = launch(r, r->k_pass_b[p], r->blocks_pass_b[p], (int)r->pass_threads, r->refill_smem, &b, q);
                     if (trace_path && r->warp_trace && st == CHAOS_OK) {
@@ -1402,7 +1445,8 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                 D->p_cuEventRecord(r->strand_ev_b[s], q);
                 if (exporting && b.n_tiles && st == CHAOS_OK) {
                     b.phase = 3u;
-                    if (streams && r->hot_first) { b.hot_capacity = b.list_capacity / 4u; b.hot_trips = std::max(b.max_iter / 4u, 64u); }
+                    b.hot_capacity = 0u;
+                    if (streams && (r->hot_first & 1u)) { b.hot_capacity = b.list_capacity / 4u; b.hot_trips = std::max(b.max_iter / 4u, 64u); }
                     st = streams ? launch_stream_chain(r, b, p, q) : launch(r, r->k_pass_c[p], r->blocks_pass_c[p], (int)r->pass_threads, 0, &b, q);
                     const int replay_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);
                     if (st == CHAOS_OK) st = launch(r, r->k_replay, replay_grid, 256, 0, &b, q);
@@ -1449,6 +1493,15 @@ extern "C" chaos_status chaos_render_quality(chaos_renderer *r, chaos_params *m)
     if (st != CHAOS_OK) return st;
     ctx_guard g(r->provider);
     return render_quality_locked(r, m);
+}
+
+/* every other rank's record buffers and counters are mapped, and the ranks run in step */
+static bool peers_open(const chaos_renderer *r)
+{
+    if (r->part_count <= 1u || r->part_count > CHAOS_MAX_PEERS || !r->barrier) return false;
+    for (uint32_t q = 0; q < r->part_count; ++q)
+        if (q != r->part_index && !(r->peer_records[q][0] && r->peer_records[q][1] && r->peer_counters[q])) return false;
+    return true;
 }
 
 /* multi-GPU fast frames are possible when the partition is one slab per rank, every other rank's record buffers are mapped

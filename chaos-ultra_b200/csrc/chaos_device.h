@@ -15,7 +15,7 @@
 struct uint2 { unsigned int x, y; };   /* host side of the launch contract (vector_types.h is CUDA-only) */
 #endif
 
-#define CHAOS_MODULE_ABI 28u
+#define CHAOS_MODULE_ABI 31u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -67,6 +67,11 @@ struct chaos_counters {
      * escape loop by what the lane was doing, [pass A/B/C/main][tested, untested][CHAOS_LS_*] */
     unsigned long long lane_stats[4][2][8];
     chaos_stream_ctl stream[2];         /* engine 2: [0] one-sample frame or pass A, [1] pass C */
+    /* cross-GPU tile stealing (one-sample frames, render_refill.cuh): this rank's tile cursor (next_tile) is open to the
+     * other ranks once frame_seq says the counters belong to the current frame; orbits finished here / by other ranks */
+    unsigned int frame_seq;
+    unsigned int pad1;
+    unsigned long long own_done, foreign_done;
 };
 #define CHAOS_LS_CAPACITY 0   /* 32 x trips the warp spent in the block */
 #define CHAOS_LS_USEFUL 1     /* trips the lanes advanced */
@@ -133,6 +138,7 @@ struct chaos_render_args {
     uint32_t pool_capacity;            /* entries of all CHAOS_POOL_SHARDS rings together; a ring holds >= 32 x its warps */
     uint32_t pool_min_lanes;
     uint32_t export_all_below;         /* pass B exports every tile it gets when chaosClassifyTiles left it at most this many */
+    uint32_t export_all_done;          /* 1 = chaosExportAll ran before pass B and took that case over */
     /* fast frame, pass R: the pixels it finishes are coloured right away (their record is in registers) instead of being
      * read back by compose: 16 R + 16 W + 4 W bytes per pixel instead of 16 R + 16 W and 16 R + 4 W.  NULL = compose does
      * it all.  The tiles pass R hands to pass S are flagged in late_tiles; a filtered compose colours them afterwards. */
@@ -152,7 +158,23 @@ struct chaos_render_args {
      * edges, so almost all taps are local and the rest are peer loads over NVLink.  0 = one buffer (`in`). */
     const chaos_pixel_info *in_peer[CHAOS_MAX_PEERS];
     uint32_t slab_rows;
-    uint32_t hot_capacity;             /* the first hot_capacity entries of long_list are the hot region (0 = none) */
+    /* Long kernel: how many of its resident CTAs per SM take part.  An orbit is a chain of dependent FP64 instructions: with 8
+     * warps per scheduler a trip takes ~97 cycles, with 2 it takes ~30 at 80 % of the throughput.  When the list holds few
+     * orbits per lane the launch is as long as its longest orbit, so it runs on fewer warps: CTA layer k (blockIdx / sm_count)
+     * takes part only if the list holds at least occ_orbits_per_lane[k-1] orbits per lane of the full grid. */
+    uint32_t sm_count;
+    uint32_t occ_orbits_per_lane[3];
+    /* Cross-GPU work stealing, one-sample frames (the deep-zoom configuration).  Every rank's tile cursor and record buffer
+     * are mapped into every other rank's process (CUDA IPC).  A rank whose own tiles are handed out goes on with the next
+     * rank's: it claims tiles from that rank's cursor with system-scope atomics over NVLink, iterates them like its own and
+     * stores the records straight into the owner's buffer; the owner waits (chaosWaitForeign) until as many orbits have
+     * been finished as its tiles hold pixels.  steal_world = 0: off. */
+    uint32_t steal_world, steal_rank, frame_seq;
+    uint32_t steal_n_tiles[CHAOS_MAX_PEERS];            /* vote tiles rank q owns */
+    chaos_counters *steal_counters[CHAOS_MAX_PEERS];    /* rank q's counter block (strand 0) */
+    chaos_pixel_info *steal_out[CHAOS_MAX_PEERS];       /* rank q's output records */
+    unsigned long long own_pixels;                      /* in-bounds pixels of this rank's tiles: what chaosWaitForeign waits for */
+    uint32_t hot_capacity;             /* the last hot_capacity entries of long_list are the hot region, filled from the end (0 = none) */
     uint32_t hot_trips;                /* pass C: a pixel whose sample 0 executed at least this many trips is expected to be long */
 };
 #define CHAOS_POOL_STRIDE 128u

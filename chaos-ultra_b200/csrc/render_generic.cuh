@@ -673,6 +673,8 @@ fractalRenderMainDoubleSync(const __grid_constant__ chaos_render_args a) { rende
 /* between pass A and pass B of a two-pass render (render_refill.cuh) */
 extern "C" __global__ void __launch_bounds__(256) chaosClassifyTiles(const __grid_constant__ chaos_render_args a) { classify_tiles(a); }
 extern "C" __global__ void __launch_bounds__(256) chaosOrderTiles(const __grid_constant__ chaos_render_args a) { order_tiles(a); }
+extern "C" __global__ void chaosWaitForeign(const __grid_constant__ chaos_render_args a) { wait_foreign(a); }
+extern "C" __global__ void __launch_bounds__(256) chaosExportAll(const __grid_constant__ chaos_render_args a) { export_all_tiles(a); }
 /* after pass C: the decisions of the tiles pass B exported */
 extern "C" __global__ void __launch_bounds__(256) chaosReplayExported(const __grid_constant__ chaos_render_args a) { replay_exported(a); }
 

@@ -258,8 +258,17 @@ static __device__ void render_main_independent(const chaos_render_args &a)
     /* work items per tile: pass C rounds 2 .. S0-1; pass A rounds 0 and 1 (both exist whenever S0 >= 2: the first
      * decision comes after sample 1, :128); one sample per pixel otherwise */
     const uint32_t rounds_per_tile = kExport ? S0 - 2u : kProbe ? 2u : 1u;
-    const uint32_t n_items = kExport ? min(a.counters->n_exported, a.exp.capacity) * rounds_per_tile : a.n_tiles * rounds_per_tile;
+    uint32_t n_items = kExport ? min(a.counters->n_exported, a.exp.capacity) * rounds_per_tile : a.n_tiles * rounds_per_tile;
     unsigned int *cursor = kExport ? &a.counters->next_export_item : &a.counters->next_tile;
+    /* cross-GPU stealing (one-sample frames, chaos_render_args::steal_world): the rank whose tiles are being handed out now,
+     * and per lane the rank its orbit belongs to */
+    const bool stealing = kMode == 0 && a.steal_world > 1u;
+    uint32_t victim = a.steal_rank, owner = a.steal_rank;
+    unsigned long long own_done = 0;
+    if (stealing && blockIdx.x == 0 && threadIdx.x == 0) {      /* the counters were cleared for this frame: the cursor is open */
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int *>(&a.counters->frame_seq) = a.frame_seq;
+    }
 
     Orbit o;
     uint32_t it = 0, px = 0, py = 0, tile = 0, rnd = 0;      /* pass C: tile = export index, px = pixel within the tile */
@@ -314,6 +323,8 @@ static __device__ void render_main_independent(const chaos_render_args &a)
         if (!take_scheduling_pass(fin, busy, a.sched_idle_lanes_indep, waited) && !first && !drain_pass) continue;
         first = false;
         CHAOS_LS(ls.pass();)
+        const bool retired_now = fin;
+        const uint32_t retired_owner = owner;
         if (fin) {
             fin = false;
             uint32_t et = o.finish(it, max_iter);
@@ -335,9 +346,26 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                     rec->is_reused = et;
                 }
             }
-            else          /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
+            else if (!stealing || owner == a.steal_rank) {   /* S == 1: value = (float)(sum / 1), weight = 1 (:152-153) */
                 store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
+                own_done += 1;
+            } else {      /* a stolen orbit: the record goes straight into its owner's buffer (a peer store over NVLink) */
+                store_record(record_at(a.steal_out[owner], a.out_pitch, px, py), __uint2float_rn(et), 1.0f, 0u, 0.f);
+                __threadfence_system();
+            }
             busy = false;
+        }
+        if (stealing) {   /* tell the owners how many of their orbits ended here: one system-scope add per owner and warp */
+            const bool foreign = retired_now && retired_owner != a.steal_rank;
+            const uint32_t fm = __ballot_sync(CHAOS_FULL_MASK, foreign);
+            if (fm) {
+                if (foreign) {
+                    const uint32_t same = __match_any_sync(fm, retired_owner);
+                    if (lane == (uint32_t)__ffs(same) - 1u)
+                        atomicAdd_system(&a.steal_counters[retired_owner]->foreign_done, (unsigned long long)__popc(same));
+                }
+                __syncwarp();
+            }
         }
         for (;;) {
             uint32_t idle = __ballot_sync(CHAOS_FULL_MASK, !busy);
@@ -345,9 +373,27 @@ static __device__ void render_main_independent(const chaos_render_args &a)
             if (!pend) {
                 if (queue_empty) break;
                 uint32_t t = 0;
-                if (lane == 0) t = atomicAdd(cursor, 1u);
+                if (lane == 0) t = (stealing && victim != a.steal_rank) ? atomicAdd_system(cursor, 1u) : atomicAdd(cursor, 1u);
                 t = __shfl_sync(CHAOS_FULL_MASK, t, 0);
-                if (t >= n_items) { queue_empty = true; break; }
+                if (t >= n_items) {
+                    if (!stealing) { queue_empty = true; break; }
+                    /* this rank's tiles are handed out: go on with the next rank whose counters belong to this frame (a rank
+                     * that has not started the frame yet is passed over, not waited for) */
+                    uint32_t next = a.steal_world;
+                    if (lane == 0) {
+                        /* ranks are visited once each, in ring order after the own rank */
+                        for (uint32_t q = (victim + 1u) % a.steal_world; q != a.steal_rank; q = (q + 1u) % a.steal_world) {
+                            const unsigned int seq = *reinterpret_cast<const volatile unsigned int *>(&a.steal_counters[q]->frame_seq);
+                            if (seq == a.frame_seq && a.steal_n_tiles[q]) { next = q; break; }
+                        }
+                    }
+                    next = __shfl_sync(CHAOS_FULL_MASK, next, 0);
+                    if (next >= a.steal_world) { queue_empty = true; break; }
+                    victim = next;
+                    cursor = &a.steal_counters[victim]->next_tile;
+                    n_items = a.steal_n_tiles[victim];
+                    continue;
+                }
                 if (kExport) {
                     cur_tile = t / rounds_per_tile;                       /* export index */
                     cur_round = 2u + (t - cur_tile * rounds_per_tile);
@@ -359,7 +405,8 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                     tile_origin(a, cur_tile, x0, y0);
                 } else {
                     cur_tile = t;
-                    tile_origin(a, t, x0, y0);
+                    if (stealing) tile_origin_of(a.tiles_x, victim, a.part_count, a.band_tile_rows, t, x0, y0);   /* the owner's band deal */
+                    else tile_origin(a, t, x0, y0);
                 }
                 pend = __ballot_sync(CHAOS_FULL_MASK, (x0 + (lane & 7u)) < a.width && (y0 + (lane >> 3)) < a.height);
             }
@@ -385,6 +432,7 @@ static __device__ void render_main_independent(const chaos_render_args &a)
                 o.start(cx, cy, ctx);
                 it = 0;
                 busy = true;
+                owner = victim;
                 tested = true;                               /* new orbits start with a tested block */
             }
             pend &= ~__reduce_or_sync(CHAOS_FULL_MASK, take ? (1u << mypix) : 0u);
@@ -479,6 +527,10 @@ static __device__ void render_main_independent(const chaos_render_args &a)
         }
     }
     if (!kExport) flush_counters(a, iters, nsamples, skipped);
+    if (stealing) {
+        for (int o2 = 16; o2; o2 >>= 1) own_done += __shfl_xor_sync(CHAOS_FULL_MASK, own_done, o2);
+        if (lane == 0 && own_done) atomicAdd(&a.counters->own_done, own_done);
+    }
     CHAOS_LS(ls.flush(a, kMode == 1 ? 0 : kMode == 2 ? 2 : 3);)
 }
 
@@ -530,6 +582,7 @@ static __device__ void render_main_rounds(const chaos_render_args &a, refill_war
      * 6 % of the lanes).  Then every tile is exported as it arrives: its rounds run side by side in pass C.  Rounds that
      * turn out not to exist are wasted work, which is why a frame with many such tiles (c2ex2) does not do it. */
     const bool export_everything = n_cont <= a.export_all_below;
+    if (export_everything && a.exp.capacity && a.export_all_done) return;     /* chaosExportAll has taken them all */
 
     for (uint32_t w = lane; w < sizeof(ws.hdr) / 4u; w += 32u) reinterpret_cast<uint32_t *>(ws.hdr)[w] = 0u;
     __syncwarp();
@@ -843,6 +896,21 @@ static __device__ void replay_exported(const chaos_render_args &a)
     flush_counters(a, iters, nsamples, skipped);
 }
 
+/* ---- cross-GPU stealing: the owner's side ---------------------------------------------------------------------- */
+/* After its own launch a rank waits until every pixel of its tiles has been finished by somebody: own_done counts the
+ * orbits that ended here, foreign_done those the other ranks finished (they add to it with system-scope atomics after
+ * their record stores).  One thread; bounded: a rank that died leaves the frame void, not hanging. */
+static __device__ void wait_foreign(const chaos_render_args &a)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0 || a.steal_world <= 1u) return;
+    const volatile unsigned long long *own = &a.counters->own_done, *foreign = &a.counters->foreign_done;
+    for (uint32_t spins = 0; *own + *foreign < a.own_pixels; ++spins) {
+        if (spins >= (1u << 26)) { a.counters->abort = 1u; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 /* ---- cost classes between the two passes ------------------------------------------------------ */
 /* Expected cost of a tile's remaining rounds from what pass A left in its records: do the pixels' trip counts agree
  * (then the i == 1 vote will most likely end the tile after one more round), and how many trips did pass A EXECUTE in
@@ -881,19 +949,14 @@ static __device__ void classify_tiles(const chaos_render_args &a)
         uint32_t S = S0;
         bool blocked = false;        /* some pixel's mean is 0: the tile looks set to use its whole budget (see render_main_rounds) */
         if (decision_entered(adaptive, 1u, S)) {
-            vote_preds p = {true, true, true, false};
-            if (part) {
-                float sm[CHAOS_ADAPTIVE_THRESHOLD];
-#pragma unroll
-                for (uint32_t q = 0; q < CHAOS_ADAPTIVE_THRESHOLD; ++q) sm[q] = 0.f;
-                sm[0] = __uint2float_rn(et0); sm[1] = __uint2float_rn(et1);
-                p = decision_preds(sm, 1u, et0 + et1);
-            }
-            const bool all_eq = __all_sync(CHAOS_FULL_MASK, p.eq);
-            const bool all_lt = __all_sync(CHAOS_FULL_MASK, p.lt);
-            const bool all_le = __all_sync(CHAOS_FULL_MASK, p.le);
-            S = decision_update(1u, S, all_eq, all_lt, all_le);
-            blocked = __any_sync(CHAOS_FULL_MASK, p.zero_mean && part);
+            /* decision_preds at i == 1, written out: the dispersion over ONE sample divides by (uint) i - 1 = 0, so it is +inf or
+             * NaN for every pixel and neither `disp < 0.01` nor `disp <= 1` can hold -- only the first rule (:140-142, both
+             * samples equal) can end the tile here.  (chaosPassB / pass D evaluate the general form for i >= 2.) */
+            const float s0 = __uint2float_rn(et0), s1 = __uint2float_rn(et1);
+            const bool eq = !part || fabsf(__fsub_rn(s0, s1)) < FLT_EPSILON;
+            const bool zero_mean = part && __uint2float_rn((et0 + et1) / 2u) == 0.f;
+            if (__all_sync(CHAOS_FULL_MASK, eq)) S = 2u;
+            blocked = __any_sync(CHAOS_FULL_MASK, zero_mean);
             /* Also set to go on: a pixel whose first two samples lie so far apart that its dispersion after sample 2 is above 1
              * whatever sample 2 is (variance >= d^2 / 2 for d = et0 - et1, mean <= (et0 + et1 + maxIterations) / 3).  Pass B
              * would export such a tile after one more round; it may as well go now.  (A scheduling hint: pass D replays
@@ -944,6 +1007,47 @@ static __device__ void classify_tiles(const chaos_render_args &a)
     for (uint32_t k = threadIdx.x; k < CHAOS_COST_BUCKETS; k += blockDim.x)
         if (hist[k]) atomicAdd(&a.counters->bucket_count[k], hist[k]);
 }
+/* Few tiles left after the decision on sample 1 (a frame whose tiles mostly ended there): every one of them is exported
+ * (see render_main_rounds: pass B would be all latency).  Exporting needs nothing of pass B's machinery -- the tile's two
+ * escape times go to the export arrays exactly as chaosClassifyTiles does it for the tiles it exports itself -- so a light
+ * kernel does it, one warp per tile, and pass B, launched right after, finds nothing to do and ends at once. */
+static __device__ void export_all_tiles(const chaos_render_args &a)
+{
+    const uint32_t n_cont = a.counters->n_continuing;
+    if (n_cont > a.export_all_below || !a.exp.capacity) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_cont; k += warps) {
+        const uint32_t t = a.tile_order[k];
+        uint32_t x0, y0;
+        tile_origin(a, t, x0, y0);
+        const uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
+        const bool part = px < a.width && py < a.height;
+        uint32_t et0 = 0u, et1 = 0u;
+        if (part) {
+            const float4 rec = *reinterpret_cast<const float4 *>(record_at(a.out, a.out_pitch, px, py));
+            et0 = __float_as_uint(rec.x); et1 = __float_as_uint(rec.z);
+        }
+        uint32_t e = 0u;
+        if (lane == 0) e = atomicAdd(&a.counters->n_exported, 1u);
+        e = __shfl_sync(CHAOS_FULL_MASK, e, 0);
+        if (e >= a.exp.capacity) continue;           /* (cannot happen: the arrays hold every tile of the launch) */
+        export_et(a, e, 0u)[lane] = et0;
+        export_et(a, e, 1u)[lane] = et1;
+        if (lane == 0) {
+            a.exp.tile[e] = t; a.exp.first[e] = 2u;
+            if (a.late_tiles) {
+                const uint32_t gt = (y0 >> 2) * a.tiles_x + (x0 >> 3);
+                atomicOr(&a.late_tiles[gt >> 5], 1u << (gt & 31u));
+            }
+        }
+        if (lane >= 2u && lane < CHAOS_EXPORT_ROUNDS) {
+            a.exp.iters[(size_t)e * CHAOS_EXPORT_ROUNDS + lane] = 0ull;
+            a.exp.skipped[(size_t)e * CHAOS_EXPORT_ROUNDS + lane] = 0ull;
+        }
+    }
+}
+
 /* counting-sort scatter: one thread per tile; every block reserves one range per class */
 static __device__ void order_tiles(const chaos_render_args &a)
 {

@@ -164,7 +164,7 @@ static __device__ void stream_probe(const chaos_render_args &a)
         else { d.a = px | (rnd << 31); d.b = py; }
         Orbit o;
         uint32_t it = 0;
-        bool ended = false;
+        bool ended = false, bailed = false;
         if (inb) sf.start(o, px, py, rnd, ctx);
         if (!Orbit::kResumable) {       /* one opaque call (fractal.cuh ClassicOrbit): the whole orbit, here */
             if (inb) { o.run(it, max_iter, true); ended = true; }
@@ -175,7 +175,7 @@ static __device__ void stream_probe(const chaos_render_args &a)
                 if (inb && !ended) ended = o.run(it, lim, true) || it >= max_iter;
                 const uint32_t live = __ballot_sync(CHAOS_FULL_MASK, inb && !ended);
                 if (!live) break;
-                if (lim >= CHAOS_PROBE_BAIL && !__any_sync(CHAOS_FULL_MASK, inb && ended)) break;
+                if (lim >= CHAOS_PROBE_BAIL && !__any_sync(CHAOS_FULL_MASK, inb && ended)) { bailed = true; break; }
             }
         }
         if (inb && ended) {
@@ -183,12 +183,17 @@ static __device__ void stream_probe(const chaos_render_args &a)
             tot.add(it, o.skipped());
         }
         /* survivors go to the long list.  Longest first: the launch ends when its last orbit does, and an orbit of maxIterations
-         * trips that starts when the list runs dry IS the tail.  Pass C knows what to expect -- the executed trips of the
-         * pixel's sample 0 are still in its record -- and puts those orbits into the list's hot region, which the long
-         * kernel hands out first. */
+         * trips that starts when the list runs dry IS the tail.  What is known about an orbit's length:
+         *   pass C  the executed trips of the pixel's sample 0 are still in its record;
+         *   other passes  a survivor of a tile in which some orbit ended sits next to the set's boundary -- where escapes are
+         *           slow and convergence is slower -- while a tile in which nobody ended within the first trips (`bailed`) lies
+         *           deep inside or deep in a zoom, where every orbit is alike.
+         * Orbits expected to be long go to the list's hot region (its END, growing down), which the long kernel hands out
+         * first.  Pass A and the one-sample pass cannot overflow the list (it holds every orbit they have), so there the two
+         * ends cannot meet; pass C reserves the hot region (hot_capacity entries). */
         bool hot = false;
-        if (pass_c && a.hot_capacity && inb && !ended)
-            hot = __float_as_uint(record_at(a.out, a.out_pitch, px, py)->weight_of_new_samples) >= a.hot_trips;
+        if (a.hot_capacity && inb && !ended)
+            hot = pass_c ? __float_as_uint(record_at(a.out, a.out_pitch, px, py)->weight_of_new_samples) >= a.hot_trips : !bailed;
         const uint32_t surv_hot = __ballot_sync(CHAOS_FULL_MASK, hot);
         if (surv_hot) {
             uint32_t base = 0;
@@ -196,7 +201,7 @@ static __device__ void stream_probe(const chaos_render_args &a)
             base = __shfl_sync(CHAOS_FULL_MASK, base, 0);
             if (hot) {
                 const uint32_t idx = base + __popc(surv_hot & lanemask_lt());
-                if (idx < a.hot_capacity) a.long_list[idx] = make_uint2(d.a, d.b);
+                if (idx < a.hot_capacity) a.long_list[a.list_capacity - 1u - idx] = make_uint2(d.a, d.b);
                 else hot = false;                                   /* region full: an ordinary entry */
             }
         }
@@ -206,8 +211,8 @@ static __device__ void stream_probe(const chaos_render_args &a)
             if (lane == 0) base = atomicAdd(&ctl->n_long, (unsigned int)__popc(surv));
             base = __shfl_sync(CHAOS_FULL_MASK, base, 0);
             if (inb && !ended && !hot) {
-                const uint32_t idx = a.hot_capacity + base + __popc(surv & lanemask_lt());
-                if (idx < a.list_capacity) {
+                const uint32_t idx = base + __popc(surv & lanemask_lt());
+                if (idx < a.list_capacity - (pass_c ? a.hot_capacity : 0u)) {
                     a.long_list[idx] = make_uint2(d.a, d.b);
                 } else {                 /* list full (never with the host's sizing for passes 0 and A): the orbit is finished here */
                     run_whole(o, it, max_iter);
@@ -345,8 +350,14 @@ static __device__ void stream_long(const chaos_render_args &a)
     const orbit_ctx ctx = {a.max_iter, a.shortcuts};
     const uint32_t which = a.phase == 3u ? 1u : 0u;
     chaos_stream_ctl *ctl = &a.counters->stream[which];
-    const uint32_t n_hot = min(ctl->n_hot, a.hot_capacity);      /* entries 0 .. n_hot-1: the hot region; then the ordinary ones */
-    const uint32_t n = n_hot + min(ctl->n_long, a.list_capacity - a.hot_capacity);
+    const uint32_t n_hot = min(ctl->n_hot, a.hot_capacity);      /* the hot region: the list's last n_hot entries, handed out first */
+    const uint32_t n = n_hot + min(ctl->n_long, a.list_capacity - (a.phase == 3u ? a.hot_capacity : 0u));
+    /* few orbits per lane: the upper CTA layers of every SM stay out (see chaos_render_args::occ_orbits_per_lane) */
+    if (a.sm_count) {
+        const uint32_t layer = blockIdx.x / a.sm_count;
+        const uint32_t per_lane = n / (gridDim.x * blockDim.x);
+        if (layer >= 1u && per_lane < a.occ_orbits_per_lane[min(layer, 3u) - 1u]) return;
+    }
     fin_t *const finish_list = reinterpret_cast<fin_t *>(a.finish_list);
     const uint32_t max_debt = max(a.sched_idle_lanes_indep, 1u) * 64u;
     stream_totals tot = {0ull, 0ull, 0ull};
@@ -419,7 +430,7 @@ static __device__ void stream_long(const chaos_render_args &a)
             base = __shfl_sync(CHAOS_FULL_MASK, base, 0);
             const uint32_t idx = base + __popc(idle & lanemask_lt());
             if (!busy && idx < n) {
-                const uint2 ent = a.long_list[idx < n_hot ? idx : a.hot_capacity + (idx - n_hot)];
+                const uint2 ent = a.long_list[idx < n_hot ? a.list_capacity - 1u - idx : idx - n_hot];
                 d.a = ent.x; d.b = ent.y;
                 uint32_t px, py, rnd;
                 sf.decode(a, d, px, py, rnd);

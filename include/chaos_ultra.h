@@ -106,6 +106,8 @@ typedef struct chaos_stats {
                                       * loop counts them */
     uint64_t samples;                /* number of evaluated samples (orbits) */
     uint64_t launches_total;         /* kernels launched since the renderer was opened */
+    uint64_t foreign_orbits;         /* several GPUs, one-sample frames: orbits of this rank's tiles that other ranks iterated
+                                      * (cross-GPU tile stealing); their work is in THOSE ranks' pixel_iterations */
     uint64_t skipped_iterations;     /* the part of pixel_iterations that was PROVEN instead of executed: an orbit whose
                                       * state recurs bit for bit never escapes, so its trip count is maxIterations
                                       * (same records as the reference; CHAOS_SHORTCUTS=0 executes every trip) */
@@ -203,9 +205,12 @@ CHAOS_API chaos_status chaos_set_host_target(chaos_renderer *r, void *host_frame
  * every rank opens every other rank's pair.  chaos_render_fast then reprojects for real: a tap into another slab is a peer
  * load from the owner's primary buffer over NVLink.  Needs a frame barrier (a rank must not start frame f + 1 before every
  * rank has finished frame f) and the same sequence of render calls on all ranks.  Without the peers' buffers a fast frame
- * of a partitioned renderer renders its bands afresh (see chaos_set_partition). */
-CHAOS_API chaos_status chaos_ipc_export_records(chaos_renderer *r, chaos_ipc_handle out[2]);
-CHAOS_API chaos_status chaos_ipc_open_records(chaos_renderer *r, uint32_t peer_rank, const chaos_ipc_handle in[2]);
+ * of a partitioned renderer renders its bands afresh (see chaos_set_partition).
+ * The same mappings give one-sample quality frames (the deep-zoom configuration) DYNAMIC REDISTRIBUTION: a rank whose own tiles
+ * are handed out claims tiles from the other ranks' cursors (system-scope atomics over NVLink), iterates them and stores the
+ * records into the owner's buffer; the owner's call returns when every pixel of its tiles has been finished by somebody. */
+CHAOS_API chaos_status chaos_ipc_export_records(chaos_renderer *r, chaos_ipc_handle out[3]);   /* two record buffers + scheduler counters */
+CHAOS_API chaos_status chaos_ipc_open_records(chaos_renderer *r, uint32_t peer_rank, const chaos_ipc_handle in[3]);
 /* `shm_block`: 64 zero-initialised bytes of host memory shared by the `world` processes of the job (NULL = no barrier).
  * Every later render call announces its frame there when its own kernels are done and returns when all ranks have
  * announced theirs -- on return the target frame holds every rank's bands.  Waits are bounded (10 s -> CHAOS_ERR_CUDA). */

@@ -25,6 +25,10 @@ def main():
     dev = int(os.environ["LOCAL_RANK"]) if torch.cuda.device_count() >= world else 0
     dist.init_process_group("gloo")
     mode = sys.argv[1]
+    if mode == "steal":
+        steal_tiles(cu, part, dist, rank, world, dev)
+        dist.destroy_process_group()
+        return
     if mode.startswith("zoom"):
         zoom_sequence(cu, part, dist, rank, world, dev, mode)
         dist.destroy_process_group()
@@ -66,6 +70,47 @@ def main():
             r.setOutputTarget(0)
         job.close(dist)
     dist.destroy_process_group()
+
+
+def steal_tiles(cu, part, dist, rank, world, dev):
+    """one-sample frame (the deep-zoom configuration) with a deliberately lopsided deal: contiguous slabs of a view whose
+    expensive part lies in the first slab.  The ranks that finish early must take tiles from the others' cursors (records
+    stored into the owner's buffer); the assembled frame, every rank's own records and the total work must not change."""
+    import cases
+    import helpers
+    import torch
+    W, H = 1024, 768
+    case = dict(name="mpsteal", fractal="mandelbrot", W=W, H=H, image=cases.seg(-0.6, 0.55, 1.2, W, H), maxIter=20000, maxSS=1.0, flags=0,
+                double=True, julia_c=(0.0, 0.0), amplifier=10)       # the set fills the upper part of the view, the lower part escapes at once
+    with cu.CudaFractalRendererProvider(device=dev) as prov:
+        r = prov.getRenderer("mandelbrot", False)
+        r.initializeRendering(W, H, None, cu.OUTPUT_DEVICE)
+        r.renderQuality(helpers.model_for(cu, case))
+        whole_rec, whole_rgba, whole_it = r.downloadRecords(), r.outputRGBA().copy(), r.stats().pixel_iterations
+        slab = part.slab_rows(H, world)
+        r.setPartition(rank, world, slab)
+        job = part.JobSharedMemory(rank, world, H, W, dist)
+        job.attach(r, host_target=True, barrier=True)
+        part.share_records(r, rank, world, dist)
+        r0, r1 = rank * slab, min(H, (rank + 1) * slab)
+        stolen = 0
+        for frame in range(4):
+            r.renderQuality(helpers.model_for(cu, case))
+            st = r.stats()
+            helpers.assert_records_equal(r.downloadRecords()[r0:r1], whole_rec[r0:r1], "rank %d frame %d: own rows (some written by other ranks)" % (rank, frame))
+            t = torch.tensor([st.pixel_iterations, st.foreign_orbits], dtype=torch.int64)
+            dist.all_reduce(t)
+            assert int(t[0]) == whole_it, "frame %d: work of the ranks %d != whole frame %d" % (frame, int(t[0]), whole_it)
+            stolen += int(t[1])
+            if rank == 0:
+                assert np.array_equal(job.frame, whole_rgba), "frame %d differs" % frame
+            dist.barrier()
+        assert stolen > 0, "no tile changed ranks although the deal was lopsided"
+        if rank == 0:
+            print("tile stealing: %d orbits changed ranks over 4 frames" % stolen)
+        r.setFrameBarrier(0, 0)
+        r.setHostTarget(0, 0)
+        job.close(dist)
 
 
 def zoom_sequence(cu, part, dist, rank, world, dev, mode):

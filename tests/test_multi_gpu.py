@@ -40,3 +40,15 @@ def test_zoom_sequence_on_several_ranks_equals_the_whole_sequence(mode, world):
            "--master-port", str(_free_port()), str(ROOT / "tests" / "mp_frame_worker.py"), mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_tiles_are_stolen_across_ranks_and_nothing_changes(world):
+    """dynamic redistribution of a one-sample frame: ranks that run out of tiles take them from the other ranks' cursors"""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(ROOT / "tests" / "mp_frame_worker.py"), "steal"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "tile stealing:" in res.stdout
