@@ -77,6 +77,56 @@ static __device__ __forceinline__ float newton_root_search(uint32_t maxIteration
     return root_of(x);
 }
 
+/* The same search as an orbit that can be suspended and resumed (fractal.cuh, `struct Orbit`): its state is the iterate and
+ * the trip at which convergence is tested next, so the lane-refill and stream engines can hand a pixel's Newton iteration
+ * from block to block and from warp to warp like an escape orbit (kResumable).  Impl supplies
+ *     static thrust::complex<Real> step(thrust::complex<Real>)      one Newton step (newton_step_cubic / newton_step_unity)
+ *     static unsigned int root_of(thrust::complex<Real>)             which root has been reached, 0 = none
+ *     static constexpr bool kTestEveryStep                           newton_iterations.cu:56-60: test after every step, the value
+ *                                                                    is the step count; otherwise newton_generic.cu:56-70: test
+ *                                                                    after 10 steps and then every maxIterations / 10, the value
+ *                                                                    is the root
+ * The step and the test are the functions above, called in the reference's order: splitting the loop changes no operation. */
+template <class Impl, class Real> struct NewtonOrbit {
+    static constexpr bool kResumable = true;
+    thrust::complex<Real> x;
+    uint32_t check_at, max_iter;
+    float result;
+    __device__ __forceinline__ void start(Real px, Real py, const orbit_ctx &ctx)
+    {
+        x = thrust::complex<Real>(px, py);
+        check_at = 10u;
+        max_iter = ctx.max_iter;
+        result = 0.f;
+    }
+    /* iterate while i < limit; true = over (a root was reached at a test, or i = maxIterations) */
+    __device__ __forceinline__ bool run(uint32_t &i, uint32_t limit, bool)
+    {
+        while (i < limit) {
+            x = Impl::template step<Real>(x);
+            ++i;
+            if (Impl::kTestEveryStep) {
+                if (Impl::template root_of<Real>(x) != 0u) { result = (float)i; return true; }
+            } else if (i == check_at) {
+                const unsigned int root = Impl::template root_of<Real>(x);
+                if (root != 0u) { result = (float)root; return true; }
+                check_at += max_iter / 10u;
+            }
+        }
+        if (i >= max_iter) {
+            result = Impl::kTestEveryStep ? (float)i : (float)Impl::template root_of<Real>(x);
+            return true;
+        }
+        return false;
+    }
+    __device__ __forceinline__ void force_exact() {}
+    __device__ __forceinline__ bool wants_tested() const { return false; }      /* one instruction stream: nothing is deferred */
+    __device__ __forceinline__ uint32_t skipped() const { return 0u; }
+    __device__ __forceinline__ void save(Real &ox, Real &oy) const { ox = x.real(); oy = x.imag(); }
+    __device__ __forceinline__ void resume(Real ox, Real oy) { x = thrust::complex<Real>(ox, oy); }
+    __device__ __forceinline__ uint32_t finish(uint32_t, uint32_t) const { return __float2uint_rz(result); }
+};
+
 /* fixed colours of the root-coloured modules (helpers.cuh:150-162, R in the low byte) */
 static __device__ __forceinline__ uint32_t newton_root_colour(float result)
 {

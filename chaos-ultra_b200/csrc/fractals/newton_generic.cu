@@ -10,13 +10,12 @@ __constant__ double roots[6];
 __constant__ double coefficients[4];
 
 struct NewtonGenericImpl {
-    template <class Real> static __device__ float compute(uint32_t maxIterations, Real px, Real py, uint32_t &trips)
+    static constexpr bool kTestEveryStep = false;
+    template <class Real> static __device__ __forceinline__ thrust::complex<Real> step(thrust::complex<Real> x) { return newton_step_cubic<Real>(coefficients, x); }
+    template <class Real> static __device__ __forceinline__ unsigned int root_of(thrust::complex<Real> x)
     {
         typedef thrust::complex<Real> cplx;
-        auto root_of = [](cplx x) {
-            return newton_convergence_root<Real>(x, cplx(roots[0], roots[1]), cplx(roots[2], roots[3]), cplx(roots[4], roots[5]));
-        };
-        return newton_root_search<Real>(maxIterations, px, py, trips, [](cplx x) { return newton_step_cubic<Real>(coefficients, x); }, root_of);
+        return newton_convergence_root<Real>(x, cplx(roots[0], roots[1]), cplx(roots[2], roots[3]), cplx(roots[4], roots[5]));
     }
 };
 
@@ -24,7 +23,7 @@ struct Fractal {
     /* no branch separates c.y's multiply and subtract in the reference build of this module: ptxas contracts them
      * into one FMA (SASS of oracle/_ref/newton_generic.src.cubin), see frame_map::plane_point */
     static constexpr bool kFusedPlaneY = true;
-    template <class Real> using Orbit = ClassicOrbit<NewtonGenericImpl, Real>;
+    template <class Real> using Orbit = NewtonOrbit<NewtonGenericImpl, Real>;
     static __device__ __forceinline__ uint32_t colorize(const uint32_t *, uint32_t, float result) { return newton_root_colour(result); }
     static __device__ void debugFractal() {}
 };

@@ -11,18 +11,12 @@ __constant__ double coefficients[4];
 __constant__ int colorMagnifier;
 
 struct NewtonIterationsImpl {
-    template <class Real> static __device__ float compute(uint32_t maxIterations, Real px, Real py, uint32_t &trips)
+    static constexpr bool kTestEveryStep = true;
+    template <class Real> static __device__ __forceinline__ thrust::complex<Real> step(thrust::complex<Real> x) { return newton_step_cubic<Real>(coefficients, x); }
+    template <class Real> static __device__ __forceinline__ unsigned int root_of(thrust::complex<Real> x)
     {
         typedef thrust::complex<Real> cplx;
-        cplx x(px, py);
-        unsigned int i = 0;
-        while (i < maxIterations) {
-            x = newton_step_cubic<Real>(coefficients, x);
-            ++i;
-            if (newton_convergence_root<Real>(x, cplx(roots[0], roots[1]), cplx(roots[2], roots[3]), cplx(roots[4], roots[5])) != 0) break;
-        }
-        trips = i;
-        return i;
+        return newton_convergence_root<Real>(x, cplx(roots[0], roots[1]), cplx(roots[2], roots[3]), cplx(roots[4], roots[5]));
     }
 };
 
@@ -30,7 +24,7 @@ struct Fractal {
     /* no branch separates c.y's multiply and subtract in the reference build of this module: ptxas contracts them
      * into one FMA (SASS of oracle/_ref/newton_iterations.src.cubin), see frame_map::plane_point */
     static constexpr bool kFusedPlaneY = true;
-    template <class Real> using Orbit = ClassicOrbit<NewtonIterationsImpl, Real>;
+    template <class Real> using Orbit = NewtonOrbit<NewtonIterationsImpl, Real>;
     static __device__ __forceinline__ uint32_t colorize(const uint32_t *palette, uint32_t len, float result)
     {
         return chaos_default_colorize(palette, len, result, (uint32_t)colorMagnifier);

@@ -32,6 +32,7 @@ __constant__ uint32_t CHAOS_MODULE_ABI_VERSION = CHAOS_MODULE_ABI;
 #define CHAOS_FULL_MASK 0xffffffffu
 #define CHAOS_RENDER_THREADS 256
 #define CHAOS_ADAPTIVE_THRESHOLD 10u                       /* :96 adaptiveTreshold */
+#define CHAOS_MAX_SAMPLES 64u                              /* :12 MAX_SUPER_SAMPLING */
 
 /* ------------------------------------------------------------------------------------------
  * frame constants every orbit needs, computed once per thread exactly like the reference does
@@ -209,11 +210,24 @@ static __device__ __forceinline__ void run_whole(Orbit &o, uint32_t &it, uint32_
  * all lanes step through the sample rounds together.  Simple; kept as the differential
  * reference for engine 1 and used by the advanced kernel for its (rare) sampled tiles.
  * ======================================================================================== */
+/* the sample offsets of a call with budget scf, for all 64 possible sample indices: a division or three each (:103-117), so
+ * a kernel whose tiles all sample with the same budget computes them once per CTA (shared memory) instead of per sample */
+template <class Real> struct sample_offsets {
+    Real dx[CHAOS_MAX_SAMPLES], dy[CHAOS_MAX_SAMPLES];
+    float scf;      /* the budget the table was made for */
+    __device__ __forceinline__ void fill(float budget)     /* all threads of the CTA; ends with a barrier */
+    {
+        if (threadIdx.x < CHAOS_MAX_SAMPLES) sample_delta<Real>(threadIdx.x, sqrtf(__fadd_rn(budget, -2.0f)), dx[threadIdx.x], dy[threadIdx.x]);
+        if (threadIdx.x == 0) scf = budget;
+        __syncthreads();
+    }
+};
+
 template <class Real, class FractalT>
 static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_args &a, const frame_map<Real> &fm,
                                                             bool participate, uint32_t px, uint32_t py, float &scf,
                                                             unsigned long long &iters, unsigned long long &nsamples,
-                                                            unsigned long long &skipped)
+                                                            unsigned long long &skipped, const sample_offsets<Real> *table = nullptr)
 {
     typedef typename FractalT::template Orbit<Real> Orbit;
     const orbit_ctx ctx = {a.max_iter, a.force_exact ? 0u : a.shortcuts};
@@ -221,13 +235,15 @@ static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_a
     uint32_t S = min(64u, __float2uint_rz(roundf(scf)));
     const float spr = sqrtf(__fadd_rn(scf, -2.0f));
     const bool adaptive = (a.flags & CHAOS_FLAG_ADAPTIVE_SS) != 0u;
+    const bool tabled = table != nullptr && table->scf == scf;      /* (bit-identical values: the table holds what sample_delta returns) */
     float samples[CHAOS_ADAPTIVE_THRESHOLD];
     uint32_t sum = 0;
     uint32_t i = 0;
     do {
         if (participate) {
             Real dx, dy, cx, cy;
-            sample_delta<Real>(i, spr, dx, dy);
+            if (tabled) { dx = table->dx[i]; dy = table->dy[i]; }
+            else sample_delta<Real>(i, spr, dx, dy);
             fm.template plane_point<fused_plane_y<FractalT>::value>(px, py, dx, dy, cx, cy);
             Orbit o;
             o.start(cx, cy, ctx);
@@ -247,12 +263,20 @@ static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_a
             }
         }
         if (decision_entered(adaptive, i, S)) {
-            vote_preds p = {true, true, true, false};
-            if (participate) p = decision_preds(samples, i, sum);
-            bool all_eq = __all_sync(CHAOS_FULL_MASK, p.eq);
-            bool all_lt = __all_sync(CHAOS_FULL_MASK, p.lt);
-            bool all_le = __all_sync(CHAOS_FULL_MASK, p.le);
-            S = decision_update(i, S, all_eq, all_lt, all_le);
+            if (i == 1u) {
+                /* after sample 1 the dispersion is a division by (uint) 1 - 1 = 0: +inf or NaN for every pixel, so neither
+                 * `disp < 0.01` nor `disp <= 1` can hold and only the first rule (:140-142, both samples equal) can end
+                 * the tile -- decision_preds/decision_update at i == 1, written out (most tiles of a frame end here) */
+                const bool eq = !participate || fabsf(__fsub_rn(samples[0], samples[1])) < FLT_EPSILON;
+                if (__all_sync(CHAOS_FULL_MASK, eq)) S = 2u;
+            } else {
+                vote_preds p = {true, true, true, false};
+                if (participate) p = decision_preds(samples, i, sum);
+                bool all_eq = __all_sync(CHAOS_FULL_MASK, p.eq);
+                bool all_lt = __all_sync(CHAOS_FULL_MASK, p.lt);
+                bool all_le = __all_sync(CHAOS_FULL_MASK, p.le);
+                S = decision_update(i, S, all_eq, all_lt, all_le);
+            }
         }
         ++i;
     } while (i < S);
@@ -263,6 +287,8 @@ static __device__ __forceinline__ uint32_t sample_tile_sync(const chaos_render_a
 template <class Real, class FractalT>
 static __device__ void render_main_sync(const chaos_render_args &a)
 {
+    __shared__ sample_offsets<Real> offsets;
+    offsets.fill(a.max_ss);
     frame_map<Real> fm;
     fm.init(a);
     const uint32_t lane = threadIdx.x & 31u;
@@ -277,7 +303,7 @@ static __device__ void render_main_sync(const chaos_render_args &a)
         uint32_t px = x0 + (lane & 7u), py = y0 + (lane >> 3);
         bool inb = px < a.width && py < a.height;
         float scf = a.max_ss;
-        uint32_t v = sample_tile_sync<Real, FractalT>(a, fm, inb, px, py, scf, iters, nsamples, skipped);
+        uint32_t v = sample_tile_sync<Real, FractalT>(a, fm, inb, px, py, scf, iters, nsamples, skipped, &offsets);
         if (inb) store_record(record_at(a.out, a.out_pitch, px, py), __uint2float_rn(v), scf, 0u, 0.f);
     }
     flush_counters(a, iters, nsamples, skipped);     /* exact work counters: warp-reduce then one atomic per warp */

@@ -13,6 +13,13 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 
 
+def _failure(res):
+    """what the worker said (it prints its own traceback), not torchrun's summary of exit codes"""
+    said = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    i = next((k for k, ln in enumerate(said) if "FAILED:" in ln), max(0, len(said) - 30))
+    return "\n".join(said[i:i + 40]) + "\n" + res.stderr[-600:]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -27,7 +34,7 @@ def test_frame_assembled_by_several_processes_equals_the_whole_frame(mode, world
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(ROOT / "tests" / "mp_frame_worker.py"), mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.returncode == 0, _failure(res)
 
 
 @pytest.mark.gpu
@@ -39,7 +46,7 @@ def test_zoom_sequence_on_several_ranks_equals_the_whole_sequence(mode, world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(ROOT / "tests" / "mp_frame_worker.py"), mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.returncode == 0, _failure(res)
 
 
 @pytest.mark.gpu
@@ -50,5 +57,5 @@ def test_tiles_are_stolen_across_ranks_and_nothing_changes(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(ROOT / "tests" / "mp_frame_worker.py"), "steal"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.returncode == 0, _failure(res)
     assert "tile stealing:" in res.stdout
