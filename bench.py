@@ -42,8 +42,10 @@ A, FOV, REUSE, ZOOMING, ZOOM_IN = 1, 4, 8, 16, 32
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel(s), per frame, from one
 # `ncu --set full` capture of the same command (never measured in a bench run); workload -> (bytes, capture)
 NCU_TRAFFIC = {
-    "c2": (int((8.36 + 92.24 + 11.22 + 0.003 + 10.89 + 0.76) * 1e6), "profiles/r01g_passes_c2.txt: chaosPassA + chaosPassB + chaosPassC Double"),
-    "c3": (int((127.08 + 85.31 + 132.73 + 9.60) * 1e6), "profiles/r01b_fast_frame_c3.txt: chaosReusePassFloat + compose "
+    "c2": (int((0.15 + 73.44 + 40.86 + 13.94 + 21.25 + 0.07 + 0.05 + 0.0 + 7.58 + 0.01 + 24.83 + 22.46 + 62.76 + 0.99) * 1e6),
+           "profiles/r02_passes_c2.txt: chaosProbe + chaosLong + chaosFinish of passes A and C + chaosPassB, Double (133 MB of that are the records "
+           "themselves; the rest is the long and finish lists and the export arrays; HBM is 1 % busy)"),
+    "c3": (int((127.10 + 85.13 + 132.73 + 6.94) * 1e6), "profiles/r02_fast_frame_c3.txt: chaosReusePassFloat + compose "
            "(part of the 133 MB of records written and of the 33 MB frame stays in the 126 MB L2)"),
 }
 
@@ -284,6 +286,15 @@ class Job:
             self.dist.barrier()
             self.torch.cuda.synchronize()
 
+    def gather(self, value):
+        """one float per rank -> the list of all ranks' values"""
+        if self.dist is None:
+            return [float(value)]
+        t = self.torch.zeros(self.world, device="cuda", dtype=self.torch.float64)
+        t[self.rank] = float(value)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.tolist()
+
     def reduce(self, values, op="max"):
         if self.dist is None:
             return list(values)
@@ -363,6 +374,7 @@ def timed_quality_loop(job, wl, to_host, steps, warmup, sampler=None):
         frame = (shm.frame.copy() if (shm is not None and to_host) else r.outputRGBA().copy())
     job.barrier()
     slowest = job.reduce(per_step, "max")                    # per step: the slowest rank's frame
+    per_rank = job.gather(sum(per_step) / max(1, len(per_step)))
     wall, render_ms, compose_ms = job.reduce([wall, acc["render_ms"], acc["compose_ms"]], "max")
     iters, skipped, launches, foreign = [int(v) for v in job.reduce([acc["iters"], acc["skipped"], acc["launches"], acc["foreign"]], "sum")]
     if shm is not None:
@@ -371,7 +383,7 @@ def timed_quality_loop(job, wl, to_host, steps, warmup, sampler=None):
         shm.close(job.dist)
     r.freeRenderingResources()
     return dict(device_seconds=sum(slowest) * 1e-3, seconds=wall, iters=iters, skipped=skipped, launches=launches, render_ms=render_ms,
-                compose_ms=compose_ms, clocks=clocks, exchange=exchange, frame=frame, steps=steps, foreign=foreign)
+                compose_ms=compose_ms, clocks=clocks, exchange=exchange, frame=frame, steps=steps, foreign=foreign, per_rank_ms=per_rank)
 
 
 def check_frame(name, frame, constants, what):
@@ -406,6 +418,7 @@ def quality_block(job, name, wl, steps, warmup, constants, sampler=None):
                             "frames_per_s": steps / e2e["seconds"], "h2d_bytes_per_step": 512 * job.world, "d2h_bytes_per_step": px * 4 + 32 * job.world},
                            **check_frame(name, e2e["frame"], constants, "end-to-end")),
                "orbits_redistributed_per_step": dev["foreign"] // steps,
+               "mean_frame_ms_per_rank": [round(v, 4) for v in dev["per_rank_ms"]],
                "gpu_launches": dev["launches"], "parallelism": "1 GPU" if job.world == 1 else
                "row bands of %d px dealt round-robin over %d GPUs; %s" % (BAND_ROWS, job.world, dev["exchange"]),
                "e2e_exchange": e2e["exchange"]}

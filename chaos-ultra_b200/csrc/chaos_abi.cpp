@@ -392,6 +392,7 @@ struct chaos_renderer {
      * independent, so the CTAs of one strand's next pass fill the SMs that the other strand's draining pass leaves idle:
      * the tail of every pass but the last is hidden.  Strand 0 runs on `stream`. */
     uint32_t strands = CHAOS_DEFAULT_STRANDS;
+    uint32_t strand_min_tiles = 50000;   /* vote tiles a strand must have (CHAOS_STRAND_MIN_TILES) */
     /* threads per CTA of the persistent pass kernels (warps are independent there): a CTA gives its SM share back only
      * when its last warp is done, so smaller CTAs let the next pass in sooner */
     uint32_t pass_threads = 256;
@@ -419,6 +420,13 @@ struct chaos_renderer {
      * the single refill launch (c4 35.0 ms against 36.1 with streams: nothing to sort, every orbit is long); several samples
      * with an iteration limit under sync_below_iters -> tile-synchronous kernel; several samples otherwise -> streams */
     uint32_t engine = 3;
+    /* engine 3, several samples, high limit: streams pay off where many orbits are long and never escape (c2: 86 % of the
+     * reference's trips are proven); where every orbit escapes after a few hundred trips (c2ex2: 0.3 %) the restart, the
+     * failed group and the finish replay are a large share of each orbit and the lane-refill engine is 8 % faster.  The
+     * previous multi-sample frame of this renderer says which kind of view this is (frames of a session resemble each
+     * other); the first frame goes through the streams. */
+    float proven_fraction = -1.f;                      /* of the last such frame; < 0: none yet */
+    float streams_above = 0.05f;                       /* CHAOS_STREAMS_ABOVE */
     uint32_t block_iters = 0;      /* 0 = choose from maxIterations */
     uint32_t shortcuts = CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE;   /* count-preserving shortcuts of the escape loop */
     uint32_t sched_idle_indep = 10, sched_idle_rounds = 16;   /* see take_scheduling_pass (render_refill.cuh) */
@@ -643,6 +651,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     /* debugging knobs (not part of the reference's interface): engine 0 is the differential check of engine 1 */
     const char *eng = getenv("CHAOS_ENGINE");
     if (eng) r->engine = (uint32_t)std::min(std::max(atoi(eng), 0), 3);
+    const char *sab = getenv("CHAOS_STREAMS_ABOVE");
+    if (sab) r->streams_above = (float)atof(sab);
     const char *stl = getenv("CHAOS_STEAL");
     if (stl) r->steal = (uint32_t)atoi(stl) ? 1u : 0u;
     const char *lo = getenv("CHAOS_LONG_OCC");
@@ -670,6 +680,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (ea) r->export_all_below = atoi(ea);
     const char *ex = getenv("CHAOS_EXPORT");      /* 0 = every tile keeps all its rounds in pass B */
     if (ex) r->export_enabled = (uint32_t)atoi(ex) ? 1u : 0u;
+    const char *smt = getenv("CHAOS_STRAND_MIN_TILES");
+    if (smt) r->strand_min_tiles = (uint32_t)std::max(atoi(smt), 0);
     const char *sn = getenv("CHAOS_STRANDS");     /* 1 = the passes of a multi-sample frame run one after the other */
     if (sn) r->strands = (uint32_t)std::min(std::max(atoi(sn), 1), CHAOS_MAX_STRANDS);
     const char *pm = getenv("CHAOS_POOL_MIN");    /* 0 = orbits never change warps */
@@ -1318,7 +1330,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters) * CHAOS_MAX_STRANDS, r->stream);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
-    bool early_compose = false;
+    bool early_compose = false, profile_frame = false;
     if (a.n_tiles) {
         const int p = dbl ? 1 : 0;
         const uint32_t S0 = (uint32_t)std::min(64.0f, roundf(m->max_super_sampling));
@@ -1328,7 +1340,9 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         const bool low_limit = S0 >= 2u && a.max_iter < r->sync_below_iters;
         const bool sync_kernel = r->engine == 0 || ((r->engine == 1 || r->engine == 3) && low_limit);
         a.force_exact = r->engine == 0 ? 1u : 0u;
-        const bool streams = r->engine == 2 || (r->engine == 3 && S0 >= 2u && !low_limit);
+        const bool streams = r->engine == 2 || (r->engine == 3 && S0 >= 2u && !low_limit &&
+                                                !(r->proven_fraction >= 0.f && r->proven_fraction < r->streams_above));
+        profile_frame = S0 >= 2u && !low_limit;
         a.probe_trips = r->probe_trips;
         if (streams && !ensure_lists(r, (size_t)((a.tiles_x * (size_t)a.tile_rows)) * (S0 <= 1u ? 32u : 64u)))
             return fail(CHAOS_ERR_CUDA, "cannot allocate the orbit lists of a %ux%u frame", r->width, r->height);
@@ -1373,6 +1387,9 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
             const uint32_t bands = (a.tile_rows + a.band_tile_rows - 1u) / a.band_tile_rows;
             uint32_t G = trace_path ? 1u : r->strands;
             while (G > 1u && (uint64_t)bands < (uint64_t)r->part_count * G * 2u) --G;   /* at least two bands per strand */
+            /* strands overlap the pass chains' tails at the price of twice the launches; a rank of a 4- or 8-GPU frame has so
+             * few tiles that its kernels are short and the launches are what it waits for (one rank of 8: 0.91 against 0.94 ms) */
+            while (G > 1u && (uint64_t)a.n_tiles < (uint64_t)r->strand_min_tiles * G) --G;
             const bool exporting = r->export_enabled && S0 >= 3u && S0 <= CHAOS_EXPORT_ROUNDS && ensure_export(r, a.n_tiles);
             if (exporting && r->overlap_compose) {
                 a.late_tiles = (uint32_t *)r->late_tiles;
@@ -1479,6 +1496,8 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         D->p_cuEventElapsedTime(&early, r->ev[6], r->ev[7]);
         r->stats.compose_ms += early;
     }
+    if (profile_frame && r->stats.pixel_iterations)
+        r->proven_fraction = (float)((double)r->stats.skipped_iterations / (double)r->stats.pixel_iterations);
     r->last = *m; r->have_last = true;                             /* lastRendering = model.copy() */
     r->primary_dirty = false;
     m->sample_reuse_cache_dirty = 0;

@@ -455,6 +455,7 @@ def test_strands_change_nothing(cu, provider, case):
     for key, (strands, threads) in {"one": (1, 256), "two": (2, 256), "three": (3, 128), "eight": (8, 64)}.items():
         os.environ["CHAOS_STRANDS"] = str(strands)
         os.environ["CHAOS_PASS_THREADS"] = str(threads)
+        os.environ["CHAOS_STRAND_MIN_TILES"] = "0"        # (small frames would otherwise run as one chain)
         try:
             provider.getRenderer("test", False)   # drop the active renderer so the knobs are re-read
             r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
@@ -464,6 +465,7 @@ def test_strands_change_nothing(cu, provider, case):
         finally:
             os.environ.pop("CHAOS_STRANDS", None)
             os.environ.pop("CHAOS_PASS_THREADS", None)
+            os.environ.pop("CHAOS_STRAND_MIN_TILES", None)
     for key in ("two", "three", "eight"):
         helpers.assert_records_equal(out[key][0], out["one"][0], case["name"] + " strands " + key)
         assert out[key][1] == out["one"][1] and out[key][2] == out["one"][2]
