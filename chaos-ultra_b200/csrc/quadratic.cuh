@@ -19,8 +19,9 @@
  *    -- 2 MUL + 2 ADD + 2 FMA, one FP64-pipe instruction fewer per trip.  Scaling by a power of two
  *    commutes with round-to-nearest as long as no value is subnormal or overflows.  Overflow cannot
  *    happen before the escape test fails (|z| < 2).  Subnormals are excluded by construction: the
- *    scaled form is used only when cx and cy are non-zero with 2^-400 <= |c| <= 2^400 and the start
- *    point's components are zero or in the same range.  Then every later x is 0 or >= ulp(cx)/2 >=
+ *    scaled form is used only when cx and cy are non-zero with 2^-400 <= |c| <= 2^400 (or cy = 0 with
+ *    y0 = 0: then y is +0 throughout in either form) and the start point's components are zero or in
+ *    the same range.  Then every later x is 0 or >= ulp(cx)/2 >=
  *    2^-453 (a sum of two doubles one of which is cx), every later y is 0 or >= 2^-107 |cy| >= 2^-507
  *    (an exactly formed product-plus-cy), so xx, yy are 0 or >= 2^-1014: normal.  Differences of
  *    nearby normal numbers (xx-yy) are exact in both forms.  Any other orbit takes the 7-operation form.
@@ -128,7 +129,12 @@ template <class Real> struct quadratic_orbit {
     {
         mode = 0u;
         max_iter = ctx.max_iter;
-        if (qb::kCanScale && qb::in_safe_range(pcx) && qb::in_safe_range(pcy) && zero_or_safe(zx) && zero_or_safe(zy)) mode |= kScaled;
+        /* (cy == 0 with y0 == 0, the mandelbrot set's real axis: y stays +0 in both forms -- fma(X, +-0, +0) = +0 -- so every
+         * y-term is an exact zero and the argument about x is untouched.  It matters for speed, not for results: a warp that
+         * holds scaled and unscaled orbits runs both instruction streams one after the other, and the axis row of the full
+         * view is 3840 orbits that never escape and never recur -- the launch's tail.) */
+        const bool cy_ok = qb::in_safe_range(pcy) || (pcy == (Real)0 && zy == (Real)0);
+        if (qb::kCanScale && qb::in_safe_range(pcx) && cy_ok && zero_or_safe(zx) && zero_or_safe(zy)) mode |= kScaled;
         /* |c|^2 < 3.6 (any rounding of this sum is fine, the proof has 5 % to spare) */
         if ((ctx.shortcuts & CHAOS_SHORTCUT_DEFER_TEST) && op::fma(pcx, pcx, op::mul(pcy, pcy)) < (Real)3.6) {
             mode |= kDeferTest;
