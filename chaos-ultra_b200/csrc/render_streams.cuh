@@ -24,6 +24,10 @@
  *   finish   one lane per entry, lock step, at most a group (+ tail) of tested trips from the stored state: finds the
  *            exact trip and delivers.
  *
+ * Two things follow from the loop's latency (one orbit advances a trip per 30 cycles with 2 warps per scheduler, per 97
+ * with 8; tools/loopbench.cu): the long list is handed out LONGEST FIRST where lengths can be guessed (its hot region,
+ * see stream_probe), and the long kernel runs on FEWER WARPS when the list is short (stream_long, occ_orbits_per_lane).
+ *
  * Work items and where results go depend on the pass (chaos_render_args::phase), as in engine 1:
  *   phase 0  one sample per pixel: item = tile; result = the pixel's record;
  *   phase 1  pass A, samples 0 and 1 of every pixel: item = (tile, sample); escape times parked in the record;
