@@ -334,6 +334,7 @@ struct chaos_renderer {
     CUdeviceptr long_list = 0, finish_list = 0;    /* allocated by the first engine-2 frame of a frame size */
     size_t list_capacity = 0;                      /* entries */
     uint32_t probe_trips = 64;
+    uint32_t list_shrink = 1;                      /* CHAOS_LIST_SHRINK=n: the lists take 1/n of their entries (tests: the overflow paths) */
     uint32_t long_occ[3] = {2, 4, 8};             /* chaos_render_args::occ_orbits_per_lane (CHAOS_LONG_OCC=a,b,c; 0,0,0 = always the full grid) */
     uint32_t hot_first = 3;                        /* orbits expected to be long are started first: bit 0 pass C (by sample 0's cost), bit 1 the
                                                     * other passes (survivors of tiles next to the boundary); CHAOS_HOT_FIRST=0: list order */
@@ -659,6 +660,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (lo) { unsigned x = 0, y = 0, z = 0; if (sscanf(lo, "%u,%u,%u", &x, &y, &z) == 3) { r->long_occ[0] = x; r->long_occ[1] = y; r->long_occ[2] = z; } }
     const char *hf = getenv("CHAOS_HOT_FIRST");
     if (hf) r->hot_first = (uint32_t)atoi(hf) & 3u;
+    const char *lsh = getenv("CHAOS_LIST_SHRINK");
+    if (lsh) r->list_shrink = (uint32_t)std::max(atoi(lsh), 1);
     const char *prb = getenv("CHAOS_PROBE_TRIPS");
     if (prb) r->probe_trips = (uint32_t)std::max(atoi(prb), 8);
     const char *sb = getenv("CHAOS_SYNC_BELOW");
@@ -1350,11 +1353,11 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
             st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a, r->stream);
         } else if (S0 <= 1u && streams) {
             a.long_list = (uint2 *)r->long_list; a.finish_list = (void *)r->finish_list;
-            a.list_capacity = (uint32_t)std::min<size_t>((size_t)a.n_tiles * 32u, r->list_capacity);
+            a.list_capacity = (uint32_t)std::min<size_t>((size_t)a.n_tiles * 32u, r->list_capacity) / r->list_shrink;
             a.pool = (unsigned char *)ensure_pool(r, 0);
             a.pool_capacity = r->pool_capacity; a.pool_min_lanes = r->pool_min_lanes; a.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
             a.phase = 0u;
-            if (r->hot_first & 2u) a.hot_capacity = a.list_capacity;
+            if ((r->hot_first & 2u) && r->list_shrink == 1u) a.hot_capacity = a.list_capacity;
             st = launch_stream_chain(r, a, p, r->stream);
         } else if (S0 <= 1u) {
             a.pool = (unsigned char *)ensure_pool(r, 0);
@@ -1425,14 +1428,14 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                 if (streams) {           /* this strand's slice of the orbit lists: two orbits per pixel of its tiles */
                     b.long_list = (uint2 *)r->long_list + (size_t)tile_base * 64u;
                     b.finish_list = (void *)(r->finish_list + (size_t)tile_base * 64u * 32u);
-                    b.list_capacity = b.n_tiles * 64u;
+                    b.list_capacity = b.n_tiles * 64u / r->list_shrink;
                 }
                 tile_base += b.n_tiles;
                 if (b.n_tiles) {
                     const int small_grid = (int)std::min<uint64_t>((b.n_tiles + 255u) / 256u, (uint64_t)r->provider->sm_count * 4u);
                     const int tile_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);   /* one warp per tile */
                     b.phase = 1u;
-                    if (streams && (r->hot_first & 2u)) b.hot_capacity = b.list_capacity;      /* the two ends cannot meet: the list holds every orbit of pass A */
+                    if (streams && (r->hot_first & 2u) && r->list_shrink == 1u) b.hot_capacity = b.list_capacity;   /* the two ends cannot meet: the list holds every orbit of pass A */
                     st = streams ? launch_stream_chain(r, b, p, q) : launch(r, r->k_pass_a[p], r->blocks_pass_a[p], (int)r->pass_threads, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_classify, tile_grid, 256, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &b, q);

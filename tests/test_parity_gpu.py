@@ -472,3 +472,28 @@ def test_strands_change_nothing(cu, provider, case):
         assert (out[key][3] == out["one"][3]).all()
     if case["H"] >= 1000:
         assert out["two"][4] > out["one"][4]      # the frame really ran as several chains
+
+
+# ---- engine 2's lists (render_streams.cuh): a survivor that finds the long list full, or an orbit that finds the finish
+# ---- list full, is finished in place by the kernel that holds it. CHAOS_LIST_SHRINK=n gives the lists 1/n of their entries
+# ---- so that these paths run; records, counters and colours must not notice.
+@pytest.mark.parametrize("case", [EXPORT_CASES[0], EXPORT_CASES[5], SHORTCUT_CASES[0]],
+                         ids=_ids([EXPORT_CASES[0], EXPORT_CASES[5], SHORTCUT_CASES[0]]))
+def test_full_lists_change_nothing(cu, provider, case):
+    out = {}
+    for shrink in (1, 16, 4096):
+        os.environ["CHAOS_LIST_SHRINK"] = str(shrink)
+        os.environ["CHAOS_ENGINE"] = "2"
+        try:
+            provider.getRenderer("test", False)   # drop the active renderer so the knobs are re-read
+            r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_DEVICE)
+            r.renderQuality(helpers.model_for(cu, case))
+            st = r.stats()
+            out[shrink] = (r.downloadRecords(), st.pixel_iterations, st.samples, r.outputRGBA())
+        finally:
+            os.environ.pop("CHAOS_LIST_SHRINK", None)
+            os.environ.pop("CHAOS_ENGINE", None)
+    for shrink in (16, 4096):
+        helpers.assert_records_equal(out[shrink][0], out[1][0], "%s lists / %d" % (case["name"], shrink))
+        assert out[shrink][1] == out[1][1] and out[shrink][2] == out[1][2]
+        assert (out[shrink][3] == out[1][3]).all()
