@@ -349,6 +349,13 @@ struct chaos_renderer {
     int blocks_reuse_f = 0, blocks_reuse_d = 0;
     CUdeviceptr tile_key = 0, tile_order = 0;
     CUdeviceptr warp_trace = 0;         /* diagnostics, CHAOS_WARP_TRACE=<file>: per-warp timeline of pass B */
+    /* diagnostics, CHAOS_TIMELINE=<file>: an event pair around every launch of a frame, written as "kernel stream start_ms end_ms"
+     * (start = when the stream's previous work was through); changes nothing but the frame's host-side cost */
+    struct timeline_entry { const char *name; int stream; CUevent a, b; };
+    std::vector<timeline_entry> timeline;
+    size_t timeline_used = 0;
+    const char *timeline_path = nullptr;
+    std::vector<std::pair<CUfunction, const char *>> fn_names;
     uint32_t sync_below_iters = 2048;   /* see render_quality_locked */
     int blocks_main_f_sync = 0, blocks_main_d_sync = 0;
     uint32_t refill_smem = 0;
@@ -427,6 +434,9 @@ struct chaos_renderer {
      * previous multi-sample frame of this renderer says which kind of view this is (frames of a session resemble each
      * other); the first frame goes through the streams. */
     float proven_fraction = -1.f;                      /* of the last such frame; < 0: none yet */
+    float proven_any = -1.f;                           /* the same of the last quality frame of any kind: below streams_above the orbits' recurrence
+                                                        * check goes back to one compare per group (CHAOS_SHORTCUT_DENSE_COMPARE off; CHAOS_DENSE_COMPARE=0/1 forces) */
+    int dense_compare = -1;
     float streams_above = 0.05f;                       /* CHAOS_STREAMS_ABOVE */
     uint32_t block_iters = 0;      /* 0 = choose from maxIterations */
     uint32_t shortcuts = CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE;   /* count-preserving shortcuts of the escape loop */
@@ -578,9 +588,11 @@ static chaos_status load_module(chaos_renderer *r)
         {"chaosProbeFloat", &r->k_probe[0]}, {"chaosProbeDouble", &r->k_probe[1]}, {"chaosLongFloat", &r->k_long[0]},
         {"chaosLongDouble", &r->k_long[1]}, {"chaosFinishFloat", &r->k_finish[0]}, {"chaosFinishDouble", &r->k_finish[1]},
     };
+    r->fn_names.clear();
     for (auto &k : fns) {
         chaos_status st = get_function(r, k.name, k.fn);
         if (st != CHAOS_OK) { unload_module(r); return st; }
+        r->fn_names.emplace_back(*k.fn, k.name);
     }
     CUdeviceptr abi_ptr = 0;
     size_t abi_size = 0;
@@ -660,6 +672,9 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (lo) { unsigned x = 0, y = 0, z = 0; if (sscanf(lo, "%u,%u,%u", &x, &y, &z) == 3) { r->long_occ[0] = x; r->long_occ[1] = y; r->long_occ[2] = z; } }
     const char *hf = getenv("CHAOS_HOT_FIRST");
     if (hf) r->hot_first = (uint32_t)atoi(hf) & 3u;
+    r->timeline_path = getenv("CHAOS_TIMELINE");
+    const char *dcp = getenv("CHAOS_DENSE_COMPARE");
+    if (dcp) r->dense_compare = atoi(dcp) ? 1 : 0;
     const char *lsh = getenv("CHAOS_LIST_SHRINK");
     if (lsh) r->list_shrink = (uint32_t)std::max(atoi(lsh), 1);
     const char *prb = getenv("CHAOS_PROBE_TRIPS");
@@ -774,7 +789,7 @@ static CUdeviceptr ensure_pool(chaos_renderer *r, uint32_t s)
     return r->pool[s];
 }
 
-/* engine 2: the long and finish lists, `entries` each (8 and 32 bytes per entry) */
+/* engine 2: the long and finish lists, `entries` each, 32 bytes per entry (CHAOS_LIST_STRIDE) */
 static bool ensure_lists(chaos_renderer *r, size_t entries)
 {
     if (r->list_capacity >= entries) return true;
@@ -782,7 +797,7 @@ static bool ensure_lists(chaos_renderer *r, size_t entries)
     if (r->long_list) { D->p_cuMemFree(r->long_list); r->long_list = 0; }
     if (r->finish_list) { D->p_cuMemFree(r->finish_list); r->finish_list = 0; }
     r->list_capacity = 0;
-    if (D->p_cuMemAlloc(&r->long_list, entries * 8u) != CUDA_SUCCESS) { r->long_list = 0; return false; }
+    if (D->p_cuMemAlloc(&r->long_list, entries * 32u) != CUDA_SUCCESS) { r->long_list = 0; return false; }
     if (D->p_cuMemAlloc(&r->finish_list, entries * 32u) != CUDA_SUCCESS) { D->p_cuMemFree(r->long_list); r->long_list = 0; r->finish_list = 0; return false; }
     r->list_capacity = entries;
     return true;
@@ -902,6 +917,8 @@ extern "C" chaos_status chaos_close(chaos_renderer *r)
     if (r->counters) D->p_cuMemFree(r->counters);
     if (r->counters_host) D->p_cuMemFreeHost(r->counters_host);
     for (int i = 0; i < 8; ++i) if (r->ev[i]) D->p_cuEventDestroy(r->ev[i]);
+    for (auto &te : r->timeline) { D->p_cuEventDestroy(te.a); D->p_cuEventDestroy(te.b); }
+    r->timeline.clear();
     if (r->stream2) { D->p_cuStreamSynchronize(r->stream2); D->p_cuStreamDestroy(r->stream2); }
     for (uint32_t i = 0; i < CHAOS_MAX_STRANDS; ++i) {
         if (i && r->strand_stream[i]) { D->p_cuStreamSynchronize(r->strand_stream[i]); D->p_cuStreamDestroy(r->strand_stream[i]); }
@@ -1200,6 +1217,9 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
      * orbit ended does not idle long; orbits are at most max_iter long */
     a->block_iters = r->block_iters ? r->block_iters : 128u;
     a->shortcuts = r->shortcuts;
+    if ((r->shortcuts & CHAOS_SHORTCUT_RECURRENCE) &&
+        (r->dense_compare >= 0 ? r->dense_compare != 0 : !(r->proven_any >= 0.f && r->proven_any < r->streams_above)))
+        a->shortcuts |= CHAOS_SHORTCUT_DENSE_COMPARE;
     a->sched_idle_lanes_indep = r->sched_idle_indep;
     a->sched_idle_lanes_rounds = r->sched_idle_rounds;
     a->sm_count = (uint32_t)r->provider->sm_count;
@@ -1210,7 +1230,24 @@ static void fill_render_args(const chaos_renderer *r, const chaos_params *m, cha
 static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg, CUstream stream)
 {
     void *params[1] = {arg};
-    CUresult e = D->p_cuLaunchKernel(fn, (unsigned)blocks, 1, 1, (unsigned)threads, 1, 1, smem, stream ? stream : r->stream, params, nullptr);
+    CUstream q = stream ? stream : r->stream;
+    chaos_renderer::timeline_entry *te = nullptr;
+    if (r->timeline_path) {
+        if (r->timeline_used == r->timeline.size()) {
+            chaos_renderer::timeline_entry n = {nullptr, 0, nullptr, nullptr};
+            if (D->p_cuEventCreate(&n.a, CU_EVENT_DEFAULT) == CUDA_SUCCESS && D->p_cuEventCreate(&n.b, CU_EVENT_DEFAULT) == CUDA_SUCCESS) r->timeline.push_back(n);
+        }
+        if (r->timeline_used < r->timeline.size()) {
+            te = &r->timeline[r->timeline_used++];
+            te->name = "?";
+            for (auto &k : r->fn_names) if (k.first == fn) te->name = k.second;
+            te->stream = q == r->stream ? 0 : q == r->stream2 ? 9 : 1;
+            for (int i = 0; i < CHAOS_MAX_STRANDS; ++i) if (i && q == r->strand_stream[i]) te->stream = i;
+            D->p_cuEventRecord(te->a, q);
+        }
+    }
+    CUresult e = D->p_cuLaunchKernel(fn, (unsigned)blocks, 1, 1, (unsigned)threads, 1, 1, smem, q, params, nullptr);
+    if (te) D->p_cuEventRecord(te->b, q);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "Error just after launching a kernel:%s", cu_err_name(e));
     r->stats.kernel_launches += 1;
     r->stats.launches_total += 1;
@@ -1260,6 +1297,19 @@ static chaos_status finish_frame(chaos_renderer *r)
     D->p_cuEventElapsedTime(&r->stats.render_ms, r->ev[0], r->ev[1]);
     D->p_cuEventElapsedTime(&r->stats.compose_ms, r->ev[2], r->ev[3]);
     D->p_cuEventElapsedTime(&r->stats.frame_ms, r->ev[0], r->ev[3]);
+    if (r->timeline_path && r->timeline_used) {       /* (diagnostics) the last frame's launches, overwritten every frame */
+        D->p_cuCtxSynchronize();
+        if (FILE *f = fopen(r->timeline_path, "w")) {
+            for (size_t i = 0; i < r->timeline_used; ++i) {
+                float t0 = 0.f, t1 = 0.f;
+                D->p_cuEventElapsedTime(&t0, r->ev[0], r->timeline[i].a);
+                D->p_cuEventElapsedTime(&t1, r->ev[0], r->timeline[i].b);
+                fprintf(f, "%-28s %d %8.4f %8.4f\n", r->timeline[i].name, r->timeline[i].stream, t0, t1);
+            }
+            fclose(f);
+        }
+    }
+    r->timeline_used = 0;
     r->stats.reuse_ms = 0.f;
     r->stats.pixel_iterations = r->stats.samples = r->stats.skipped_iterations = 0;
     r->stats.foreign_orbits = r->counters_host[0].foreign_done;
@@ -1278,6 +1328,22 @@ static chaos_status finish_frame(chaos_renderer *r)
             if (r->counters_host[s].next_tile)
                 fprintf(stderr, "strand %u: tiles after sample 1: to pass B %u, exported (by the classifier or pass B) %u\n", s,
                         r->counters_host[s].n_continuing, r->counters_host[s].n_exported);
+        for (uint32_t s = 0; s < CHAOS_MAX_STRANDS; ++s) for (int w = 0; w < 2; ++w) {      /* the long kernels' timeline (engine 2) */
+            unsigned long long *v = &r->counters_host[s].lane_stats[3][1][w * 4];
+            if (!v[3]) continue;
+            const double t0 = (double)~v[0];
+            fprintf(stderr, "strand %u long kernel %c: first warp saw the list dry after %.3f ms, last warp after %.3f ms, last warp ended after %.3f ms\n",
+                    s, w ? 'C' : 'A', v[1] ? ((double)~v[1] - t0) * 1e-6 : -1.0, ((double)v[2] - t0) * 1e-6, ((double)v[3] - t0) * 1e-6);
+            v[0] = v[1] = v[2] = v[3] = 0ull;
+            unsigned long long *u = &r->counters_host[s].lane_stats[3][0][w * 4];
+            if (u[0]) fprintf(stderr, "strand %u long kernel %c: %llu orbits ran all the way unproven: mean %.3f ms, longest %.3f ms, the last one started after %.3f ms\n",
+                              s, w ? 'C' : 'A', u[0], (double)u[1] / (double)u[0] * 1e-6, (double)u[2] * 1e-6, (double)u[3] * 1e-6);
+            u[0] = u[1] = u[2] = u[3] = 0ull;
+            unsigned long long *h = &r->counters_host[s].lane_stats[1][w][0];
+            fprintf(stderr, "strand %u long kernel %c: orbits that ran (nearly) all the way, by when they were taken from the list (0.131 ms bins): %llu %llu %llu %llu %llu %llu %llu %llu\n",
+                    s, w ? 'C' : 'A', h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+            for (int k = 0; k < 8; ++k) h[k] = 0ull;
+        }
         static const char *pass[4] = {"A", "B", "C", "main"}, *kind[2] = {"tested", "untested"};
         for (int p = 0; p < 4; ++p) for (int t = 0; t < 2; ++t) {
             unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1352,7 +1418,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         if (sync_kernel) {
             st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a, r->stream);
         } else if (S0 <= 1u && streams) {
-            a.long_list = (uint2 *)r->long_list; a.finish_list = (void *)r->finish_list;
+            a.long_list = (void *)r->long_list; a.finish_list = (void *)r->finish_list;
             a.list_capacity = (uint32_t)std::min<size_t>((size_t)a.n_tiles * 32u, r->list_capacity) / r->list_shrink;
             a.pool = (unsigned char *)ensure_pool(r, 0);
             a.pool_capacity = r->pool_capacity; a.pool_min_lanes = r->pool_min_lanes; a.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
@@ -1426,7 +1492,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     b.exp.iters += (size_t)tile_base * CHAOS_EXPORT_ROUNDS; b.exp.skipped += (size_t)tile_base * CHAOS_EXPORT_ROUNDS;
                 }
                 if (streams) {           /* this strand's slice of the orbit lists: two orbits per pixel of its tiles */
-                    b.long_list = (uint2 *)r->long_list + (size_t)tile_base * 64u;
+                    b.long_list = (void *)(r->long_list + (size_t)tile_base * 64u * 32u);
                     b.finish_list = (void *)(r->finish_list + (size_t)tile_base * 64u * 32u);
                     b.list_capacity = b.n_tiles * 64u / r->list_shrink;
                 }
@@ -1501,6 +1567,8 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     }
     if (profile_frame && r->stats.pixel_iterations)
         r->proven_fraction = (float)((double)r->stats.skipped_iterations / (double)r->stats.pixel_iterations);
+    if (r->stats.pixel_iterations && (r->shortcuts & CHAOS_SHORTCUT_RECURRENCE))
+        r->proven_any = (float)((double)r->stats.skipped_iterations / (double)r->stats.pixel_iterations);
     r->last = *m; r->have_last = true;                             /* lastRendering = model.copy() */
     r->primary_dirty = false;
     m->sample_reuse_cache_dirty = 0;

@@ -15,7 +15,7 @@
 struct uint2 { unsigned int x, y; };   /* host side of the launch contract (vector_types.h is CUDA-only) */
 #endif
 
-#define CHAOS_MODULE_ABI 31u
+#define CHAOS_MODULE_ABI 35u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -35,6 +35,8 @@ struct chaos_pixel_info {
 /* count-preserving shortcuts of the escape loop (quadratic.cuh items 3 and 4) */
 #define CHAOS_SHORTCUT_DEFER_TEST (1u << 0)  /* test the escape condition once per group of trips, replay on failure */
 #define CHAOS_SHORTCUT_RECURRENCE (1u << 1)  /* an orbit whose state recurs bit for bit is reported as never escaping */
+#define CHAOS_SHORTCUT_DENSE_COMPARE (1u << 2)  /* ... and is compared with its kept state every 8 trips, not only at group ends (set by the
+                                                  * host unless the renderer's previous frame proved next to nothing: quadratic.cuh) */
 
 /* device counters, one block per renderer (zeroed by the host before each render call) */
 #define CHAOS_MAX_PEERS 8          /* ranks of one NVSwitch domain */
@@ -147,8 +149,8 @@ struct chaos_render_args {
     uint32_t fuse_palette_len;
     uint32_t pool_epoch;               /* distinguishes this launch's entries from older ones (host: += 2 per frame; pass C uses epoch + 1) */
     /* engine 2 (render_streams.cuh) */
-    uint2 *long_list;                  /* [list_capacity] destination words of the orbits that outlived the probe */
-    void *finish_list;                 /* [list_capacity] finish_item<Real>: orbits that need a last group of tested trips */
+    void *long_list;                   /* [list_capacity] finish_item<Real>, 32 bytes apart: the orbits that outlived the probe, with their state */
+    void *finish_list;                 /* [list_capacity] finish_item<Real>, 32 bytes apart: orbits that need a last group of tested trips */
     uint32_t list_capacity;
     uint32_t probe_trips;              /* tested trips an orbit gets in the probe kernel before it goes to the long list */
     /* Multi-GPU fast frames: the frame is cut into one slab of slab_rows pixel rows per rank (slab q = rows q * slab_rows ...),

@@ -57,8 +57,9 @@
  *    The orbit reports i = maxIterations at once -- the very value the reference arrives at, not an
  *    approximation; an orbit that does not close exactly (chaotic boundary points, |multiplier| close to 1)
  *    simply runs on.  One earlier state is kept, replaced at trip counts growing by 1.25x (Brent's scheme), and
- *    compared once per group on the integer pipe.  A cycle of period p is seen when the distance to the kept
- *    state is a common multiple of p and kGroup.  skipped() tells the engine how many trips were proven
+ *    compared every kCompareEvery = 8 trips on the integer pipe (the outcome is looked at once per group, after the
+ *    group's test).  A cycle of period p is seen when the distance to the kept state is a common multiple of p and
+ *    kCompareEvery.  skipped() tells the engine how many trips were proven
  *    instead of executed, so executed work is reported separately from the reference-equivalent count.
  *
  * The "below 4" test itself reads the high word of the sum on the integer pipe (see real_ops).
@@ -79,6 +80,14 @@
 #define CHAOS_GROUP_LOOP_UNROLL 1   /* groups per iteration of the untested loop (the copies that keep the state before a group
                                      * alive are made once per iteration) */
 #endif
+#ifndef CHAOS_COMPARE_EVERY
+#define CHAOS_COMPARE_EVERY 8   /* the state is compared with the kept state every so many trips of a group (a power of two up to the group).  The kept state is taken at a group boundary, so a cycle of period p
+                                 * shows when the distance to it is a common multiple of p and this number -- and the cycles that computed
+                                 * orbits end in have all sorts of periods (rounding noise around an attracting point), so comparing at group
+                                 * ends only (32) waits for a distance of lcm(p, 32).  Executed trips of a c2-like frame by this number
+                                 * (host model of the scheme): 32: 94.6 M, 16: 82.7 M, 8: 77.2 M, 4: 75.8 M, 1: 75.4 M; orbits that run
+                                 * all 10 000 trips unproven: 1699, 1523, 1465, 1444, 1440.  A compare is 4 LOP3 + 1 min on the integer side. */
+#endif
 #ifndef CHAOS_SAVE_SHIFT
 #define CHAOS_SAVE_SHIFT 2   /* the kept state of the recurrence check is replaced at trip counts growing by 1 + 2^-shift.
                               * Executed trips of c2 by shift: 0: 5.98 G, 1: 5.62 G, 2: 5.63 G, 3: 5.97 G, 4: 6.88 G, 5: 8.39 G
@@ -91,6 +100,11 @@ template <> struct quad_bits<float> {
     static __device__ __forceinline__ bool in_safe_range(float) { return false; }
     static __device__ __forceinline__ bool below16(float s) { return s < 16.0f; }
     static __device__ __forceinline__ bool same(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
+    /* 0 iff (x, y) and (sx, sy) are the same bit patterns (integer pipe) */
+    static __device__ __forceinline__ uint32_t differs(float x, float y, float sx, float sy)
+    {
+        return (__float_as_uint(x) ^ __float_as_uint(sx)) | (__float_as_uint(y) ^ __float_as_uint(sy));
+    }
     static __device__ __forceinline__ float never() { return __uint_as_float(0x7fc00000u); }
 };
 template <> struct quad_bits<double> {
@@ -105,6 +119,11 @@ template <> struct quad_bits<double> {
     {
         return ((__double2hiint(a) ^ __double2hiint(b)) | (__double2loint(a) ^ __double2loint(b))) == 0;
     }
+    static __device__ __forceinline__ uint32_t differs(double x, double y, double sx, double sy)
+    {
+        return (uint32_t)((__double2hiint(x) ^ __double2hiint(sx)) | (__double2loint(x) ^ __double2loint(sx)) |
+                          (__double2hiint(y) ^ __double2hiint(sy)) | (__double2loint(y) ^ __double2loint(sy)));
+    }
     static __device__ __forceinline__ double never() { return __hiloint2double(0x7ff80000, 0); }
 };
 
@@ -112,10 +131,11 @@ template <class Real> struct quadratic_orbit {
     typedef real_ops<Real> op;
     typedef quad_bits<Real> qb;
     static constexpr bool kResumable = true;
-    static constexpr uint32_t kScaled = 1u, kDeferTest = 2u, kDetectCycle = 4u, kPeriodic = 8u, kReplay = 16u;
+    static constexpr uint32_t kScaled = 1u, kDeferTest = 2u, kDetectCycle = 4u, kPeriodic = 8u, kReplay = 16u, kDense = 32u;
     static constexpr uint32_t kGroup = CHAOS_GROUP;   /* untested trips per group (power of two) */
     static constexpr int kGroupUnroll = CHAOS_GROUP_UNROLL;
     static constexpr int kLoopUnroll = CHAOS_GROUP_LOOP_UNROLL;
+    static constexpr int kCompareEvery = CHAOS_COMPARE_EVERY;
 
     Real x, y, cx, cy;      /* kScaled: 2x, 2y, 2cx, 2cy */
     Real sx, sy;            /* the earlier state the orbit is compared with (kDetectCycle) */
@@ -139,6 +159,7 @@ template <class Real> struct quadratic_orbit {
         if ((ctx.shortcuts & CHAOS_SHORTCUT_DEFER_TEST) && op::fma(pcx, pcx, op::mul(pcy, pcy)) < (Real)3.6) {
             mode |= kDeferTest;
             if (ctx.shortcuts & CHAOS_SHORTCUT_RECURRENCE) mode |= kDetectCycle;
+            if ((mode & kDetectCycle) && (ctx.shortcuts & CHAOS_SHORTCUT_DENSE_COMPARE)) mode |= kDense;
         }
         const Real k = (mode & kScaled) ? (Real)2 : (Real)1;   /* exact */
         x = op::mul(zx, k); y = op::mul(zy, k); cx = op::mul(pcx, k); cy = op::mul(pcy, k);
@@ -216,14 +237,25 @@ template <class Real> struct quadratic_orbit {
             return run_tested<kS>(i, limit);
         }
         if (mode & kReplay) return false;           /* waits for a tested phase */
+        /* (the same for every orbit of a launch: one instruction stream per warp either way) */
+        return (mode & kDense) ? run_groups<kS, kCompareEvery>(i, limit) : run_groups<kS, (int)kGroup>(i, limit);
+    }
+    /* untested groups while a whole one fits below `limit`; the state is compared with the kept one every kEvery trips */
+    template <bool kS, int kEvery> __device__ __forceinline__ bool run_groups(uint32_t &i, uint32_t limit)
+    {
+        static_assert(kEvery > 0 && (kEvery & (kEvery - 1)) == 0 && kEvery <= (int)kGroup, "compare points: a power of two up to the group");
         Real xx = op::mul(x, x), yy = op::mul(y, y);
 #pragma unroll kLoopUnroll
         while (i + kGroup <= limit) {
             const Real bx = x, by = y;
+            uint32_t apart = 0xffffffffu;           /* 0 once the state was the kept state at one of the group's compare points */
 #pragma unroll kGroupUnroll
             for (uint32_t r = 0; r < kGroup / 8u; ++r) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) advance<kS>(xx, yy);
+                for (int k = 0; k < 8; ++k) {
+                    advance<kS>(xx, yy);
+                    if ((r * 8u + (uint32_t)k + 1u) % (uint32_t)kEvery == 0u) apart = min(apart, qb::differs(x, y, sx, sy));
+                }
             }
             if (!below<kS>(op::add(xx, yy))) {      /* a test among trips i .. i+kGroup fails: back to the state before the group */
                 x = bx; y = by;
@@ -232,7 +264,7 @@ template <class Real> struct quadratic_orbit {
             }
             i += kGroup;
             if (mode & kDetectCycle) {
-                if (qb::same(x, sx) && qb::same(y, sy)) {   /* exactly periodic: the loop runs to maxIterations */
+                if (apart == 0u) {          /* exactly periodic (and the group's test passed): the loop runs to maxIterations */
                     mode |= kPeriodic;
                     next_save = i;
                     i = max_iter;

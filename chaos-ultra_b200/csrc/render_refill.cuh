@@ -163,9 +163,9 @@ struct lane_stats {
         }
     }
 };
-#define CHAOS_LS(x) x
+#define CHAOS_LS(...) __VA_ARGS__
 #else
-#define CHAOS_LS(x)
+#define CHAOS_LS(...)
 #endif
 
 template <class Orbit>

@@ -11,9 +11,9 @@
  *
  *   probe    one warp per work item (a vote tile, or a (tile, sample) pair), lane = pixel, lock step: every orbit's
  *            first trips with a test per trip (quadratic.cuh step()).  Orbits that end -- most of a frame's orbits --
- *            deliver their result.  The survivors are appended to the LONG list (8 bytes each: where the result
- *            goes; the orbit is restarted from its plane point, which is cheaper than carrying its state through
- *            memory).  A tile in which nobody has ended after CHAOS_PROBE_BAIL trips stops probing: deep inside or
+ *            deliver their result.  The survivors are appended to the LONG list (32 bytes each: where the result
+ *            goes, the trips run and the state after them -- restarting an orbit from its plane point instead costs its
+ *            first 64 trips a second time, a seventh of c2's executed trips).  A tile in which nobody has ended after CHAOS_PROBE_BAIL trips stops probing: deep inside or
  *            deep zoom, every pixel is long.
  *   long     persistent warps, lane refill from the long list (one atomicAdd per warp and refill, the n-th idle lane
  *            takes the n-th claimed entry).  ONLY the untested stream: groups of 32 trips of 5 FP64 instructions, one
@@ -42,11 +42,19 @@
 
 #define CHAOS_PROBE_BAIL 16u     /* probe trips after which a tile in which no orbit has ended goes to the long list as it is */
 
-template <class Real> struct finish_item {
+/* an orbit on its way from one kernel to the next (long list: after the probe's trips; finish list: before the group that
+ * failed).  Entries of both lists are CHAOS_LIST_STRIDE bytes apart whatever Real is. */
+template <class Real> struct alignas(16) finish_item {
     uint32_t a, b;      /* destination, see stream_dest */
-    uint32_t it, pad;
-    Real x, y;          /* orbit state (Orbit::save) before the group that failed */
+    uint32_t it, pad;   /* trips run so far */
+    Real x, y;          /* orbit state (Orbit::save) after them */
 };
+#define CHAOS_LIST_STRIDE 32u
+static_assert(sizeof(finish_item<double>) == CHAOS_LIST_STRIDE && sizeof(finish_item<float>) == CHAOS_LIST_STRIDE, "list entries are 32 bytes");
+template <class Real> static __device__ __forceinline__ finish_item<Real> *list_entry(void *list, uint32_t idx)
+{
+    return reinterpret_cast<finish_item<Real> *>(static_cast<char *>(list) + (size_t)idx * CHAOS_LIST_STRIDE);
+}
 
 /* the three ways a result is addressed, packed into two words */
 struct stream_dest {
@@ -127,6 +135,14 @@ struct stream_totals {
 };
 
 /* ---- probe ------------------------------------------------------------------------------------------------ */
+template <class Real, class Orbit>
+static __device__ __forceinline__ void put_survivor(void *list, uint32_t idx, stream_dest d, uint32_t it, const Orbit &o)
+{
+    finish_item<Real> f;
+    f.a = d.a; f.b = d.b; f.it = it; f.pad = 0u;
+    o.save(f.x, f.y);
+    *list_entry<Real>(list, idx) = f;
+}
 template <class Real, class FractalT>
 static __device__ void stream_probe(const chaos_render_args &a)
 {
@@ -194,7 +210,12 @@ static __device__ void stream_probe(const chaos_render_args &a)
          *           deep inside or deep in a zoom, where every orbit is alike.
          * Orbits expected to be long go to the list's hot region (its END, growing down), which the long kernel hands out
          * first.  Pass A and the one-sample pass cannot overflow the list (it holds every orbit they have), so there the two
-         * ends cannot meet; pass C reserves the hot region (hot_capacity entries). */
+         * ends cannot meet; pass C reserves the hot region (hot_capacity entries).
+         * (Measured and removed: guessing the length from the orbit's rate of convergence -- the ratio of |z(64) - z(48)|^2 to
+         * |z(48) - z(32)|^2 is |multiplier|^32 -- with a third region for the longest.  It does what it should: of c2's 46 000
+         * orbits per pass that run all 10 000 trips, 92 % then start in the first 0.4 ms of the long kernel instead of evenly
+         * over its 0.85 ms; the kernel is not shorter for it, because its last 0.4 ms belong to the few hundred long orbits any
+         * guess misses) */
         bool hot = false;
         if (a.hot_capacity && inb && !ended)
             hot = pass_c ? __float_as_uint(record_at(a.out, a.out_pitch, px, py)->weight_of_new_samples) >= a.hot_trips : !bailed;
@@ -205,7 +226,7 @@ static __device__ void stream_probe(const chaos_render_args &a)
             base = __shfl_sync(CHAOS_FULL_MASK, base, 0);
             if (hot) {
                 const uint32_t idx = base + __popc(surv_hot & lanemask_lt());
-                if (idx < a.hot_capacity) a.long_list[a.list_capacity - 1u - idx] = make_uint2(d.a, d.b);
+                if (idx < a.hot_capacity) put_survivor<Real>(a.long_list, a.list_capacity - 1u - idx, d, it, o);
                 else hot = false;                                   /* region full: an ordinary entry */
             }
         }
@@ -217,7 +238,7 @@ static __device__ void stream_probe(const chaos_render_args &a)
             if (inb && !ended && !hot) {
                 const uint32_t idx = base + __popc(surv & lanemask_lt());
                 if (idx < a.list_capacity - (pass_c ? a.hot_capacity : 0u)) {
-                    a.long_list[idx] = make_uint2(d.a, d.b);
+                    put_survivor<Real>(a.long_list, idx, d, it, o);
                 } else {                 /* list full (never with the host's sizing for passes 0 and A): the orbit is finished here */
                     run_whole(o, it, max_iter);
                     sf.deliver(a, d, o.finish(it, max_iter), it, o.skipped());
@@ -338,6 +359,7 @@ template <class Rec> struct stream_pool {
 template <class Orbit> struct stream_parked {
     Orbit o;
     uint32_t it, a, b;
+    CHAOS_LS(unsigned long long tt;)      /* (diagnostics) when the orbit was taken from the list */
 };
 template <class Real, class FractalT>
 static __device__ void stream_long(const chaos_render_args &a)
@@ -362,7 +384,6 @@ static __device__ void stream_long(const chaos_render_args &a)
         const uint32_t per_lane = n / (gridDim.x * blockDim.x);
         if (layer >= 1u && per_lane < a.occ_orbits_per_lane[min(layer, 3u) - 1u]) return;
     }
-    fin_t *const finish_list = reinterpret_cast<fin_t *>(a.finish_list);
     const uint32_t max_debt = max(a.sched_idle_lanes_indep, 1u) * 64u;
     stream_totals tot = {0ull, 0ull, 0ull};
     stream_pool<parked_t> pool;
@@ -377,7 +398,10 @@ static __device__ void stream_long(const chaos_render_args &a)
     bool dry = n == 0u, keep_all = false;
     uint32_t debt = 0, drain_wait = 0, park_cooldown = 0;
     CHAOS_LS(lane_stats ls; ls.init();)
+    CHAOS_LS(unsigned long long tt_orbit = 0ull;)
+    CHAOS_LS(unsigned long long tt_start, tt_dry = 0ull; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt_start));)
     for (;;) {
+        CHAOS_LS(if (dry && !tt_dry) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt_dry));)
         CHAOS_LS(ls.before(busy, fin || stall, false, false, dry, it);)
         if (busy && !fin && !stall) {
             const uint32_t lim = min(it + nb, max_iter);
@@ -400,11 +424,18 @@ static __device__ void stream_long(const chaos_render_args &a)
         debt = 0u; drain_wait = 0u;
         CHAOS_LS(ls.pass();)
         /* retire */
+        CHAOS_LS(if (fin && it >= max_iter && !o.skipped() && a.phase != 0u) {      /* (diagnostics) the orbits that ran all the way */
+            unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            unsigned long long *w = &a.counters->lane_stats[3][0][which * 4u];
+            atomicAdd(w + 0, 1ull); atomicAdd(w + 1, now - tt_orbit); atomicMax(w + 2, now - tt_orbit); atomicMax(w + 3, tt_orbit - tt_start);
+            atomicAdd(&a.counters->lane_stats[1][which][min((tt_orbit - tt_start) >> 17, 7ull)], 1ull);       /* when they started, 0.131 ms bins */
+        })
         if (fin) {
             sf.deliver(a, d, o.finish(it, max_iter), it, o.skipped());
             tot.add(it, o.skipped());
             fin = false; busy = false;
         }
+        CHAOS_LS(if (stall && max_iter - it < 32u && a.phase != 0u) atomicAdd(&a.counters->lane_stats[1][which][min((tt_orbit - tt_start) >> 17, 7ull)], 1ull);)
         const uint32_t stalled = __ballot_sync(CHAOS_FULL_MASK, stall);
         if (stalled) {
             uint32_t base = 0;
@@ -416,7 +447,7 @@ static __device__ void stream_long(const chaos_render_args &a)
                     fin_t f;
                     f.a = d.a; f.b = d.b; f.it = it; f.pad = 0u;
                     o.save(f.x, f.y);
-                    finish_list[idx] = f;
+                    *list_entry<Real>(a.finish_list, idx) = f;
                 } else {                 /* list full: the tested trips are run here */
                     o.run(it, max_iter, true);
                     sf.deliver(a, d, o.finish(it, max_iter), it, o.skipped());
@@ -434,13 +465,15 @@ static __device__ void stream_long(const chaos_render_args &a)
             base = __shfl_sync(CHAOS_FULL_MASK, base, 0);
             const uint32_t idx = base + __popc(idle & lanemask_lt());
             if (!busy && idx < n) {
-                const uint2 ent = a.long_list[idx < n_hot ? a.list_capacity - 1u - idx : idx - n_hot];
-                d.a = ent.x; d.b = ent.y;
+                const fin_t ent = *list_entry<Real>(a.long_list, idx < n_hot ? a.list_capacity - 1u - idx : idx - n_hot);
+                d.a = ent.a; d.b = ent.b;
                 uint32_t px, py, rnd;
                 sf.decode(a, d, px, py, rnd);
                 sf.start(o, px, py, rnd, ctx);
-                it = 0;
+                o.resume(ent.x, ent.y);          /* goes on where the probe stopped */
+                it = ent.it;
                 busy = true;
+                CHAOS_LS(asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt_orbit));)
             }
             if (base + cnt >= n) dry = true;
         }
@@ -448,12 +481,13 @@ static __device__ void stream_long(const chaos_render_args &a)
             if (park_cooldown) --park_cooldown;
             for (int again = 0; again < 2; ++again) {
                 parked_t rec;
-                if (pool.claim(!busy, rec)) { o = rec.o; it = rec.it; d.a = rec.a; d.b = rec.b; busy = true; }
+                if (pool.claim(!busy, rec)) { o = rec.o; it = rec.it; d.a = rec.a; d.b = rec.b; busy = true; CHAOS_LS(tt_orbit = rec.tt;) }
                 /* too few orbits left for a whole warp's issue slots: park them all, then claim a warpful */
                 const uint32_t n_run = (uint32_t)__popc(__ballot_sync(CHAOS_FULL_MASK, busy));
                 if (again || !n_run || n_run >= a.pool_min_lanes || keep_all || park_cooldown) break;
                 park_cooldown = CHAOS_PARK_COOLDOWN;
                 rec.o = o; rec.it = it; rec.a = d.a; rec.b = d.b;
+                CHAOS_LS(rec.tt = tt_orbit;)
                 if (!pool.park(busy, rec)) break;
                 busy = false;
             }
@@ -465,6 +499,12 @@ static __device__ void stream_long(const chaos_render_args &a)
     }
     tot.flush(a);
     CHAOS_LS(ls.flush(a, a.phase == 1u ? 0 : a.phase == 3u ? 2 : 3);)
+    /* (diagnostics) when the launch's warps started, saw the list dry, and ended: min / max over the warps, as ~t for the minima */
+    CHAOS_LS(if (lane == 0u && a.phase != 0u) {
+        unsigned long long tt_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt_end));
+        unsigned long long *w = &a.counters->lane_stats[3][1][which * 4u];
+        atomicMax(w + 0, ~tt_start); if (tt_dry) { atomicMax(w + 1, ~tt_dry); atomicMax(w + 2, tt_dry); } atomicMax(w + 3, tt_end);
+    })
 }
 
 /* ---- finish ----------------------------------------------------------------------------------------------- */
@@ -480,10 +520,9 @@ static __device__ void stream_finish(const chaos_render_args &a)
     const orbit_ctx ctx = {a.max_iter, a.shortcuts};
     chaos_stream_ctl *ctl = &a.counters->stream[a.phase == 3u ? 1 : 0];
     const uint32_t n = min(ctl->n_finish, a.list_capacity);
-    const fin_t *const finish_list = reinterpret_cast<const fin_t *>(a.finish_list);
     stream_totals tot = {0ull, 0ull, 0ull};
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-        const fin_t f = finish_list[idx];
+        const fin_t f = *list_entry<Real>(a.finish_list, idx);
         stream_dest d = {f.a, f.b};
         uint32_t px, py, rnd;
         sf.decode(a, d, px, py, rnd);

@@ -497,3 +497,4 @@ def test_full_lists_change_nothing(cu, provider, case):
         helpers.assert_records_equal(out[shrink][0], out[1][0], "%s lists / %d" % (case["name"], shrink))
         assert out[shrink][1] == out[1][1] and out[shrink][2] == out[1][2]
         assert (out[shrink][3] == out[1][3]).all()
+
