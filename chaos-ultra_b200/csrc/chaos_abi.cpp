@@ -1343,6 +1343,14 @@ static chaos_status finish_frame(chaos_renderer *r)
             fprintf(stderr, "strand %u long kernel %c: orbits that ran (nearly) all the way, by when they were taken from the list (0.131 ms bins): %llu %llu %llu %llu %llu %llu %llu %llu\n",
                     s, w ? 'C' : 'A', h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
             for (int k = 0; k < 8; ++k) h[k] = 0ull;
+            fprintf(stderr, "strand %u long kernel %c over time: warps alive at 0, 65.5, 131 ... us:", s, w ? 'C' : 'A');
+            for (int k = 0; k < 32; ++k) if (r->counters_host[s].long_hist[w][0][k]) fprintf(stderr, " %llu", r->counters_host[s].long_hist[w][0][k]);
+            fprintf(stderr, "\n");
+            {
+                unsigned long long *c = &r->counters_host[s].long_hist[w][3][0];
+                if (c[1]) fprintf(stderr, "   inside the loop, list not dry: %.1f cycles per trip (%llu calls); dry: %.1f cycles per trip (%llu calls)\n",
+                                  (double)c[0] / (double)c[1], c[2], c[5] ? (double)c[4] / (double)c[5] : 0.0, c[6]);
+            }
         }
         static const char *pass[4] = {"A", "B", "C", "main"}, *kind[2] = {"tested", "untested"};
         for (int p = 0; p < 4; ++p) for (int t = 0; t < 2; ++t) {

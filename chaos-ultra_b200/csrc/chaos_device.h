@@ -15,7 +15,7 @@
 struct uint2 { unsigned int x, y; };   /* host side of the launch contract (vector_types.h is CUDA-only) */
 #endif
 
-#define CHAOS_MODULE_ABI 35u
+#define CHAOS_MODULE_ABI 37u
 
 /* helpers.cuh:106-130 -- the 16-byte record both frame buffers hold */
 struct chaos_pixel_info {
@@ -69,6 +69,9 @@ struct chaos_counters {
      * escape loop by what the lane was doing, [pass A/B/C/main][tested, untested][CHAOS_LS_*] */
     unsigned long long lane_stats[4][2][8];
     chaos_stream_ctl stream[2];         /* engine 2: [0] one-sample frame or pass A, [1] pass C */
+    /* diagnostics (CHAOS_LANE_STATS modules), [pass A, pass C]: [0] warps of the long kernel alive per 65.5 us bin; [3] cycles
+     * inside the loop / trips of its longest lane / calls, before ([0..2]) and after ([4..6]) the list ran dry */
+    unsigned long long long_hist[2][4][32];
     /* cross-GPU tile stealing (one-sample frames, render_refill.cuh): this rank's tile cursor (next_tile) is open to the
      * other ranks once frame_seq says the counters belong to the current frame; orbits finished here / by other ranks */
     unsigned int frame_seq;

@@ -57,9 +57,10 @@
  *    The orbit reports i = maxIterations at once -- the very value the reference arrives at, not an
  *    approximation; an orbit that does not close exactly (chaotic boundary points, |multiplier| close to 1)
  *    simply runs on.  One earlier state is kept, replaced at trip counts growing by 1.25x (Brent's scheme), and
- *    compared every kCompareEvery = 8 trips on the integer pipe (the outcome is looked at once per group, after the
+ *    compared every kCompareEvery = 16 (FP32: 8) trips on the integer pipe when the host sets
+ *    CHAOS_SHORTCUT_DENSE_COMPARE, else once per group (the outcome is looked at once per group either way, after the
  *    group's test).  A cycle of period p is seen when the distance to the kept state is a common multiple of p and
- *    kCompareEvery.  skipped() tells the engine how many trips were proven
+ *    the compare distance.  skipped() tells the engine how many trips were proven
  *    instead of executed, so executed work is reported separately from the reference-equivalent count.
  *
  * The "below 4" test itself reads the high word of the sum on the integer pipe (see real_ops).
@@ -80,13 +81,19 @@
 #define CHAOS_GROUP_LOOP_UNROLL 1   /* groups per iteration of the untested loop (the copies that keep the state before a group
                                      * alive are made once per iteration) */
 #endif
-#ifndef CHAOS_COMPARE_EVERY
-#define CHAOS_COMPARE_EVERY 8   /* the state is compared with the kept state every so many trips of a group (a power of two up to the group).  The kept state is taken at a group boundary, so a cycle of period p
-                                 * shows when the distance to it is a common multiple of p and this number -- and the cycles that computed
-                                 * orbits end in have all sorts of periods (rounding noise around an attracting point), so comparing at group
-                                 * ends only (32) waits for a distance of lcm(p, 32).  Executed trips of a c2-like frame by this number
-                                 * (host model of the scheme): 32: 94.6 M, 16: 82.7 M, 8: 77.2 M, 4: 75.8 M, 1: 75.4 M; orbits that run
-                                 * all 10 000 trips unproven: 1699, 1523, 1465, 1444, 1440.  A compare is 4 LOP3 + 1 min on the integer side. */
+/* With CHAOS_SHORTCUT_DENSE_COMPARE the state is compared with the kept state every so many trips of a group (a power of
+ * two up to the group).  The kept state is taken at a group boundary, so a cycle of period p shows when the distance to it
+ * is a common multiple of p and this number -- and the cycles that computed orbits end in have all sorts of periods
+ * (rounding noise around an attracting point), so comparing at group ends only waits for a distance of lcm(p, 32).
+ * Executed trips of c2 by this number: 32: 5.35 G, 16: 4.86 G, 8: 4.62 G (host model: 4: -2 %, 1: -2.5 % more); frame 3.03 /
+ * 2.92 / 2.91 ms; FP32 2.12 / 1.96 / 1.88 ms.  A compare is 4 LOP3 + 1 min (FP32: 2 + 1) on the integer side of a loop that
+ * is bound by the FP64 pipe only when every trip is needed: frames without provable orbits (c4, c2 "M ex 2") lose 2 % / 5 %
+ * with 16 / 8, so the host drops the flag when the renderer's previous frame proved next to nothing. */
+#ifndef CHAOS_COMPARE_EVERY_F64
+#define CHAOS_COMPARE_EVERY_F64 16
+#endif
+#ifndef CHAOS_COMPARE_EVERY_F32
+#define CHAOS_COMPARE_EVERY_F32 8
 #endif
 #ifndef CHAOS_SAVE_SHIFT
 #define CHAOS_SAVE_SHIFT 2   /* the kept state of the recurrence check is replaced at trip counts growing by 1 + 2^-shift.
@@ -135,7 +142,7 @@ template <class Real> struct quadratic_orbit {
     static constexpr uint32_t kGroup = CHAOS_GROUP;   /* untested trips per group (power of two) */
     static constexpr int kGroupUnroll = CHAOS_GROUP_UNROLL;
     static constexpr int kLoopUnroll = CHAOS_GROUP_LOOP_UNROLL;
-    static constexpr int kCompareEvery = CHAOS_COMPARE_EVERY;
+    static constexpr int kCompareEvery = sizeof(Real) == 8 ? CHAOS_COMPARE_EVERY_F64 : CHAOS_COMPARE_EVERY_F32;
 
     Real x, y, cx, cy;      /* kScaled: 2x, 2y, 2cx, 2cy */
     Real sx, sy;            /* the earlier state the orbit is compared with (kDetectCycle) */

@@ -403,12 +403,22 @@ static __device__ void stream_long(const chaos_render_args &a)
     for (;;) {
         CHAOS_LS(if (dry && !tt_dry) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt_dry));)
         CHAOS_LS(ls.before(busy, fin || stall, false, false, dry, it);)
+        CHAOS_LS(const long long ck0 = clock64(); const uint32_t it_before = it;)
         if (busy && !fin && !stall) {
             const uint32_t lim = min(it + nb, max_iter);
             const bool e = o.run(it, lim, false);
             fin = e || it >= max_iter;
             stall = !fin && o.wants_tested();
         }
+        CHAOS_LS({
+            const long long ck1 = clock64();
+            const uint32_t adv = __reduce_max_sync(CHAOS_FULL_MASK, (fin && o.skipped()) ? 0u : it - it_before);
+            if (lane == 0u && a.phase != 0u && adv) {
+                atomicAdd(&a.counters->long_hist[which][3][dry ? 4 : 0], (unsigned long long)(ck1 - ck0));
+                atomicAdd(&a.counters->long_hist[which][3][dry ? 5 : 1], (unsigned long long)adv);
+                atomicAdd(&a.counters->long_hist[which][3][dry ? 6 : 2], 1ull);
+            }
+        })
         CHAOS_LS(ls.after((fin ? it - o.skipped() : it) - ls.it0);)
         const uint32_t running = __ballot_sync(CHAOS_FULL_MASK, busy && !fin && !stall);
         if (running) {
@@ -502,6 +512,7 @@ static __device__ void stream_long(const chaos_render_args &a)
     /* (diagnostics) when the launch's warps started, saw the list dry, and ended: min / max over the warps, as ~t for the minima */
     CHAOS_LS(if (lane == 0u && a.phase != 0u) {
         unsigned long long tt_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt_end));
+        for (unsigned long long bin = 0; bin <= min((tt_end - tt_start) >> 16, 31ull); ++bin) atomicAdd(&a.counters->long_hist[which][0][bin], 1ull);
         unsigned long long *w = &a.counters->lane_stats[3][1][which * 4u];
         atomicMax(w + 0, ~tt_start); if (tt_dry) { atomicMax(w + 1, ~tt_dry); atomicMax(w + 2, tt_dry); } atomicMax(w + 3, tt_end);
     })

@@ -23,7 +23,9 @@ if __name__ == "__main__":
     cu = importlib.import_module("chaos-ultra_b200")
     import bench
     for w in sys.argv[1:] or ["c2"]:
-        wl = bench.WORKLOADS[w]
+        wl = dict(bench.WORKLOADS[w.split("@")[0]])
+        if "@" in w:        # c2@256x144: the workload's view at another size
+            wl["W"], wl["H"] = map(int, w.split("@")[1].split("x"))
         with cu.CudaFractalRendererProvider(kernels_dir=os.environ.get("CHAOS_KERNELS_DIR", KD), device=0) as prov:
             r = prov.getRenderer(wl["fractal"], False)
             r.initializeRendering(wl["W"], wl["H"], output_mode=cu.OUTPUT_DEVICE)
