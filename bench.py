@@ -42,9 +42,10 @@ A, FOV, REUSE, ZOOMING, ZOOM_IN = 1, 4, 8, 16, 32
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel(s), per frame, from one
 # `ncu --set full` capture of the same command (never measured in a bench run); workload -> (bytes, capture)
 NCU_TRAFFIC = {
-    "c2": (int((0.15 + 73.44 + 40.86 + 13.94 + 21.25 + 0.07 + 0.05 + 0.0 + 7.58 + 0.01 + 24.83 + 22.46 + 62.76 + 0.99) * 1e6),
-           "profiles/r02_passes_c2.txt: chaosProbe + chaosLong + chaosFinish of passes A and C + chaosPassB, Double (133 MB of that are the records "
-           "themselves; the rest is the long and finish lists and the export arrays; HBM is 1 % busy)"),
+    "c2": (int((0.17 + 171.61 + 140.50 + 29.68 + 19.51 + 0.05 + 0.06 + 0.0 + 7.59 + 23.50 + 76.16 + 27.01 + 58.58 + 0.27) * 1e6),
+           "profiles/r03_passes_c2.txt: chaosProbe + chaosLong + chaosFinish of passes A and C + chaosPassB, Double (133 MB of that are the records "
+           "themselves; the rest is the long list -- 32 B per surviving orbit, written by the probe and read by the long kernel -- the finish list "
+           "and the export arrays; HBM is 2 % busy)"),
     "c3": (int((127.10 + 85.13 + 132.73 + 6.94) * 1e6), "profiles/r02_fast_frame_c3.txt: chaosReusePassFloat + compose "
            "(part of the 133 MB of records written and of the 33 MB frame stays in the 126 MB L2)"),
 }
