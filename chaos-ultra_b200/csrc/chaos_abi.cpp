@@ -407,6 +407,13 @@ struct chaos_renderer {
     /* resident warps per SM of the escape-loop kernels (0 = what fits).  Fewer warps per scheduler make every orbit
      * advance faster (a trip is a chain of three dependent FP64 instructions) at some cost in pipe utilisation */
     int loop_warps_per_sm = 0;
+    /* A frame that runs as several strands has several long kernels in flight, each a persistent grid sized for the whole
+     * machine.  Asking for a third of an SM's shared memory per CTA (never touched) caps the long-kernel CTAs an SM holds
+     * ACROSS those launches at 3: the fourth CTA's worth of registers and issue slots stays with the other kernels of the
+     * strands' chains (finish, classify, the next probe ...), which the strand that is ahead needs to get on (c2 2.95 ->
+     * 2.85 ms; 2 per SM: 3.03).  CHAOS_LONG_SMEM=bytes, 0 = off.  A single chain gets the uncapped grid. */
+    uint32_t long_smem = 72u * 1024u;
+    int blocks_long_shared[2] = {0, 0};
     /* orbit pool of the independent-orbit passes (chaos_render_args::pool): one per strand, allocated by the first frame */
     CUdeviceptr pool[CHAOS_MAX_STRANDS] = {};
     uint32_t pool_capacity = 0;
@@ -624,6 +631,10 @@ static chaos_status load_module(chaos_renderer *r)
         r->blocks_pass_c[p] = persistent_blocks(r, r->k_pass_c[p], T, 0, r->loop_warps_per_sm);
         r->blocks_probe[p] = persistent_blocks(r, r->k_probe[p], 256);
         r->blocks_long[p] = persistent_blocks(r, r->k_long[p], T, 0, r->loop_warps_per_sm);
+        r->blocks_long_shared[p] = r->blocks_long[p];
+        if (r->long_smem && D->p_cuFuncSetAttribute(r->k_long[p], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)r->long_smem) == CUDA_SUCCESS)
+            r->blocks_long_shared[p] = persistent_blocks(r, r->k_long[p], T, r->long_smem, r->loop_warps_per_sm);
+        else r->long_smem = 0;
         r->blocks_finish[p] = persistent_blocks(r, r->k_finish[p], 256);
     }
     r->blocks_main_f_sync = persistent_blocks(r, r->k_main_f_sync, 256);
@@ -708,6 +719,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (pt && (atoi(pt) == 32 || atoi(pt) == 64 || atoi(pt) == 128 || atoi(pt) == 256)) r->pass_threads = (uint32_t)atoi(pt);
     const char *lw = getenv("CHAOS_LOOP_WARPS_PER_SM");
     if (lw) r->loop_warps_per_sm = std::max(atoi(lw), 0);
+    const char *lsm = getenv("CHAOS_LONG_SMEM");
+    if (lsm) r->long_smem = (uint32_t)std::max(atoi(lsm), 0);
     const char *sc = getenv("CHAOS_SHORTCUTS");   /* 0 = every trip executed and tested, as the reference does */
     if (sc) r->shortcuts = (uint32_t)atoi(sc) & (CHAOS_SHORTCUT_DEFER_TEST | CHAOS_SHORTCUT_RECURRENCE);
     chaos_status st = load_module(r);
@@ -805,10 +818,11 @@ static bool ensure_lists(chaos_renderer *r, size_t entries)
 
 /* engine 2: one probe -> long -> finish chain on stream q; b.phase says which pass it serves */
 static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int threads, unsigned smem, void *arg, CUstream stream);
-static chaos_status launch_stream_chain(chaos_renderer *r, chaos_render_args &b, int p, CUstream q)
+static chaos_status launch_stream_chain(chaos_renderer *r, chaos_render_args &b, int p, CUstream q, bool shared_machine = false)
 {
     chaos_status st = launch(r, r->k_probe[p], r->blocks_probe[p], 256, 0, &b, q);
-    if (st == CHAOS_OK) st = launch(r, r->k_long[p], r->blocks_long[p], (int)r->pass_threads, 0, &b, q);
+    if (st == CHAOS_OK) st = shared_machine && r->long_smem ? launch(r, r->k_long[p], r->blocks_long_shared[p], (int)r->pass_threads, r->long_smem, &b, q)
+                                                            : launch(r, r->k_long[p], r->blocks_long[p], (int)r->pass_threads, 0, &b, q);
     if (st == CHAOS_OK) st = launch(r, r->k_finish[p], r->blocks_finish[p], 256, 0, &b, q);
     return st;
 }
@@ -1510,7 +1524,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     const int tile_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);   /* one warp per tile */
                     b.phase = 1u;
                     if (streams && (r->hot_first & 2u) && r->list_shrink == 1u) b.hot_capacity = b.list_capacity;   /* the two ends cannot meet: the list holds every orbit of pass A */
-                    st = streams ? launch_stream_chain(r, b, p, q) : launch(r, r->k_pass_a[p], r->blocks_pass_a[p], (int)r->pass_threads, 0, &b, q);
+                    st = streams ? launch_stream_chain(r, b, p, q, G > 1u) : launch(r, r->k_pass_a[p], r->blocks_pass_a[p], (int)r->pass_threads, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_classify, tile_grid, 256, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &b, q);
                     b.phase = 2u;
@@ -1541,7 +1555,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     b.phase = 3u;
                     b.hot_capacity = 0u;
                     if (streams && (r->hot_first & 1u)) { b.hot_capacity = b.list_capacity / 4u; b.hot_trips = std::max(b.max_iter / 4u, 64u); }
-                    st = streams ? launch_stream_chain(r, b, p, q) : launch(r, r->k_pass_c[p], r->blocks_pass_c[p], (int)r->pass_threads, 0, &b, q);
+                    st = streams ? launch_stream_chain(r, b, p, q, G > 1u) : launch(r, r->k_pass_c[p], r->blocks_pass_c[p], (int)r->pass_threads, 0, &b, q);
                     const int replay_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);
                     if (st == CHAOS_OK) st = launch(r, r->k_replay, replay_grid, 256, 0, &b, q);
                 }
