@@ -1489,6 +1489,9 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     return fail(CHAOS_ERR_CUDA, "cuMemsetD32Async failed");
             }
             for (uint32_t s = 0; s < G; ++s) ensure_pool(r, s);      /* (a new pool is cleared on r->stream) */
+            /* (chaos_renderer::long_smem) not when the frame is composed into host memory next to passes C and D: that compose moves at
+             * PCIe speed from its first CTA on, and an SM set up for the long kernels' shared memory takes it in late (c2 end to end 3.19 -> 3.51 ms) */
+            const bool capped = G > 1u && !((r->mode == CHAOS_OUTPUT_HOST && !r->rgba_target) || r->host_target);
             if (G > 1u) D->p_cuEventRecord(r->ev[4], r->stream);     /* counters, bitmap and pools are clear */
             uint32_t tile_base = 0;
             a.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
@@ -1524,7 +1527,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     const int tile_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);   /* one warp per tile */
                     b.phase = 1u;
                     if (streams && (r->hot_first & 2u) && r->list_shrink == 1u) b.hot_capacity = b.list_capacity;   /* the two ends cannot meet: the list holds every orbit of pass A */
-                    st = streams ? launch_stream_chain(r, b, p, q, G > 1u) : launch(r, r->k_pass_a[p], r->blocks_pass_a[p], (int)r->pass_threads, 0, &b, q);
+                    st = streams ? launch_stream_chain(r, b, p, q, capped) : launch(r, r->k_pass_a[p], r->blocks_pass_a[p], (int)r->pass_threads, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_classify, tile_grid, 256, 0, &b, q);
                     if (st == CHAOS_OK) st = launch(r, r->k_order, small_grid, 256, 0, &b, q);
                     b.phase = 2u;
@@ -1555,7 +1558,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     b.phase = 3u;
                     b.hot_capacity = 0u;
                     if (streams && (r->hot_first & 1u)) { b.hot_capacity = b.list_capacity / 4u; b.hot_trips = std::max(b.max_iter / 4u, 64u); }
-                    st = streams ? launch_stream_chain(r, b, p, q, G > 1u) : launch(r, r->k_pass_c[p], r->blocks_pass_c[p], (int)r->pass_threads, 0, &b, q);
+                    st = streams ? launch_stream_chain(r, b, p, q, capped) : launch(r, r->k_pass_c[p], r->blocks_pass_c[p], (int)r->pass_threads, 0, &b, q);
                     const int replay_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);
                     if (st == CHAOS_OK) st = launch(r, r->k_replay, replay_grid, 256, 0, &b, q);
                 }
