@@ -414,6 +414,12 @@ struct chaos_renderer {
      * 2.85 ms; 2 per SM: 3.03).  CHAOS_LONG_SMEM=bytes, 0 = off.  A single chain gets the uncapped grid. */
     uint32_t long_smem = 72u * 1024u;
     int blocks_long_shared[2] = {0, 0};
+    /* A frame that is ONE launch (one sample per pixel, or the tile-synchronous kernel) and goes to host memory used to be
+     * rendered, then composed over PCIe: 0.6 ms of a 4K frame's, 5 ms of an 8192^2 frame's end-to-end time with the GPU idle.
+     * It is rendered in host_parts interleaved sets of row bands instead, one launch each, and part k is composed into host
+     * memory (second stream) while part k + 1 is rendered: only the last part's compose is left over.  CHAOS_HOST_PARTS,
+     * 1 = off; a part has at least 60 000 vote tiles. */
+    uint32_t host_parts = 4;
     /* orbit pool of the independent-orbit passes (chaos_render_args::pool): one per strand, allocated by the first frame */
     CUdeviceptr pool[CHAOS_MAX_STRANDS] = {};
     uint32_t pool_capacity = 0;
@@ -637,6 +643,10 @@ static chaos_status load_module(chaos_renderer *r)
         else r->long_smem = 0;
         r->blocks_finish[p] = persistent_blocks(r, r->k_finish[p], 256);
     }
+    /* the one-launch kernels run next to the compose of the part before (chaos_renderer::host_parts), which stages its palette in
+     * shared memory: an SM that holds their CTAs must be set up with room for it (they use none themselves, and nothing of L1) */
+    for (CUfunction fn : {r->k_main_f, r->k_main_d, r->k_main_f_sync, r->k_main_d_sync})
+        D->p_cuFuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 50);
     r->blocks_main_f_sync = persistent_blocks(r, r->k_main_f_sync, 256);
     r->blocks_main_d_sync = persistent_blocks(r, r->k_main_d_sync, 256);
     r->blocks_reuse_f = persistent_blocks(r, r->k_reuse_f, 256);
@@ -719,6 +729,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (pt && (atoi(pt) == 32 || atoi(pt) == 64 || atoi(pt) == 128 || atoi(pt) == 256)) r->pass_threads = (uint32_t)atoi(pt);
     const char *lw = getenv("CHAOS_LOOP_WARPS_PER_SM");
     if (lw) r->loop_warps_per_sm = std::max(atoi(lw), 0);
+    const char *hps = getenv("CHAOS_HOST_PARTS");
+    if (hps) r->host_parts = (uint32_t)std::min(std::max(atoi(hps), 1), CHAOS_MAX_STRANDS);
     const char *lsm = getenv("CHAOS_LONG_SMEM");
     if (lsm) r->long_smem = (uint32_t)std::max(atoi(lsm), 0);
     const char *sc = getenv("CHAOS_SHORTCUTS");   /* 0 = every trip executed and tested, as the reference does */
@@ -1272,11 +1284,13 @@ static chaos_status launch(chaos_renderer *r, CUfunction fn, int blocks, int thr
 static void fill_compose_args(chaos_renderer *r, const chaos_params *m, chaos_compose_args &c);
 
 /* only_tiles: compose just the tiles flagged there (the ones pass D finished after the frame-wide compose had started) */
-static chaos_status launch_compose(chaos_renderer *r, const chaos_params *m, CUstream stream = nullptr, const uint32_t *only_tiles = nullptr)
+static chaos_status launch_compose(chaos_renderer *r, const chaos_params *m, CUstream stream = nullptr, const uint32_t *only_tiles = nullptr,
+                                   uint32_t part_index = 0, uint32_t part_count = 0)
 {
     chaos_compose_args c;
     fill_compose_args(r, m, c);
     c.only_tiles = only_tiles;
+    if (part_count) { c.part_index = part_index; c.part_count = part_count; }      /* (one part of a frame rendered in parts, below) */
     c.tiles_x = (r->width + 7u) / 8u;
     uint64_t quads = (uint64_t)((r->width + 3u) / 4u) * r->height;
     int max_blocks = r->provider->sm_count * 8;
@@ -1421,7 +1435,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters) * CHAOS_MAX_STRANDS, r->stream);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
-    bool early_compose = false, profile_frame = false;
+    bool early_compose = false, profile_frame = false, parts_composed = false;
     if (a.n_tiles) {
         const int p = dbl ? 1 : 0;
         const uint32_t S0 = (uint32_t)std::min(64.0f, roundf(m->max_super_sampling));
@@ -1437,7 +1451,41 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         a.probe_trips = r->probe_trips;
         if (streams && !ensure_lists(r, (size_t)((a.tiles_x * (size_t)a.tile_rows)) * (S0 <= 1u ? 32u : 64u)))
             return fail(CHAOS_ERR_CUDA, "cannot allocate the orbit lists of a %ux%u frame", r->width, r->height);
-        if (sync_kernel) {
+        /* one-launch frames on their way to host memory: in parts, composed as they come (chaos_renderer::host_parts) */
+        const bool to_host = (r->mode == CHAOS_OUTPUT_HOST && !r->rgba_target) || r->host_target;
+        const bool one_launch = sync_kernel || (S0 <= 1u && !streams);
+        uint32_t K = (to_host && one_launch && !(r->steal && peers_open(r))) ? r->host_parts : 1u;
+        K = (uint32_t)std::min<uint64_t>(K, std::max<uint64_t>(a.n_tiles / 60000u, 1u));
+        {
+            const uint32_t bands = (a.tile_rows + a.band_tile_rows - 1u) / a.band_tile_rows;
+            while (K > 1u && (uint64_t)bands < (uint64_t)r->part_count * K * 2u) --K;       /* at least two bands per part */
+        }
+        if (K > 1u) {
+            for (uint32_t k = 0; k < K && st == CHAOS_OK; ++k) {
+                chaos_render_args b = a;
+                b.part_count = r->part_count * K; b.part_index = r->part_index + r->part_count * k;
+                b.n_tiles = owned_tile_rows(b.tile_rows, b.band_tile_rows, b.part_index, b.part_count) * b.tiles_x;
+                b.counters = (chaos_counters *)r->counters + k;
+                if (!b.n_tiles) continue;
+                /* (one CTA per SM fewer than fit: the compose of the part before needs a CTA slot next to this launch's persistent grid) */
+                const int sms = r->provider->sm_count;
+                if (sync_kernel) {
+                    const int blocks = dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync;
+                    st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, blocks >= 2 * sms ? blocks - sms : blocks, 256, 0, &b, r->stream);
+                } else {
+                    b.pool = (unsigned char *)ensure_pool(r, 0);
+                    b.pool_capacity = r->pool_capacity; b.pool_min_lanes = r->pool_min_lanes; b.pool_epoch = (r->pool_epoch += 2u) & 0xffffffu;
+                    const int blocks = dbl ? r->blocks_main_d : r->blocks_main_f;
+                    st = launch(r, dbl ? r->k_main_d : r->k_main_f, blocks >= 2 * sms ? blocks - sms : blocks, 256, 0, &b, r->stream);
+                }
+                D->p_cuEventRecord(r->strand_ev_b[k], r->stream);
+                D->p_cuStreamWaitEvent(r->stream2, r->strand_ev_b[k], 0);
+                if (k == 0u) D->p_cuEventRecord(r->ev[6], r->stream2);
+                if (st == CHAOS_OK) st = launch_compose(r, m, r->stream2, nullptr, b.part_index, b.part_count);
+            }
+            D->p_cuEventRecord(r->ev[7], r->stream2);
+            parts_composed = st == CHAOS_OK;
+        } else if (sync_kernel) {
             st = launch(r, dbl ? r->k_main_d_sync : r->k_main_f_sync, dbl ? r->blocks_main_d_sync : r->blocks_main_f_sync, 256, 0, &a, r->stream);
         } else if (S0 <= 1u && streams) {
             a.long_list = (void *)r->long_list; a.finish_list = (void *)r->finish_list;
@@ -1578,14 +1626,14 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
         if (st != CHAOS_OK) return st;
     }
     D->p_cuEventRecord(r->ev[1], r->stream);
-    if (early_compose) D->p_cuStreamWaitEvent(r->stream, r->ev[7], 0);
+    if (early_compose || parts_composed) D->p_cuStreamWaitEvent(r->stream, r->ev[7], 0);
     D->p_cuEventRecord(r->ev[2], r->stream);
-    st = early_compose ? launch_compose(r, m, nullptr, a.late_tiles) : launch_compose(r, m);
+    if (!parts_composed) st = early_compose ? launch_compose(r, m, nullptr, a.late_tiles) : launch_compose(r, m);
     if (st != CHAOS_OK) return st;
     D->p_cuEventRecord(r->ev[3], r->stream);
     st = finish_frame(r);
     if (st != CHAOS_OK) return st;
-    if (early_compose) {
+    if (early_compose || parts_composed) {
         float early = 0.f;
         D->p_cuEventElapsedTime(&early, r->ev[6], r->ev[7]);
         r->stats.compose_ms += early;

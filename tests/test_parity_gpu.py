@@ -498,3 +498,48 @@ def test_full_lists_change_nothing(cu, provider, case):
         assert out[shrink][1] == out[1][1] and out[shrink][2] == out[1][2]
         assert (out[shrink][3] == out[1][3]).all()
 
+
+
+# ---- one-launch frames on their way to host memory are rendered in parts (chaos_renderer::host_parts), each part composed
+# ---- while the next one is rendered: frame, records and counters must be those of the single launch, for the
+# ---- tile-synchronous kernel and for the lane-refill kernel, whole frames and one rank's bands.
+PARTS_CASES = [
+    dict(name="parts_julia_a8_f64", fractal="julia", W=3840, H=2160, image=cases.seg(0.0, 0.0, 4.0, 3840, 2160), maxIter=900,
+         maxSS=8.0, flags=cases.A, double=True, julia_c=(-0.4, 0.6), amplifier=10),
+    dict(name="parts_mandel_n1_f64", fractal="mandelbrot", W=3840, H=2161, image=cases.seg(-0.5, 0.0, 2.0, 3840, 2161), maxIter=700,
+         maxSS=1.0, flags=0, double=True, julia_c=(0.0, 0.0), amplifier=10),
+    dict(name="parts_mandel_n1_f32", fractal="mandelbrot", W=4093, H=2051, image=cases.seg(-0.7, 0.2, 1.0, 4093, 2051), maxIter=300,
+         maxSS=1.0, flags=0, double=False, julia_c=(0.0, 0.0), amplifier=10),
+]
+
+
+@pytest.mark.parametrize("case", PARTS_CASES, ids=_ids(PARTS_CASES))
+def test_one_launch_frames_in_parts_change_nothing(cu, provider, case):
+    out = {}
+    for parts, part in ((1, None), (2, None), (4, None), (3, (1, 2))):
+        os.environ["CHAOS_HOST_PARTS"] = str(parts)
+        try:
+            provider.getRenderer("test", False)   # drop the active renderer so the knob is re-read
+            r = helpers.open_renderer(cu, provider, case, mode=cu.OUTPUT_HOST)
+            if part:
+                r.setPartition(part[0], part[1], 32)
+            r.renderQuality(helpers.model_for(cu, case))
+            st = r.stats()
+            out[(parts, part)] = (r.downloadRecords(), st.pixel_iterations, st.samples, r.outputRGBA().copy(), st.kernel_launches)
+            if part:
+                r.setPartition(0, 1, 32)
+        finally:
+            os.environ.pop("CHAOS_HOST_PARTS", None)
+    whole = out[(1, None)]
+    for key in ((2, None), (4, None)):
+        helpers.assert_records_equal(out[key][0], whole[0], "%s in %d parts" % (case["name"], key[0]))
+        assert out[key][1] == whole[1] and out[key][2] == whole[2]
+        assert (out[key][3] == whole[3]).all()
+        assert out[key][4] == 2 * key[0]          # a render and a compose launch per part
+    # one rank of two, its bands in three parts: its rows equal the whole frame's
+    rows = np.zeros(case["H"], dtype=bool)
+    for b in range(1, (case["H"] + 31) // 32, 2):
+        rows[b * 32:(b + 1) * 32] = True
+    rank = out[(3, (1, 2))]
+    helpers.assert_records_equal(rank[0][rows], whole[0][rows], case["name"] + " rank 1 of 2 in 3 parts")
+    assert (rank[3][rows] == whole[3][rows]).all()

@@ -10,11 +10,13 @@ cu = importlib.import_module("chaos-ultra_b200")
 sizes = [(int(sys.argv[i]), int(sys.argv[i + 1])) for i in range(1, len(sys.argv) - 1, 2)] or [(256, 144), (640, 360)]
 with cu.CudaFractalRendererProvider() as prov:
     for W, H in sizes:
-        wl = dict(bench.WORKLOADS["c2"], W=W, H=H)
+        wl = dict(bench.WORKLOADS[os.environ.get("TINY_WL", "c2")], W=W, H=H)
         if "TINY_CENTER" in os.environ:      # (a view without pixels on the axes: x,y)
             wl["center"] = tuple(float(v) for v in os.environ["TINY_CENTER"].split(","))
-        r = prov.getRenderer("mandelbrot", True)
-        r.initializeRendering(W, H, None, cu.OUTPUT_DEVICE)
+        r = prov.getRenderer(wl["fractal"], True)
+        if wl["fractal"] == "julia":
+            r.setFractalCustomParams("%r;%r" % tuple(wl["julia_c"]))
+        r.initializeRendering(W, H, None, cu.OUTPUT_HOST if os.environ.get("TINY_HOST") else cu.OUTPUT_DEVICE)
         if "TINY_PART" in os.environ:        # (what one rank of an N-GPU frame does: rank:world)
             pi, pn = map(int, os.environ["TINY_PART"].split(":"))
             r.setPartition(pi, pn, 32)
