@@ -420,6 +420,7 @@ struct chaos_renderer {
      * memory (second stream) while part k + 1 is rendered: only the last part's compose is left over.  CHAOS_HOST_PARTS,
      * 1 = off; a part has at least 60 000 vote tiles. */
     uint32_t host_parts = 4;
+    uint32_t late_by_strand = 1;   /* the exported tiles of a strand are composed when ITS pass D is over (CHAOS_LATE_BY_STRAND=0: all of them after the render) */
     /* orbit pool of the independent-orbit passes (chaos_render_args::pool): one per strand, allocated by the first frame */
     CUdeviceptr pool[CHAOS_MAX_STRANDS] = {};
     uint32_t pool_capacity = 0;
@@ -729,6 +730,8 @@ extern "C" chaos_status chaos_open(chaos_provider *p, const char *fractal_name, 
     if (pt && (atoi(pt) == 32 || atoi(pt) == 64 || atoi(pt) == 128 || atoi(pt) == 256)) r->pass_threads = (uint32_t)atoi(pt);
     const char *lw = getenv("CHAOS_LOOP_WARPS_PER_SM");
     if (lw) r->loop_warps_per_sm = std::max(atoi(lw), 0);
+    const char *lbs = getenv("CHAOS_LATE_BY_STRAND");
+    if (lbs) r->late_by_strand = atoi(lbs) ? 1u : 0u;
     const char *hps = getenv("CHAOS_HOST_PARTS");
     if (hps) r->host_parts = (uint32_t)std::min(std::max(atoi(hps), 1), CHAOS_MAX_STRANDS);
     const char *lsm = getenv("CHAOS_LONG_SMEM");
@@ -1435,7 +1438,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     CUresult e = D->p_cuMemsetD8Async(r->counters, 0, sizeof(chaos_counters) * CHAOS_MAX_STRANDS, r->stream);
     if (e != CUDA_SUCCESS) return fail(CHAOS_ERR_CUDA, "cuMemsetD8Async failed: %s", cu_err_name(e));
     D->p_cuEventRecord(r->ev[0], r->stream);
-    bool early_compose = false, profile_frame = false, parts_composed = false;
+    bool early_compose = false, profile_frame = false, parts_composed = false, late_composed = false;
     if (a.n_tiles) {
         const int p = dbl ? 1 : 0;
         const uint32_t S0 = (uint32_t)std::min(64.0f, roundf(m->max_super_sampling));
@@ -1610,7 +1613,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                     const int replay_grid = (int)std::min<uint64_t>((b.n_tiles + 7u) / 8u, (uint64_t)r->provider->sm_count * 8u);
                     if (st == CHAOS_OK) st = launch(r, r->k_replay, replay_grid, 256, 0, &b, q);
                 }
-                if (s) D->p_cuEventRecord(r->strand_ev_done[s], q);
+                if (s || (G > 1u && a.late_tiles)) D->p_cuEventRecord(r->strand_ev_done[s], q);
             }
             if (a.late_tiles && st == CHAOS_OK) {
                 /* every tile pass B did not export is final: stream the frame out once every strand's pass B is over,
@@ -1618,6 +1621,14 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
                 for (uint32_t s = 0; s < G; ++s) D->p_cuStreamWaitEvent(r->stream2, r->strand_ev_b[s], 0);
                 D->p_cuEventRecord(r->ev[6], r->stream2);
                 st = launch_compose(r, m, r->stream2);
+                /* ... and the exported tiles of a strand once ITS pass D is over, behind that compose on the same stream (it
+                 * coloured them from records that were not final): the strand that is ahead does not wait for the other */
+                if (G > 1u && r->late_by_strand)
+                    for (uint32_t s = 0; s < G && st == CHAOS_OK; ++s) {
+                        D->p_cuStreamWaitEvent(r->stream2, r->strand_ev_done[s], 0);
+                        st = launch_compose(r, m, r->stream2, a.late_tiles, r->part_index + r->part_count * s, r->part_count * G);
+                    }
+                late_composed = G > 1u && r->late_by_strand && st == CHAOS_OK;
                 D->p_cuEventRecord(r->ev[7], r->stream2);
                 early_compose = st == CHAOS_OK;
             }
@@ -1628,7 +1639,7 @@ static chaos_status render_quality_locked(chaos_renderer *r, chaos_params *m)
     D->p_cuEventRecord(r->ev[1], r->stream);
     if (early_compose || parts_composed) D->p_cuStreamWaitEvent(r->stream, r->ev[7], 0);
     D->p_cuEventRecord(r->ev[2], r->stream);
-    if (!parts_composed) st = early_compose ? launch_compose(r, m, nullptr, a.late_tiles) : launch_compose(r, m);
+    if (!parts_composed && !late_composed) st = early_compose ? launch_compose(r, m, nullptr, a.late_tiles) : launch_compose(r, m);
     if (st != CHAOS_OK) return st;
     D->p_cuEventRecord(r->ev[3], r->stream);
     st = finish_frame(r);
