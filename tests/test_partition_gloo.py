@@ -101,3 +101,21 @@ def test_gather_over_gloo(world, H, W, band):
     foreign = sum((r1 - r0) * W * 4 for rank in range(1, world) for r0, r1 in part.rows_owned(rank, world, H, band))
     assert res[0][2] == foreign                      # rank 0 received every foreign band exactly once
     assert sum(r[2] for r in res[1:]) == foreign
+
+
+def test_a_ranks_bands_subdivide_into_strands_and_parts():
+    """chaos_abi.cpp runs a rank's frame as G strands / K parts: sub-partition k of rank q is partition q + world * k of
+    world * K.  Those must be exactly rank q's bands, each once (the kernels and the compose filter only know
+    `band % part_count == part_index`)."""
+    part = importlib.import_module("chaos-ultra_b200.partition")
+    for world in (1, 2, 3, 8):
+        for sub in (2, 3, 4, 8):
+            for height, band_rows in ((2160, 32), (2161, 32), (8192, 64), (130, 4)):
+                for rank in range(world):
+                    mine = part.rows_owned(rank, world, height, band_rows)
+                    pieces = []
+                    for k in range(sub):
+                        pieces += part.rows_owned(rank + world * k, world * sub, height, band_rows)
+                    assert sorted(pieces) == sorted(mine)
+                    assert sum(part.tiles_owned(rank + world * k, world * sub, 3840, height, band_rows) for k in range(sub)) == \
+                        part.tiles_owned(rank, world, 3840, height, band_rows)
