@@ -15,7 +15,7 @@ frames = [
     dict(name="newton", fractal="newton_generic", W=120, H=72, image=cases.seg(0.0, 0.0, 4.0, 120, 72), maxIter=100, maxSS=3.0, flags=A, double=True, julia_c=(0, 0), amplifier=10, params=cases.N3),
 ]
 with cu.CudaFractalRendererProvider() as prov:
-    for eng in ("3", "2", "1"):
+    for eng in os.environ.get("SANITIZE_ENGINES", "3,2,1").split(","):
         os.environ["CHAOS_ENGINE"] = eng
         prov.getRenderer("test", False)
         for c in frames:
