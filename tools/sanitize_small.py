@@ -23,6 +23,12 @@ with cu.CudaFractalRendererProvider() as prov:
             r.renderQuality(helpers.model_for(cu, c))
             print(eng, c["name"], r.stats().pixel_iterations, flush=True)
     os.environ.pop("CHAOS_ENGINE")
+    if os.environ.get("SANITIZE_PARTS"):     # one-launch frames on their way to host memory, rendered in parts (4K: a part needs 60 000 tiles)
+        for c in (dict(name="parts_sync", fractal="julia", W=3840, H=2160, image=cases.seg(0.0, 0.0, 4.0, 3840, 2160), maxIter=300, maxSS=4.0, flags=A, double=True, julia_c=(-0.4, 0.6), amplifier=10),
+                  dict(name="parts_one_sample", fractal="mandelbrot", W=3840, H=2160, image=cases.seg(-0.5, 0.0, 2.0, 3840, 2160), maxIter=200, maxSS=1.0, flags=0, double=False, julia_c=(0, 0), amplifier=10)):
+            r = helpers.open_renderer(cu, prov, c, mode=cu.OUTPUT_HOST)
+            r.renderQuality(helpers.model_for(cu, c))
+            print("parts", c["name"], r.stats().pixel_iterations, r.stats().kernel_launches, flush=True)
     case = cases.ADV_CASES[2]
     img0, img1 = cases.adv_segments(case)
     r = helpers.open_renderer(cu, prov, case)
